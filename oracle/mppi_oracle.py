@@ -1,0 +1,282 @@
+"""CPU oracle for the MPPI rollout hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A float64 torch-on-CPU restatement of what one `mpc.command(state)` computes in the reference, working from a
+`tampc_b200.spec.RolloutSpec` (plain arrays) instead of live controller objects so that it can travel to the
+GPU box, where /root/reference does not exist.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.
+
+torch (CPU, float64) rather than numpy because the reference itself is torch float64: the same ATen kernels
+give the closest arithmetic, and bench.py's CPU baseline then times the same op mix the reference runs.
+
+Pinned (tests/test_oracle_vs_reference.py, tests/golden/*.npz): against the reference's UNMODIFIED in-tree
+classes run over oracle/shim (ExperimentalMPPI, OnlineMPC._apply_dynamics, HybridDynamicsModel,
+NetworkModelWrapper, InvariantTransformer/RexExtract, cost.py, env static fns) on the committed checkpoints.
+Upstream-unpinned: the pytorch_mppi softmax update and the scaler fit live in libraries that are not under
+/root/reference (see oracle/shim/README.md) — "parity unpinned" for those two.
+
+Each function cites the reference lines it follows (paths relative to /root/reference).
+"""
+import math
+
+import numpy as np
+import torch
+
+from tampc_b200 import spec as S
+
+DT = torch.float64
+
+
+def _t(a):
+    return torch.as_tensor(np.asarray(a), dtype=DT)
+
+
+def _leaky(x, slope):
+    return torch.nn.functional.leaky_relu(x, negative_slope=slope)
+
+
+def mlp_forward(m: S.MLPSpec, x):
+    """make_sequential_network: Linear, act, ..., Linear (model.py:72-74 user.sample)."""
+    n = len(m.weights)
+    for i in range(n):
+        x = torch.nn.functional.linear(x, _t(m.weights[i]), _t(m.biases[i]))
+        if i + 1 < n:
+            x = _leaky(x, m.slope)
+    return x
+
+
+def angle_normalize(a):
+    """arm_pytorch_utilities.math_utils.angle_normalize: ((a+pi) mod 2pi) - pi (push_main.py:192)."""
+    return torch.remainder(a + math.pi, 2 * math.pi) - math.pi
+
+
+def compare_to_goal(c: S.CostSpec, X, goal):
+    """env.state_difference: x - goal with single-wrap angular dims (block_push.py:954-960, peg_in_hole.py:91-97,
+    pendulum.py:66-71)."""
+    d = X - goal
+    for k in c.ang_dims:
+        col = d[:, k].clone()
+        col[col > math.pi] -= 2 * math.pi
+        col[col < -math.pi] += 2 * math.pi
+        d[:, k] = col
+    return d
+
+
+def state_dist(c: S.CostSpec, diff):
+    """env.state_distance as a weighted 2-norm (block_push.py:663-666 r_g-scaled yaw; peg_in_hole.py:103-105)."""
+    return (diff * _t(c.dist_scale)).norm(dim=1)
+
+
+def u_similarity(c: S.CostSpec, U, goal_u):
+    """env.control_similarity: cosine similarity on a dim subset, clamped to [0,1] (block_push.py:980-986,
+    peg_in_hole.py:117-121, cost.py:69-70)."""
+    dims = list(c.usim_dims)
+    return torch.cosine_similarity(U[:, dims], goal_u.view(1, -1)[:, dims], dim=-1).clamp(0, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# dynamics
+
+def predict(d: S.DynamicsSpec, x, u):
+    """NetworkModelWrapper.predict on cat(x,u) -> next state (model.py:147-170,131-133,300-301), with the
+    preprocessor chain of util.py:408-411 and RexExtract (invariant.py:628-640,792-795,926-931)."""
+    if d.kind == S.DYN_PENDULUM:
+        # scripts/pendulum.py:223-241 true_dynamics
+        g, m, l, dt, umax, thdmax = d.pendulum
+        th, thdot = x[:, 0:1], x[:, 1:2]
+        uc = torch.clamp(u, -umax, umax)
+        newthdot = thdot + (-3 * g / (2 * l) * torch.sin(th + np.pi) + 3. / (m * l ** 2) * uc) * dt
+        newth = th + newthdot * dt
+        newthdot = torch.clamp(newthdot, -thdmax, thdmax)
+        return torch.cat((newth, newthdot), dim=1)
+    xu = torch.cat((x, u), dim=1)
+    if d.kind == S.DYN_MLP:
+        # PytorchTransformer(RobustMinMaxScaler) on both sides (util.py:422-423)
+        z = xu * _t(d.aff_in.scale) + _t(d.aff_in.offset)
+        y = mlp_forward(d.net, z)
+        dx = (y - _t(d.aff_out.offset)) / _t(d.aff_out.scale)
+        return x + dx
+    # DYN_REX: Compose[ y-scaler, InvariantTransformer(RexExtract), z/v scaler ]
+    z = mlp_forward(d.encoder, xu)  # xu_to_z, invariant.py:792-795
+    z = z * _t(d.aff_in.scale) + _t(d.aff_in.offset)  # stage 3 transform_x
+    v = mlp_forward(d.net, z)  # latent dynamics, model.py:300-301
+    v = (v - _t(d.aff_out.offset)) / _t(d.aff_out.scale)  # stage 3 invert_transform
+    e = torch.nn.functional.linear(x, _t(d.ext_w), _t(d.ext_b))  # x_extractor, invariant.py:885
+    C = mlp_forward(d.decoder, e).view(-1, d.nx, d.nv)  # get_dx, invariant.py:926-931
+    dxs = (C @ v.unsqueeze(2)).squeeze(2)  # linalg.batch_batch_product
+    dx = (dxs - _t(d.aff_y.offset)) / _t(d.aff_y.scale)  # stage 1 invert_transform
+    return x + dx  # advance_pred_all_diff, model.py:131-133
+
+
+def apply_dynamics(d: S.DynamicsSpec, state, u):
+    """OnlineMPC._apply_dynamics (online_controller.py:60-79) with AlwaysSelectNominal gating.
+
+    Returns (next_state, u_seen_by_cost): rows whose ||state|| > 1e5 have state AND action zeroed in place in the
+    reference (through views), come back as zeros, and the running cost of that step sees u = 0."""
+    state = state.clone()
+    u = u.clone()
+    if d.bad_state_norm is not None:
+        bad = state.norm(dim=1) > d.bad_state_norm
+        state[bad] = 0
+        u[bad] = 0
+    else:
+        bad = None
+    nxt = predict(d, state, u)
+    for k in d.wrap_dims:  # constrain_state (push_main.py:190-193)
+        nxt[:, k] = angle_normalize(nxt[:, k])
+    if bad is not None:
+        nxt[bad] = state[bad]  # == 0
+    return nxt, u
+
+
+# ------------------------------------------------------------------------------------------------
+# cost
+
+def qr_cost(c: S.CostSpec, X, U=None, terminal=False):
+    """cost.qr_cost / CostQROnlineTorch (cost.py:11-36)."""
+    d = compare_to_goal(c, X, _t(c.goal).view(1, -1))
+    cost = torch.einsum('ij,ij->i', d @ _t(c.Q), d)
+    if U is not None and not terminal:
+        cost = cost + torch.einsum('ij,ij->i', U @ _t(c.R), U)
+    return cost
+
+
+def trap_cost(c: S.CostSpec, X, U=None, terminal=False):
+    """TrapSetCost (cost.py:154-189) with MPC._trap_cost_reduce (controller.py:245-246)."""
+    total = torch.zeros(X.shape[0], dtype=DT)
+    if len(c.trap_x) == 0:
+        return total
+    costs = []
+    for gx, gu in zip(c.trap_x, c.trap_u):
+        c_x = compare_to_goal(c, X, _t(gx).view(1, -1))
+        c_x = state_dist(c, c_x).square()
+        c_x = torch.clamp(1 / c_x, 0, S.TRAP_MAX_COST)
+        if terminal:
+            c_u = 0
+        elif U is None:
+            c_u = 1
+        else:
+            c_u = u_similarity(c, U, _t(gu))
+        costs.append(c_x * c_u)
+    return torch.stack(costs, dim=0).sum(dim=0) * c.trap_weight
+
+
+def recovery_cost(c: S.CostSpec, X):
+    """GoalSetCost with min_cost inside ComposeCost(weights) (cost.py:114-147,65-66,213-235;
+    online_controller.py:370-396)."""
+    total = torch.zeros(X.shape[0], dtype=DT)
+    for G, w in zip(c.goal_sets, c.set_weights):
+        per_goal = []
+        for g in G:
+            diff = compare_to_goal(c, X, _t(g).view(1, -1))
+            per_goal.append(state_dist(c, diff).square() * c.recovery_scale)
+        total = total + torch.stack(per_goal, dim=0).min(dim=0).values * w
+    return total
+
+
+def running_cost(c: S.CostSpec, X, U):
+    """MPC._running_cost -> ComposeCost([goal_cost, trap_cost]) (controller.py:227,248-249; cost.py:213-235)
+    or OnlineMPPI._recovery_running_cost (online_controller.py:188-189)."""
+    if c.kind == S.COST_RECOVERY:
+        return recovery_cost(c, X)
+    cost = qr_cost(c, X, U)
+    if c.use_trap_cost:
+        cost = cost + trap_cost(c, X, U)
+    return cost
+
+
+def terminal_cost(c: S.CostSpec, X_last):
+    """MPC._terminal_cost = multiplier * cost(x_T, terminal=True) (controller.py:251-259); None -> skipped
+    (controller.py:376)."""
+    if c.kind == S.COST_RECOVERY or c.terminal_multiplier is None:
+        return torch.zeros(X_last.shape[0], dtype=DT)
+    cost = qr_cost(c, X_last, None, terminal=True)
+    if c.use_trap_cost:
+        cost = cost + trap_cost(c, X_last, None, terminal=True)
+    return c.terminal_multiplier * cost
+
+
+# ------------------------------------------------------------------------------------------------
+# MPPI
+
+def rollout_costs(spec: S.RolloutSpec, state, perturbed_actions, return_states=False):
+    """ExperimentalMPPI._compute_rollout_costs (controller.py:340-381) for a deterministic model: all M replicas
+    are identical, so mean over M = one rollout and the variance term is 0."""
+    K, T, nu = perturbed_actions.shape
+    x = _t(state).view(1, -1).repeat(K, 1)
+    total = torch.zeros(K, dtype=DT)
+    states = []
+    for t in range(T):
+        x, u_seen = apply_dynamics(spec.dynamics, x, perturbed_actions[:, t])
+        total = total + running_cost(spec.cost, x, u_seen)
+        if return_states:
+            states.append(x)
+    total = total + terminal_cost(spec.cost, x)
+    if return_states:
+        return total, torch.stack(states, dim=1)
+    return total
+
+
+def perturb(spec: S.RolloutSpec, U, noise):
+    """controller.py:388-395: perturbed = clamp(U + noise); post-clamp noise; lambda * noise @ Sigma^-1."""
+    s = spec.sampler
+    perturbed = U.view(1, *U.shape) + noise
+    if s.sample_null_action:
+        perturbed[s.K - 1] = 0
+    if s.u_min is not None:
+        perturbed = torch.max(torch.min(perturbed, _t(s.u_max)), _t(s.u_min))
+    noise_post = perturbed - U
+    action_cost = s.lambda_ * noise_post @ _t(s.noise_sigma_inv)
+    return perturbed, noise_post, action_cost
+
+
+def total_cost(spec: S.RolloutSpec, state, U, noise):
+    """ExperimentalMPPI._compute_total_cost_batch (controller.py:383-402) with the noise injected."""
+    perturbed, noise_post, action_cost = perturb(spec, U, noise)
+    cost = rollout_costs(spec, state, perturbed)
+    cost = cost + torch.sum(perturbed * action_cost, dim=(1, 2))  # NB perturbed_action, not U (controller.py:400)
+    return cost, perturbed, noise_post
+
+
+def shift_nominal(spec: S.RolloutSpec, U):
+    """MPPI.command: U = roll(U,-1); U[-1] = u_init (pytorch_mppi)."""
+    U = torch.roll(U, -1, dims=0)
+    U[-1] = _t(spec.sampler.u_init)
+    return U
+
+
+def command(spec: S.RolloutSpec, state, U, noise):
+    """One MPPI.command(state): shift, total cost, beta/eta/omega, U update; returns a dict.
+    `U` is the nominal sequence BEFORE the shift; `noise` is the (K,T,nu) draw N(mu, Sigma)."""
+    U = shift_nominal(spec, _t(U).clone())
+    noise = _t(noise)
+    cost, perturbed, noise_post = total_cost(spec, state, U, noise)
+    beta = torch.min(cost)
+    w = torch.exp(-(1.0 / spec.sampler.lambda_) * (cost - beta))
+    eta = torch.sum(w)
+    omega = (1. / eta) * w
+    U_new = U.clone()
+    for t in range(U.shape[0]):
+        U_new[t] = U_new[t] + torch.sum(omega.view(-1, 1) * noise_post[:, t], dim=0)
+    return {'action': U_new[0].clone(), 'U': U_new, 'cost_total': cost, 'omega': omega, 'beta': beta, 'eta': eta,
+            'argmin': int(torch.argmin(cost)), 'perturbed_action': perturbed, 'noise': noise_post}
+
+
+def get_rollouts(spec: S.RolloutSpec, state, U):
+    """MPPI.get_rollouts(state)[0]: states after applying the current nominal U (controller.py:434-435)."""
+    x = _t(state).view(1, -1)
+    out = []
+    for t in range(U.shape[0]):
+        x, _ = apply_dynamics(spec.dynamics, x, _t(U[t]).view(1, -1))
+        out.append(x[0])
+    return torch.stack(out, dim=0)
+
+
+def sample_noise(spec: S.RolloutSpec, seed, K=None, T=None):
+    """Injected-noise convention of the parity tests: noise = mu + eps @ L^T,
+    eps ~ torch.randn(K,T,nu; seed) in float64."""
+    s = spec.sampler
+    K = s.K if K is None else K
+    T = s.T if T is None else T
+    g = torch.Generator().manual_seed(seed)
+    eps = torch.randn(K, T, s.nu, dtype=DT, generator=g)
+    return _t(s.noise_mu) + eps @ _t(s.noise_chol).T
