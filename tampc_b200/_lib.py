@@ -1,0 +1,268 @@
+"""ctypes binding of libtampc_mppi.so (include/tampc_mppi.h).  Structures mirror the header field by field.
+
+The library is the product's compute path; if it is missing or cannot be loaded this module raises — there is
+no Python / CPU fallback (BASELINE.json north_star)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import spec as S
+
+MAX_NX, MAX_NU, MAX_TRAPS, MAX_GOAL_SETS, MAX_SET_GOALS, MAX_LAYERS, MAX_HORIZON = 8, 4, 16, 2, 8, 4, 128
+ABI_VERSION = 1
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
+PREC_F64, PREC_MIXED, PREC_F32 = 0, 1, 2
+PRECISIONS = {'f64': PREC_F64, 'mixed': PREC_MIXED, 'f32': PREC_F32}
+NOISE_PHILOX, NOISE_INJECTED, NOISE_ACTIONS = 0, 1, 2
+Q_COST_TOTAL, Q_PERTURBED, Q_NOMINAL, Q_OMEGA, Q_STATS, Q_STATES = 0, 1, 2, 3, 4, 5
+
+EXPORTS = [
+    'tampc_mppi_last_error', 'tampc_mppi_abi_version', 'tampc_mppi_create', 'tampc_mppi_destroy',
+    'tampc_mppi_set_model', 'tampc_mppi_set_cost', 'tampc_mppi_set_nominal', 'tampc_mppi_get_nominal',
+    'tampc_mppi_command', 'tampc_mppi_command_begin', 'tampc_mppi_command_finish', 'tampc_mppi_rollout_costs',
+    'tampc_mppi_get_rollouts', 'tampc_mppi_query', 'tampc_mppi_device_costs', 'tampc_mppi_synchronize',
+    'tampc_mppi_command_resident', 'tampc_mppi_set_state_resident',
+]
+
+
+class MlpDesc(C.Structure):
+    _fields_ = [('n_layers', C.c_int32), ('dims', C.c_int32 * (MAX_LAYERS + 1)), ('w_off', C.c_int32 * MAX_LAYERS),
+                ('b_off', C.c_int32 * MAX_LAYERS)]
+
+
+class AffineDesc(C.Structure):
+    _fields_ = [('scale_off', C.c_int32), ('offset_off', C.c_int32)]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('nx', C.c_int32), ('nu', C.c_int32), ('nv', C.c_int32),
+                ('leaky_slope', C.c_double), ('net', MlpDesc), ('encoder', MlpDesc), ('decoder', MlpDesc),
+                ('ext_w_off', C.c_int32), ('ext_b_off', C.c_int32), ('ne', C.c_int32),
+                ('aff_in', AffineDesc), ('aff_out', AffineDesc), ('aff_y', AffineDesc),
+                ('wrap_mask', C.c_uint32), ('has_bad_state_guard', C.c_int32), ('bad_state_norm', C.c_double),
+                ('pendulum', C.c_double * 6)]
+
+
+class CostDesc(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('nx', C.c_int32), ('nu', C.c_int32), ('ang_mask', C.c_uint32),
+                ('dist_scale', C.c_double * MAX_NX), ('usim_mask', C.c_uint32),
+                ('Q', C.c_double * (MAX_NX * MAX_NX)), ('R', C.c_double * (MAX_NU * MAX_NU)),
+                ('goal', C.c_double * MAX_NX), ('use_trap_cost', C.c_int32), ('n_traps', C.c_int32),
+                ('trap_x', (C.c_double * MAX_NX) * MAX_TRAPS), ('trap_u', (C.c_double * MAX_NU) * MAX_TRAPS),
+                ('trap_weight', C.c_double), ('has_terminal', C.c_int32), ('terminal_multiplier', C.c_double),
+                ('n_sets', C.c_int32), ('set_size', C.c_int32 * MAX_GOAL_SETS),
+                ('set_goals', ((C.c_double * MAX_NX) * MAX_SET_GOALS) * MAX_GOAL_SETS),
+                ('set_weight', C.c_double * MAX_GOAL_SETS), ('recovery_scale', C.c_double)]
+
+
+class MppiConfig(C.Structure):
+    _fields_ = [('abi_version', C.c_int32), ('device', C.c_int32), ('nx', C.c_int32), ('nu', C.c_int32),
+                ('num_samples', C.c_int32), ('sample_offset', C.c_int32), ('num_local', C.c_int32),
+                ('max_horizon', C.c_int32), ('precision', C.c_int32), ('lambda_', C.c_double),
+                ('noise_mu', C.c_double * MAX_NU), ('noise_sigma', C.c_double * (MAX_NU * MAX_NU)),
+                ('has_bounds', C.c_int32), ('u_min', C.c_double * MAX_NU), ('u_max', C.c_double * MAX_NU),
+                ('u_init', C.c_double * MAX_NU), ('sample_null_action', C.c_int32), ('seed', C.c_uint64),
+                ('stream', C.c_void_p)]
+
+
+class Partial(C.Structure):
+    _fields_ = [('beta', C.c_double), ('eta', C.c_double), ('argmin', C.c_int64), ('count', C.c_int64),
+                ('wsum', C.c_double * (MAX_HORIZON * MAX_NU))]
+
+
+PARTIAL_DOUBLES = C.sizeof(Partial) // 8
+
+
+def lib_path():
+    return os.environ.get('TAMPC_MPPI_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc',
+                                                              'libtampc_mppi.so')
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library and declare every prototype of include/tampc_mppi.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError("libtampc_mppi.so not found at {}; build it with `python -m tampc_b200.build` "
+                           "(there is no CPU fallback)".format(path))
+    lib = C.CDLL(path)
+    dp, vp, i32 = C.POINTER(C.c_double), C.c_void_p, C.c_int32
+    lib.tampc_mppi_last_error.restype = C.c_char_p
+    lib.tampc_mppi_last_error.argtypes = [vp]
+    lib.tampc_mppi_abi_version.restype = C.c_int
+    lib.tampc_mppi_abi_version.argtypes = []
+    lib.tampc_mppi_create.argtypes = [C.POINTER(MppiConfig), C.POINTER(vp)]
+    lib.tampc_mppi_destroy.restype = None
+    lib.tampc_mppi_destroy.argtypes = [vp]
+    lib.tampc_mppi_set_model.argtypes = [vp, C.POINTER(ModelDesc), dp, C.c_size_t]
+    lib.tampc_mppi_set_cost.argtypes = [vp, C.POINTER(CostDesc)]
+    lib.tampc_mppi_set_nominal.argtypes = [vp, dp, i32]
+    lib.tampc_mppi_get_nominal.argtypes = [vp, dp]
+    lib.tampc_mppi_command.argtypes = [vp, dp, i32, dp, dp]
+    lib.tampc_mppi_command_begin.argtypes = [vp, dp, i32, dp, i32, vp]
+    lib.tampc_mppi_command_finish.argtypes = [vp, vp, i32, dp]
+    lib.tampc_mppi_rollout_costs.argtypes = [vp, dp, dp, i32, dp, dp]
+    lib.tampc_mppi_get_rollouts.argtypes = [vp, dp, dp]
+    lib.tampc_mppi_query.argtypes = [vp, i32, dp, C.c_size_t]
+    lib.tampc_mppi_device_costs.argtypes = [vp, C.POINTER(vp)]
+    lib.tampc_mppi_synchronize.argtypes = [vp]
+    lib.tampc_mppi_command_resident.argtypes = [vp, i32]
+    lib.tampc_mppi_set_state_resident.argtypes = [vp, dp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ('tampc_mppi_last_error', 'tampc_mppi_destroy'):
+            fn.restype = C.c_int
+    if lib.tampc_mppi_abi_version() != ABI_VERSION:
+        raise RuntimeError("libtampc_mppi.so ABI {} != binding ABI {}".format(lib.tampc_mppi_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def dptr(a):
+    """float64 C-contiguous numpy array -> double*."""
+    assert a.dtype == np.float64 and a.flags['C_CONTIGUOUS']
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+# ------------------------------------------------------------------------------------------------
+# spec -> descriptors
+
+def _mask(dims):
+    m = 0
+    for d in dims:
+        m |= 1 << int(d)
+    return m
+
+
+class _ParamBuilder:
+    def __init__(self):
+        self.chunks = []
+        self.n = 0
+
+    def add(self, a):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64)).reshape(-1)
+        off = self.n
+        self.chunks.append(a)
+        self.n += a.size
+        return off
+
+    def mlp(self, m: S.MLPSpec):
+        d = MlpDesc()
+        d.n_layers = len(m.weights)
+        for i, v in enumerate(m.dims):
+            d.dims[i] = v
+        for i, (w, b) in enumerate(zip(m.weights, m.biases)):
+            d.w_off[i] = self.add(w)
+            d.b_off[i] = self.add(b)
+        return d
+
+    def affine(self, a):
+        d = AffineDesc()
+        if a is None:
+            d.scale_off = d.offset_off = -1
+        else:
+            d.scale_off = self.add(a.scale)
+            d.offset_off = self.add(a.offset)
+        return d
+
+    def array(self):
+        return np.concatenate(self.chunks) if self.chunks else np.zeros(0)
+
+
+def model_desc(dyn: S.DynamicsSpec):
+    """DynamicsSpec -> (tampc_model_desc, float64 params array)."""
+    pb = _ParamBuilder()
+    d = ModelDesc()
+    d.kind, d.nx, d.nu, d.nv = dyn.kind, dyn.nx, dyn.nu, dyn.nv
+    none = AffineDesc(-1, -1)
+    d.aff_in = d.aff_out = d.aff_y = none
+    d.ext_w_off = d.ext_b_off = -1
+    slopes = set()
+    if dyn.kind == S.DYN_MLP:
+        d.net = pb.mlp(dyn.net)
+        d.aff_in, d.aff_out = pb.affine(dyn.aff_in), pb.affine(dyn.aff_out)
+        slopes.add(dyn.net.slope)
+    elif dyn.kind == S.DYN_REX:
+        d.net, d.encoder, d.decoder = pb.mlp(dyn.net), pb.mlp(dyn.encoder), pb.mlp(dyn.decoder)
+        d.ext_w_off, d.ext_b_off, d.ne = pb.add(dyn.ext_w), pb.add(dyn.ext_b), dyn.ext_w.shape[0]
+        d.aff_in, d.aff_out, d.aff_y = pb.affine(dyn.aff_in), pb.affine(dyn.aff_out), pb.affine(dyn.aff_y)
+        slopes.update((dyn.net.slope, dyn.encoder.slope, dyn.decoder.slope))
+    if len(slopes) > 1:
+        raise ValueError("networks with different LeakyReLU slopes are not supported: {}".format(slopes))
+    d.leaky_slope = slopes.pop() if slopes else 0.01
+    d.wrap_mask = _mask(dyn.wrap_dims)
+    d.has_bad_state_guard = int(dyn.bad_state_norm is not None)
+    d.bad_state_norm = dyn.bad_state_norm if dyn.bad_state_norm is not None else 0.0
+    for i, v in enumerate(dyn.pendulum):
+        d.pendulum[i] = v
+    return d, pb.array()
+
+
+def cost_desc(c: S.CostSpec):
+    d = CostDesc()
+    d.kind, d.nx, d.nu = c.kind, c.nx, c.nu
+    d.ang_mask, d.usim_mask = _mask(c.ang_dims), _mask(c.usim_dims)
+    for i in range(c.nx):
+        d.dist_scale[i] = c.dist_scale[i]
+    if c.kind == S.COST_GOAL_TRAP:
+        for i in range(c.nx):
+            d.goal[i] = c.goal[i]
+            for j in range(c.nx):
+                d.Q[i * MAX_NX + j] = c.Q[i, j]
+        for i in range(c.nu):
+            for j in range(c.nu):
+                d.R[i * MAX_NU + j] = c.R[i, j]
+        d.use_trap_cost = int(c.use_trap_cost)
+        d.n_traps = len(c.trap_x)
+        for p in range(len(c.trap_x)):
+            for i in range(c.nx):
+                d.trap_x[p][i] = c.trap_x[p, i]
+            for i in range(c.nu):
+                d.trap_u[p][i] = c.trap_u[p, i]
+        d.trap_weight = c.trap_weight
+        d.has_terminal = int(c.terminal_multiplier is not None)
+        d.terminal_multiplier = c.terminal_multiplier if c.terminal_multiplier is not None else 0.0
+    else:
+        d.n_sets = len(c.goal_sets)
+        for j, (g, w) in enumerate(zip(c.goal_sets, c.set_weights)):
+            d.set_size[j] = len(g)
+            d.set_weight[j] = w
+            for k in range(len(g)):
+                for i in range(c.nx):
+                    d.set_goals[j][k][i] = g[k, i]
+        d.recovery_scale = c.recovery_scale
+    return d
+
+
+def mppi_config(s: S.SamplerSpec, nx, precision, device=0, sample_offset=0, num_local=None, max_horizon=None,
+                seed=0, stream=None):
+    cfg = MppiConfig()
+    cfg.abi_version = ABI_VERSION
+    cfg.device = device
+    cfg.nx, cfg.nu = nx, s.nu
+    cfg.num_samples = s.K
+    cfg.sample_offset = sample_offset
+    cfg.num_local = s.K if num_local is None else num_local
+    cfg.max_horizon = max(s.T, max_horizon or 0)
+    cfg.precision = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+    cfg.lambda_ = s.lambda_
+    for i in range(s.nu):
+        cfg.noise_mu[i] = s.noise_mu[i]
+        cfg.u_init[i] = s.u_init[i]
+        for j in range(s.nu):
+            cfg.noise_sigma[i * s.nu + j] = s.noise_sigma[i, j]
+    cfg.has_bounds = int(s.u_min is not None)
+    if s.u_min is not None:
+        for i in range(s.nu):
+            cfg.u_min[i], cfg.u_max[i] = s.u_min[i], s.u_max[i]
+    cfg.sample_null_action = int(s.sample_null_action)
+    cfg.seed = seed
+    cfg.stream = stream
+    return cfg

@@ -1,0 +1,860 @@
+// mppi_api.cu — C ABI of libtampc_mppi.so (include/tampc_mppi.h): handle, model packing, command sequencing.
+//
+// Host-side shell of pytorch_mppi `MPPI` as used by tampc (tampc/controller/controller.py:316-435):
+//   command()        -> rollout_kernel + partials_kernel + combine_kernel on one stream, one pinned D2H of U[0]
+//   set_model()      -> folds the scaler chain of tampc/util.py:408-411 into the network layers and lays the
+//                       weights out for broadcast LDS.128 (device_common.cuh `linear`)
+//   set_cost()       -> cost program by value (mutated between calls: online_controller.py:400-402,416-418)
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "reduce_kernels.cuh"
+#include "variants.cuh"
+
+using namespace tampc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define CUDA_TRY(h, expr)                                                                            \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess) {                                                                        \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                                \
+      return TAMPC_ERR_CUDA;                                                                         \
+    }                                                                                                \
+  } while (0)
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct tampc_mppi {
+  tampc_mppi_config cfg{};
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+
+  const ModelVariant* variant = nullptr;
+  tampc_model_desc model{};
+  bool has_model = false, has_cost = false, has_nominal = false;
+  int T = 0;
+  uint64_t call = 0;
+  long long launches = 0;
+
+  SamplerD* d_sampler = nullptr;
+  tampc_cost_desc* d_cost = nullptr;
+  double* d_U[2] = {nullptr, nullptr};
+  int cur = 0;           // d_U[cur] = current nominal sequence
+  double* d_state = nullptr;
+  double* d_costs = nullptr;
+  double* d_noise = nullptr;    // injected noise / given actions staging (K_local, Tmax, nu)
+  double* d_states = nullptr;   // optional trajectories (K_local, Tmax, nx)
+  double* d_scratch = nullptr;  // perturbed-action readback
+  tampc_partial* d_partials = nullptr;
+  tampc_partial* d_rank_partial = nullptr;
+  double* d_action = nullptr;
+  double* d_stats = nullptr;
+  void* d_weights = nullptr;
+  size_t weights_bytes = 0;
+  int n_weight_elems = 0;
+
+  double* h_pin = nullptr;  // pinned staging: [0..15] in, [16..31] out
+  int n_chunks = 0, chunk = 0;
+
+  // last command bookkeeping (for queries)
+  int last_mode = kModePhilox;
+  uint64_t last_call = 0;
+  int last_T = 0;
+  int last_U = 0;  // index of the pre-shift nominal the last command used
+  bool last_valid = false;
+  bool states_valid = false;
+  double last_stats[3] = {0, 0, 0};
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// model packing (all folding in float64, then converted to the network type)
+
+struct HostLayer {
+  int in = 0, out = 0;
+  std::vector<double> W;  // (out, in) row-major
+  std::vector<double> b;
+};
+
+int read_mlp(tampc_mppi* h, const tampc_mlp_desc& d, const double* p, size_t n, std::vector<HostLayer>& out) {
+  if (d.n_layers < 1 || d.n_layers > TAMPC_MAX_LAYERS) { h->err = "mlp n_layers out of range"; return TAMPC_ERR_INVALID; }
+  out.resize(d.n_layers);
+  for (int l = 0; l < d.n_layers; ++l) {
+    HostLayer& L = out[l];
+    L.in = d.dims[l];
+    L.out = d.dims[l + 1];
+    if (L.in < 1 || L.out < 1) { h->err = "mlp layer with non-positive width"; return TAMPC_ERR_INVALID; }
+    if (d.w_off[l] < 0 || d.b_off[l] < 0 || (size_t)d.w_off[l] + (size_t)L.in * L.out > n || (size_t)d.b_off[l] + L.out > n) {
+      h->err = "mlp weight offsets outside the params array";
+      return TAMPC_ERR_INVALID;
+    }
+    L.W.assign(p + d.w_off[l], p + d.w_off[l] + (size_t)L.in * L.out);
+    L.b.assign(p + d.b_off[l], p + d.b_off[l] + L.out);
+  }
+  return TAMPC_OK;
+}
+
+int read_affine(tampc_mppi* h, const tampc_affine_desc& a, const double* p, size_t n, int dim, std::vector<double>& scale,
+                std::vector<double>& offset) {
+  scale.assign(dim, 1.0);
+  offset.assign(dim, 0.0);
+  if (a.scale_off < 0 && a.offset_off < 0) return TAMPC_OK;
+  if (a.scale_off < 0 || a.offset_off < 0 || (size_t)a.scale_off + dim > n || (size_t)a.offset_off + dim > n) {
+    h->err = "affine offsets outside the params array";
+    return TAMPC_ERR_INVALID;
+  }
+  for (int i = 0; i < dim; ++i) {
+    scale[i] = p[a.scale_off + i];
+    offset[i] = p[a.offset_off + i];
+    if (scale[i] == 0.0 || !std::isfinite(scale[i])) { h->err = "affine scale must be finite and non-zero"; return TAMPC_ERR_INVALID; }
+  }
+  return TAMPC_OK;
+}
+
+// y = W (x*s + o) + b  ->  W' = W diag(s), b' = b + W o
+void fold_input_affine(HostLayer& L, const std::vector<double>& s, const std::vector<double>& o) {
+  for (int r = 0; r < L.out; ++r) {
+    double acc = L.b[r];
+    for (int c = 0; c < L.in; ++c) {
+      acc += L.W[(size_t)r * L.in + c] * o[c];
+      L.W[(size_t)r * L.in + c] *= s[c];
+    }
+    L.b[r] = acc;
+  }
+}
+// y' = y*s + o applied after the layer
+void fold_output_affine(HostLayer& L, const std::vector<double>& s, const std::vector<double>& o) {
+  for (int r = 0; r < L.out; ++r) {
+    for (int c = 0; c < L.in; ++c) L.W[(size_t)r * L.in + c] *= s[r];
+    L.b[r] = L.b[r] * s[r] + o[r];
+  }
+}
+
+template <typename NT>
+void pack_layer(std::vector<NT>& blob, const HostLayer& L) {
+  const int OP = pad_out<NT>(L.out);
+  const size_t base = blob.size();
+  blob.resize(base + (size_t)(L.in + 1) * OP, (NT)0);
+  for (int j = 0; j < L.out; ++j) blob[base + j] = (NT)L.b[j];
+  for (int i = 0; i < L.in; ++i)
+    for (int j = 0; j < L.out; ++j) blob[base + (size_t)(i + 1) * OP + j] = (NT)L.W[(size_t)j * L.in + i];
+}
+
+template <typename NT>
+void pack_mlp(std::vector<NT>& blob, const std::vector<HostLayer>& m) {
+  for (const HostLayer& L : m) pack_layer<NT>(blob, L);
+}
+
+bool dims_are(const std::vector<HostLayer>& m, std::initializer_list<int> dims) {
+  if (m.size() + 1 != dims.size()) return false;
+  auto it = dims.begin();
+  if (m[0].in != *it) return false;
+  ++it;
+  for (size_t l = 0; l < m.size(); ++l, ++it)
+    if (m[l].out != *it) return false;
+  return true;
+}
+
+struct PackedModel {
+  const ModelVariant* variant = nullptr;
+  std::vector<float> f32;
+  std::vector<double> f64;
+};
+
+int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t n, PackedModel& out) {
+  const int nx = d.nx, nu = d.nu;
+  if (nx != h->cfg.nx || nu != h->cfg.nu) { h->err = "model nx/nu differ from the handle's"; return TAMPC_ERR_INVALID; }
+  if (!(d.leaky_slope >= 0.0 && d.leaky_slope <= 1.0)) { h->err = "leaky_slope must be in [0,1]"; return TAMPC_ERR_UNSUPPORTED; }
+  const ModelVariant* all[] = {variant_rex_push(), variant_rex_peg(), variant_mlp_5_3_32(), variant_mlp_5_3_64(), variant_pendulum()};
+  char buf[256];
+  if (d.kind == TAMPC_DYN_PENDULUM) {
+    if (nx != 2 || nu != 1) { h->err = "pendulum dynamics need nx=2, nu=1"; return TAMPC_ERR_INVALID; }
+    out.variant = variant_pendulum();
+    out.f32.assign(8, 0.f);
+    out.f64.assign(8, 0.0);
+    for (int i = 0; i < 6; ++i) { out.f32[i] = (float)d.pendulum[i]; out.f64[i] = d.pendulum[i]; }
+    return TAMPC_OK;
+  }
+  if (d.kind == TAMPC_DYN_MLP) {
+    std::vector<HostLayer> net;
+    int rc = read_mlp(h, d.net, p, n, net);
+    if (rc) return rc;
+    if (net.size() != 3 || net[0].in != nx + nu || net[2].out != nx) {
+      h->err = "MLP dynamics must be (nx+nu) -> h1 -> h2 -> nx";
+      return TAMPC_ERR_UNSUPPORTED;
+    }
+    std::vector<double> s, o;
+    if ((rc = read_affine(h, d.aff_in, p, n, nx + nu, s, o))) return rc;
+    fold_input_affine(net[0], s, o);
+    if ((rc = read_affine(h, d.aff_out, p, n, nx, s, o))) return rc;
+    {  // dx = (y - o)/s
+      std::vector<double> si(nx), oi(nx);
+      for (int i = 0; i < nx; ++i) { si[i] = 1.0 / s[i]; oi[i] = -o[i] / s[i]; }
+      fold_output_affine(net[2], si, oi);
+    }
+    for (const ModelVariant* v : all) {
+      if (v->kind == TAMPC_DYN_MLP && v->nx == nx && v->nu == nu && net[0].out == v->dims[0] && net[1].out == v->dims[1]) out.variant = v;
+    }
+    if (!out.variant) {
+      snprintf(buf, sizeof buf, "no compiled kernel for MLP dynamics nx=%d nu=%d hidden=%d,%d", nx, nu, net[0].out, net[1].out);
+      h->err = buf;
+      return TAMPC_ERR_UNSUPPORTED;
+    }
+    pack_mlp<float>(out.f32, net);
+    pack_mlp<double>(out.f64, net);
+    return TAMPC_OK;
+  }
+  if (d.kind != TAMPC_DYN_REX) { h->err = "unknown dynamics kind"; return TAMPC_ERR_INVALID; }
+  std::vector<HostLayer> enc, dyn, dec;
+  int rc;
+  if ((rc = read_mlp(h, d.encoder, p, n, enc)) || (rc = read_mlp(h, d.net, p, n, dyn)) || (rc = read_mlp(h, d.decoder, p, n, dec))) return rc;
+  const int nv = d.nv, ne = d.ne;
+  if (enc.size() != 3 || dyn.size() != 3 || dec.size() != 3 || enc[0].in != nx + nu || dyn[0].in != enc[2].out || dyn[2].out != nv ||
+      dec[0].in != ne || dec[2].out != nx * nv) {
+    h->err = "REX dynamics must be three 3-layer MLPs: (nx+nu)->..->nz, nz->..->nv, ne->..->nx*nv";
+    return TAMPC_ERR_UNSUPPORTED;
+  }
+  const int nz = enc[2].out;
+  std::vector<double> s, o;
+  // z' = z*s + o  after the encoder
+  if ((rc = read_affine(h, d.aff_in, p, n, nz, s, o))) return rc;
+  fold_output_affine(enc[2], s, o);
+  // v = (v' - o)/s after the latent dynamics
+  if ((rc = read_affine(h, d.aff_out, p, n, nv, s, o))) return rc;
+  {
+    std::vector<double> si(nv), oi(nv);
+    for (int i = 0; i < nv; ++i) { si[i] = 1.0 / s[i]; oi[i] = -o[i] / s[i]; }
+    fold_output_affine(dyn[2], si, oi);
+  }
+  // e = Wx x + bx feeds the decoder's first Linear with no activation in between: compose them
+  if (d.ext_w_off < 0 || d.ext_b_off < 0 || (size_t)d.ext_w_off + (size_t)ne * nx > n || (size_t)d.ext_b_off + ne > n) {
+    h->err = "extractor offsets outside the params array";
+    return TAMPC_ERR_INVALID;
+  }
+  {
+    const double* Wx = p + d.ext_w_off;
+    const double* bx = p + d.ext_b_off;
+    HostLayer L;
+    L.in = nx;
+    L.out = dec[0].out;
+    L.W.assign((size_t)L.out * nx, 0.0);
+    L.b = dec[0].b;
+    for (int r = 0; r < L.out; ++r) {
+      for (int e = 0; e < ne; ++e) {
+        const double w = dec[0].W[(size_t)r * ne + e];
+        L.b[r] += w * bx[e];
+        for (int c = 0; c < nx; ++c) L.W[(size_t)r * nx + c] += w * Wx[(size_t)e * nx + c];
+      }
+    }
+    dec[0] = L;
+  }
+  // dx_i = (sum_j C[i][j] v_j - o_i)/s_i : scale decoder output rows i*nv+j by 1/s_i, keep d0_i = -o_i/s_i
+  if ((rc = read_affine(h, d.aff_y, p, n, nx, s, o))) return rc;
+  std::vector<double> d0(nx);
+  {
+    std::vector<double> si((size_t)nx * nv), oi((size_t)nx * nv, 0.0);
+    for (int i = 0; i < nx; ++i) {
+      d0[i] = -o[i] / s[i];
+      for (int j = 0; j < nv; ++j) si[(size_t)i * nv + j] = 1.0 / s[i];
+    }
+    fold_output_affine(dec[2], si, oi);
+  }
+  for (const ModelVariant* v : all) {
+    if (v->kind == TAMPC_DYN_REX && v->nx == nx && v->nu == nu && enc[0].out == v->dims[0] && enc[1].out == v->dims[1] && nz == v->dims[2] &&
+        dyn[0].out == v->dims[3] && dyn[1].out == v->dims[4] && nv == v->dims[5] && dec[0].out == v->dims[6] && dec[1].out == v->dims[7])
+      out.variant = v;
+  }
+  if (!out.variant) {
+    snprintf(buf, sizeof buf, "no compiled kernel for REX dynamics nx=%d nu=%d enc=%d,%d,%d dyn=%d,%d,%d dec=%d,%d", nx, nu, enc[0].out,
+             enc[1].out, nz, dyn[0].out, dyn[1].out, nv, dec[0].out, dec[1].out);
+    h->err = buf;
+    return TAMPC_ERR_UNSUPPORTED;
+  }
+  pack_mlp<float>(out.f32, enc);
+  pack_mlp<float>(out.f32, dyn);
+  pack_mlp<float>(out.f32, dec);
+  pack_mlp<double>(out.f64, enc);
+  pack_mlp<double>(out.f64, dyn);
+  pack_mlp<double>(out.f64, dec);
+  const int d0p = (nx + 3) & ~3;
+  for (int i = 0; i < d0p; ++i) {
+    out.f32.push_back(i < nx ? (float)d0[i] : 0.f);
+    out.f64.push_back(i < nx ? d0[i] : 0.0);
+  }
+  return TAMPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+
+void choose_launch(const tampc_mppi* h, int& S, int& block) {
+  const int K = h->cfg.num_local;
+  const bool f64 = h->cfg.precision == TAMPC_PREC_F64;
+  const bool has_s2 = !f64 && h->variant->mixed_s2 != nullptr;
+  // two samples per thread halves the LDS:FFMA2 ratio (tools/peaks) but needs >= ~2 CTAs of 128 threads per SM
+  S = (has_s2 && K >= 2 * 148 * 128 * 2) ? 2 : 1;
+  const int threads = (K + S - 1) / S;
+  if (threads >= 2 * 148 * 128) block = 128;
+  else if (threads >= 2 * 148 * 64) block = 64;
+  else block = 32;
+  const int es = env_int("TAMPC_SAMPLES_PER_THREAD", 0), eb = env_int("TAMPC_BLOCK", 0);
+  if (es == 1 || (es == 2 && has_s2)) S = es;
+  if (eb == 32 || eb == 64 || eb == 128) block = eb;
+}
+
+rollout_launch_fn pick_kernel(const tampc_mppi* h, int S) {
+  const ModelVariant* v = h->variant;
+  switch (h->cfg.precision) {
+    case TAMPC_PREC_F64: return v->f64_s1;
+    case TAMPC_PREC_MIXED: return S == 2 ? v->mixed_s2 : v->mixed_s1;
+    default: return S == 2 ? v->f32_s2 : v->f32_s1;
+  }
+}
+
+SampleSrc make_src(const tampc_mppi* h, int mode, uint64_t call, int T) {
+  SampleSrc s{};
+  s.mode = mode;
+  s.noise = h->d_noise;
+  s.actions = h->d_noise;
+  s.seed = h->cfg.seed;
+  s.call = call;
+  s.sample_offset = h->cfg.sample_offset;
+  s.k_global = h->cfg.num_samples;
+  s.T = T;
+  return s;
+}
+
+int check_ready(tampc_mppi* h) {
+  if (!h->has_model) { h->err = "set_model has not been called"; return TAMPC_ERR_STATE; }
+  if (!h->has_cost) { h->err = "set_cost has not been called"; return TAMPC_ERR_STATE; }
+  if (!h->has_nominal) { h->err = "set_nominal has not been called"; return TAMPC_ERR_STATE; }
+  return TAMPC_OK;
+}
+
+int launch_rollout_for(tampc_mppi* h, int mode, int shift, const double* d_U, int T, uint64_t call, bool keep_states) {
+  RolloutArgs a{};
+  a.weights = h->d_weights;
+  a.n_weight_elems = h->n_weight_elems;
+  a.slope = h->model.leaky_slope;
+  a.cost = h->d_cost;
+  a.sampler = h->d_sampler;
+  a.U = d_U;
+  a.shift = shift;
+  a.state = h->d_state;
+  a.src = make_src(h, mode, call, T);
+  a.K_local = h->cfg.num_local;
+  a.cost_out = h->d_costs;
+  a.states_out = keep_states ? h->d_states : nullptr;
+  a.wrap_mask = h->model.wrap_mask;
+  a.has_guard = h->model.has_bad_state_guard;
+  a.bad_norm = h->model.bad_state_norm;
+  int S, block;
+  choose_launch(h, S, block);
+  rollout_launch_fn fn = pick_kernel(h, S);
+  if (!fn) { h->err = "no kernel compiled for this precision / samples-per-thread"; return TAMPC_ERR_UNSUPPORTED; }
+  CUDA_TRY(h, fn(a, block, h->stream));
+  h->launches++;
+  return TAMPC_OK;
+}
+
+int ensure_states(tampc_mppi* h) {
+  if (!h->d_states)
+    CUDA_TRY(h, cudaMalloc(&h->d_states, sizeof(double) * (size_t)h->cfg.num_local * h->cfg.max_horizon * h->cfg.nx));
+  return TAMPC_OK;
+}
+
+int ensure_noise(tampc_mppi* h) {
+  if (!h->d_noise)
+    CUDA_TRY(h, cudaMalloc(&h->d_noise, sizeof(double) * (size_t)h->cfg.num_local * h->cfg.max_horizon * h->cfg.nu));
+  return TAMPC_OK;
+}
+
+template <int NU>
+void launch_partials(const ReduceArgs& r, int n_chunks, cudaStream_t s) {
+  partials_kernel<NU><<<n_chunks, kReduceThreads, 0, s>>>(r);
+}
+
+// rollout of the shard + reduction of the shard to CTA partials
+int run_rollout_and_partials(tampc_mppi* h, int mode, bool keep_states) {
+  const int T = h->T;
+  const double* U = h->d_U[h->cur];
+  h->call++;
+  int rc = launch_rollout_for(h, mode, /*shift=*/1, U, T, h->call, keep_states);
+  if (rc) return rc;
+  ReduceArgs r{};
+  r.cost = h->d_costs;
+  r.sampler = h->d_sampler;
+  r.U = U;
+  r.src = make_src(h, mode, h->call, T);
+  r.K_local = h->cfg.num_local;
+  r.chunk = h->chunk;
+  r.nu = h->cfg.nu;
+  r.partials = h->d_partials;
+  switch (h->cfg.nu) {
+    case 1: launch_partials<1>(r, h->n_chunks, h->stream); break;
+    case 2: launch_partials<2>(r, h->n_chunks, h->stream); break;
+    case 3: launch_partials<3>(r, h->n_chunks, h->stream); break;
+    default: launch_partials<4>(r, h->n_chunks, h->stream); break;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  h->last_mode = mode;
+  h->last_call = h->call;
+  h->last_T = T;
+  h->last_U = h->cur;
+  h->last_valid = true;
+  h->states_valid = keep_states;
+  return TAMPC_OK;
+}
+
+int run_combine(tampc_mppi* h, const tampc_partial* partials, int n, int finalize, tampc_partial* partial_out = nullptr) {
+  CombineArgs c{};
+  c.partials = partials;
+  c.n_partials = n;
+  c.sampler = h->d_sampler;
+  c.U = h->d_U[h->cur];
+  c.T = h->T;
+  c.nu = h->cfg.nu;
+  c.finalize = finalize;
+  c.U_out = h->d_U[h->cur ^ 1];
+  c.action_out = h->d_action;
+  c.stats_out = h->d_stats;
+  c.partial_out = partial_out ? partial_out : h->d_rank_partial;
+  combine_kernel<<<1, kCombineThreads, 0, h->stream>>>(c);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  if (finalize) h->cur ^= 1;
+  return TAMPC_OK;
+}
+
+int upload_state(tampc_mppi* h, const double* state) {
+  memcpy(h->h_pin, state, sizeof(double) * h->cfg.nx);
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_state, h->h_pin, sizeof(double) * h->cfg.nx, cudaMemcpyHostToDevice, h->stream));
+  return TAMPC_OK;
+}
+
+int upload_noise(tampc_mppi* h, int mode, const double* noise, int T) {
+  if (mode == kModePhilox) return TAMPC_OK;
+  if (mode != kModeInjected && mode != kModeActions) { h->err = "unknown noise_mode"; return TAMPC_ERR_INVALID; }
+  if (!noise) { h->err = "noise_mode needs a host array"; return TAMPC_ERR_INVALID; }
+  int rc = ensure_noise(h);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_noise, noise, sizeof(double) * (size_t)h->cfg.num_local * T * h->cfg.nu, cudaMemcpyHostToDevice, h->stream));
+  return TAMPC_OK;
+}
+
+int download_action(tampc_mppi* h, double* action) {
+  double* out = h->h_pin + 16;
+  CUDA_TRY(h, cudaMemcpyAsync(out, h->d_action, sizeof(double) * h->cfg.nu, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(out + 8, h->d_stats, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  memcpy(action, out, sizeof(double) * h->cfg.nu);
+  memcpy(h->last_stats, out + 8, sizeof(double) * 3);
+  return TAMPC_OK;
+}
+
+}  // namespace
+
+// ==================================================================================================
+extern "C" {
+
+TAMPC_API int tampc_mppi_abi_version(void) { return TAMPC_ABI_VERSION; }
+
+TAMPC_API const char* tampc_mppi_last_error(const tampc_mppi* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+TAMPC_API int tampc_mppi_create(const tampc_mppi_config* cfg, tampc_mppi** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return TAMPC_ERR_INVALID; }
+  *out = nullptr;
+  if (cfg->abi_version != TAMPC_ABI_VERSION) { g_create_error = "ABI version mismatch"; return TAMPC_ERR_INVALID; }
+  if (cfg->nx < 1 || cfg->nx > TAMPC_MAX_NX || cfg->nu < 1 || cfg->nu > TAMPC_MAX_NU) { g_create_error = "nx/nu out of range"; return TAMPC_ERR_INVALID; }
+  if (cfg->num_samples < 1 || cfg->num_local < 1 || cfg->sample_offset < 0 || cfg->sample_offset + cfg->num_local > cfg->num_samples) {
+    g_create_error = "sample shard [offset, offset+num_local) must lie inside [0, num_samples)";
+    return TAMPC_ERR_INVALID;
+  }
+  if (cfg->max_horizon < 1 || cfg->max_horizon > TAMPC_MAX_HORIZON) { g_create_error = "max_horizon out of range (1..128)"; return TAMPC_ERR_INVALID; }
+  if (cfg->precision < TAMPC_PREC_F64 || cfg->precision > TAMPC_PREC_F32) { g_create_error = "unknown precision"; return TAMPC_ERR_INVALID; }
+  if (!(cfg->lambda_ > 0.0)) { g_create_error = "lambda_ must be positive"; return TAMPC_ERR_INVALID; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+    return TAMPC_ERR_NO_DEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return TAMPC_ERR_INVALID; }
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+    return TAMPC_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "kernels are compiled for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return TAMPC_ERR_NO_DEVICE;
+  }
+  // Cholesky and inverse of the noise covariance (float64, host)
+  const int nu = cfg->nu;
+  double L[kMaxNu * kMaxNu] = {0}, inv[kMaxNu * kMaxNu] = {0};
+  for (int i = 0; i < nu; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = cfg->noise_sigma[i * nu + j];
+      for (int k = 0; k < j; ++k) s -= L[i * kMaxNu + k] * L[j * kMaxNu + k];
+      if (i == j) {
+        if (!(s > 0.0)) { g_create_error = "noise_sigma is not positive definite"; return TAMPC_ERR_INVALID; }
+        L[i * kMaxNu + i] = sqrt(s);
+      } else {
+        L[i * kMaxNu + j] = s / L[j * kMaxNu + j];
+      }
+    }
+  {  // Sigma^-1 = L^-T L^-1
+    double Li[kMaxNu * kMaxNu] = {0};
+    for (int c = 0; c < nu; ++c)
+      for (int r = 0; r < nu; ++r) {
+        if (r < c) continue;
+        double s = (r == c) ? 1.0 : 0.0;
+        for (int k = c; k < r; ++k) s -= L[r * kMaxNu + k] * Li[k * kMaxNu + c];
+        Li[r * kMaxNu + c] = s / L[r * kMaxNu + r];
+      }
+    for (int i = 0; i < nu; ++i)
+      for (int j = 0; j < nu; ++j) {
+        double s = 0.0;
+        for (int k = 0; k < nu; ++k) s += Li[k * kMaxNu + i] * Li[k * kMaxNu + j];
+        inv[i * kMaxNu + j] = s;
+      }
+  }
+  tampc_mppi* h = new tampc_mppi();
+  h->cfg = *cfg;
+  auto fail = [&](const std::string& msg, int code) {
+    g_create_error = msg;
+    tampc_mppi_destroy(h);
+    return code;
+  };
+#define CREATE_TRY(expr)                                                                  \
+  do {                                                                                    \
+    cudaError_t e2 = (expr);                                                              \
+    if (e2 != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e2), TAMPC_ERR_CUDA); \
+  } while (0)
+  if (cfg->stream) {
+    h->stream = (cudaStream_t)cfg->stream;
+  } else {
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  const int Tm = cfg->max_horizon, K = cfg->num_local;
+  h->chunk = env_int("TAMPC_REDUCE_CHUNK", K >= (1 << 16) ? 256 : 64);
+  if (h->chunk < 1 || h->chunk > kReduceThreads) h->chunk = 64;
+  h->n_chunks = (K + h->chunk - 1) / h->chunk;
+  CREATE_TRY(cudaMalloc(&h->d_sampler, sizeof(SamplerD)));
+  CREATE_TRY(cudaMalloc(&h->d_cost, sizeof(tampc_cost_desc)));
+  CREATE_TRY(cudaMalloc(&h->d_U[0], sizeof(double) * Tm * kMaxNu));
+  CREATE_TRY(cudaMalloc(&h->d_U[1], sizeof(double) * Tm * kMaxNu));
+  CREATE_TRY(cudaMalloc(&h->d_state, sizeof(double) * kMaxNx));
+  CREATE_TRY(cudaMalloc(&h->d_costs, sizeof(double) * K));
+  CREATE_TRY(cudaMalloc(&h->d_partials, sizeof(tampc_partial) * h->n_chunks));
+  CREATE_TRY(cudaMalloc(&h->d_rank_partial, sizeof(tampc_partial)));
+  CREATE_TRY(cudaMalloc(&h->d_action, sizeof(double) * kMaxNu));
+  CREATE_TRY(cudaMalloc(&h->d_stats, sizeof(double) * 4));
+  CREATE_TRY(cudaMallocHost(&h->h_pin, sizeof(double) * 32));
+  SamplerD sd{};
+  for (int i = 0; i < nu; ++i) {
+    sd.mu[i] = cfg->noise_mu[i];
+    sd.u_min[i] = cfg->u_min[i];
+    sd.u_max[i] = cfg->u_max[i];
+    sd.u_init[i] = cfg->u_init[i];
+    for (int j = 0; j < nu; ++j) {
+      sd.chol[i * kMaxNu + j] = L[i * kMaxNu + j];
+      sd.lam_sigma_inv[i * kMaxNu + j] = cfg->lambda_ * inv[i * kMaxNu + j];
+    }
+  }
+  sd.lambda_inv = 1.0 / cfg->lambda_;
+  sd.has_bounds = cfg->has_bounds;
+  sd.null_action = cfg->sample_null_action;
+  CREATE_TRY(cudaMemcpy(h->d_sampler, &sd, sizeof sd, cudaMemcpyHostToDevice));
+#undef CREATE_TRY
+  *out = h;
+  return TAMPC_OK;
+}
+
+TAMPC_API void tampc_mppi_destroy(tampc_mppi* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_sampler); cudaFree(h->d_cost); cudaFree(h->d_U[0]); cudaFree(h->d_U[1]); cudaFree(h->d_state);
+  cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_partials);
+  cudaFree(h->d_rank_partial); cudaFree(h->d_action); cudaFree(h->d_stats); cudaFree(h->d_weights);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+TAMPC_API int tampc_mppi_set_model(tampc_mppi* h, const tampc_model_desc* desc, const double* params, size_t n_params) {
+  if (!h || !desc) return TAMPC_ERR_INVALID;
+  if (n_params && !params) { h->err = "params is null"; return TAMPC_ERR_INVALID; }
+  PackedModel pm;
+  int rc = pack_model(h, *desc, params, n_params, pm);
+  if (rc) return rc;
+  const bool f64 = h->cfg.precision == TAMPC_PREC_F64;
+  const void* src = f64 ? (const void*)pm.f64.data() : (const void*)pm.f32.data();
+  const size_t elems = f64 ? pm.f64.size() : pm.f32.size();
+  const int expect = f64 ? pm.variant->elems_f64 : pm.variant->elems_f32;
+  if ((int)elems != expect) {
+    h->err = "internal: packed size " + std::to_string(elems) + " != kernel layout " + std::to_string(expect) + " for " + pm.variant->name;
+    return TAMPC_ERR_INVALID;
+  }
+  const size_t bytes = ((f64 ? 8 : 4) * elems + 15) & ~size_t(15);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (bytes > h->weights_bytes) {
+    cudaFree(h->d_weights);
+    h->d_weights = nullptr;
+    CUDA_TRY(h, cudaMalloc(&h->d_weights, bytes));
+    h->weights_bytes = bytes;
+  }
+  CUDA_TRY(h, cudaMemset(h->d_weights, 0, h->weights_bytes));
+  CUDA_TRY(h, cudaMemcpy(h->d_weights, src, (f64 ? 8 : 4) * elems, cudaMemcpyHostToDevice));
+  h->n_weight_elems = (int)(bytes / (f64 ? 8 : 4));
+  h->variant = pm.variant;
+  h->model = *desc;
+  h->has_model = true;
+  return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_set_cost(tampc_mppi* h, const tampc_cost_desc* d) {
+  if (!h || !d) return TAMPC_ERR_INVALID;
+  if (d->nx != h->cfg.nx || d->nu != h->cfg.nu) { h->err = "cost nx/nu differ from the handle's"; return TAMPC_ERR_INVALID; }
+  if (d->kind == TAMPC_COST_GOAL_TRAP) {
+    if (d->n_traps < 0 || d->n_traps > TAMPC_MAX_TRAPS) { h->err = "n_traps out of range"; return TAMPC_ERR_INVALID; }
+  } else if (d->kind == TAMPC_COST_RECOVERY) {
+    if (d->n_sets < 1 || d->n_sets > TAMPC_MAX_GOAL_SETS) { h->err = "n_sets out of range"; return TAMPC_ERR_INVALID; }
+    for (int j = 0; j < d->n_sets; ++j)
+      if (d->set_size[j] < 1 || d->set_size[j] > TAMPC_MAX_SET_GOALS) { h->err = "goal set size out of range"; return TAMPC_ERR_INVALID; }
+  } else {
+    h->err = "unknown cost kind";
+    return TAMPC_ERR_INVALID;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  // stream-ordered with respect to earlier commands; the pageable source is consumed before the call returns
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_cost, d, sizeof *d, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->has_cost = true;
+  return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_set_nominal(tampc_mppi* h, const double* U, int32_t horizon) {
+  if (!h || !U) return TAMPC_ERR_INVALID;
+  if (horizon < 1 || horizon > h->cfg.max_horizon) { h->err = "horizon outside [1, max_horizon]"; return TAMPC_ERR_INVALID; }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_U[h->cur], U, sizeof(double) * horizon * h->cfg.nu, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->T = horizon;
+  h->has_nominal = true;
+  return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_get_nominal(tampc_mppi* h, double* U) {
+  if (!h || !U) return TAMPC_ERR_INVALID;
+  if (!h->has_nominal) { h->err = "set_nominal has not been called"; return TAMPC_ERR_STATE; }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaMemcpyAsync(U, h->d_U[h->cur], sizeof(double) * h->T * h->cfg.nu, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_command_begin(tampc_mppi* h, const double* state, int32_t noise_mode, const double* noise, int32_t keep_states,
+                             void* partial_dev) {
+  if (!h || !state) return TAMPC_ERR_INVALID;
+  int rc = check_ready(h);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if ((rc = upload_state(h, state))) return rc;
+  if ((rc = upload_noise(h, noise_mode, noise, h->T))) return rc;
+  if (keep_states && (rc = ensure_states(h))) return rc;
+  if ((rc = run_rollout_and_partials(h, noise_mode, keep_states != 0))) return rc;
+  if (!partial_dev) { h->err = "partial_dev is null"; return TAMPC_ERR_INVALID; }
+  return run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/0, (tampc_partial*)partial_dev);
+}
+
+TAMPC_API int tampc_mppi_command_finish(tampc_mppi* h, const void* partials_dev, int32_t world, double* action) {
+  if (!h || !partials_dev || !action || world < 1) return TAMPC_ERR_INVALID;
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!h->last_valid) { h->err = "command_finish without command_begin"; return TAMPC_ERR_STATE; }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if ((rc = run_combine(h, (const tampc_partial*)partials_dev, world, /*finalize=*/1))) return rc;
+  return download_action(h, action);
+}
+
+TAMPC_API int tampc_mppi_command(tampc_mppi* h, const double* state, int32_t noise_mode, const double* noise, double* action) {
+  if (!h || !state || !action) return TAMPC_ERR_INVALID;
+  int rc = check_ready(h);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if ((rc = upload_state(h, state))) return rc;
+  if ((rc = upload_noise(h, noise_mode, noise, h->T))) return rc;
+  if ((rc = run_rollout_and_partials(h, noise_mode, false))) return rc;
+  if ((rc = run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/1))) return rc;
+  return download_action(h, action);
+}
+
+TAMPC_API int tampc_mppi_set_state_resident(tampc_mppi* h, const double* state) {
+  if (!h || !state) return TAMPC_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  int rc = upload_state(h, state);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_command_resident(tampc_mppi* h, int32_t noise_mode) {
+  if (!h) return TAMPC_ERR_INVALID;
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (noise_mode != kModePhilox && !h->d_noise) { h->err = "resident command with injected noise needs a previous upload"; return TAMPC_ERR_STATE; }
+  if ((rc = run_rollout_and_partials(h, noise_mode, false))) return rc;
+  return run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/1);
+}
+
+TAMPC_API int tampc_mppi_rollout_costs(tampc_mppi* h, const double* state, const double* actions, int32_t horizon, double* cost_out, double* states_out) {
+  if (!h || !state || !actions || !cost_out) return TAMPC_ERR_INVALID;
+  if (!h->has_model || !h->has_cost) { h->err = "set_model / set_cost first"; return TAMPC_ERR_STATE; }
+  if (horizon < 1 || horizon > h->cfg.max_horizon) { h->err = "horizon outside [1, max_horizon]"; return TAMPC_ERR_INVALID; }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  int rc;
+  if ((rc = upload_state(h, state))) return rc;
+  if ((rc = upload_noise(h, kModeActions, actions, horizon))) return rc;
+  if (states_out && (rc = ensure_states(h))) return rc;
+  if ((rc = launch_rollout_for(h, kModeActions, 0, h->d_U[h->cur], horizon, 0, states_out != nullptr))) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(cost_out, h->d_costs, sizeof(double) * h->cfg.num_local, cudaMemcpyDeviceToHost, h->stream));
+  if (states_out)
+    CUDA_TRY(h, cudaMemcpyAsync(states_out, h->d_states, sizeof(double) * (size_t)h->cfg.num_local * horizon * h->cfg.nx, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->last_valid = false;
+  h->states_valid = false;
+  return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_get_rollouts(tampc_mppi* h, const double* state, double* states_out) {
+  if (!h || !state || !states_out) return TAMPC_ERR_INVALID;
+  int rc = check_ready(h);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if ((rc = upload_state(h, state))) return rc;
+  if ((rc = ensure_states(h))) return rc;
+  // one sample, nominal actions, states dumped; the per-sample cost buffer is left untouched via a K_local=1 view
+  RolloutArgs a{};
+  a.weights = h->d_weights;
+  a.n_weight_elems = h->n_weight_elems;
+  a.slope = h->model.leaky_slope;
+  a.cost = h->d_cost;
+  a.sampler = h->d_sampler;
+  a.U = h->d_U[h->cur];
+  a.shift = 0;
+  a.state = h->d_state;
+  a.src = make_src(h, kModeNominal, 0, h->T);
+  a.K_local = 1;
+  a.cost_out = h->d_stats + 3;
+  a.states_out = h->d_states;
+  a.wrap_mask = h->model.wrap_mask;
+  a.has_guard = h->model.has_bad_state_guard;
+  a.bad_norm = h->model.bad_state_norm;
+  rollout_launch_fn fn = pick_kernel(h, 1);
+  CUDA_TRY(h, fn(a, 32, h->stream));
+  h->launches++;
+  CUDA_TRY(h, cudaMemcpyAsync(states_out, h->d_states, sizeof(double) * h->T * h->cfg.nx, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->states_valid = false;
+  return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_query(tampc_mppi* h, int32_t what, double* out, size_t n) {
+  if (!h || !out) return TAMPC_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const size_t K = h->cfg.num_local;
+  switch (what) {
+    case TAMPC_Q_COST_TOTAL: {
+      if (n < K) { h->err = "query buffer too small"; return TAMPC_ERR_INVALID; }
+      CUDA_TRY(h, cudaMemcpyAsync(out, h->d_costs, sizeof(double) * K, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      return TAMPC_OK;
+    }
+    case TAMPC_Q_OMEGA: {
+      if (!h->last_valid) { h->err = "no command has run"; return TAMPC_ERR_STATE; }
+      if (n < K) { h->err = "query buffer too small"; return TAMPC_ERR_INVALID; }
+      CUDA_TRY(h, cudaMemcpyAsync(out, h->d_costs, sizeof(double) * K, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      const double li = 1.0 / h->cfg.lambda_;
+      for (size_t k = 0; k < K; ++k) out[k] = exp(-li * (out[k] - h->last_stats[0])) / h->last_stats[1];
+      return TAMPC_OK;
+    }
+    case TAMPC_Q_NOMINAL: {
+      if (n < (size_t)h->T * h->cfg.nu) { h->err = "query buffer too small"; return TAMPC_ERR_INVALID; }
+      return tampc_mppi_get_nominal(h, out);
+    }
+    case TAMPC_Q_STATS: {
+      if (n < 4) { h->err = "query buffer too small"; return TAMPC_ERR_INVALID; }
+      out[0] = h->last_stats[0]; out[1] = h->last_stats[1]; out[2] = h->last_stats[2]; out[3] = (double)h->launches;
+      return TAMPC_OK;
+    }
+    case TAMPC_Q_PERTURBED: {
+      if (!h->last_valid) { h->err = "no command has run"; return TAMPC_ERR_STATE; }
+      const size_t total = K * h->last_T * h->cfg.nu;
+      if (n < total) { h->err = "query buffer too small"; return TAMPC_ERR_INVALID; }
+      if (!h->d_scratch) CUDA_TRY(h, cudaMalloc(&h->d_scratch, sizeof(double) * K * h->cfg.max_horizon * h->cfg.nu));
+      PerturbedArgs p{};
+      p.sampler = h->d_sampler;
+      p.U = h->d_U[h->last_U];
+      p.src = make_src(h, h->last_mode, h->last_call, h->last_T);
+      p.K_local = (int)K;
+      p.out = h->d_scratch;
+      const long long items = (long long)K * h->last_T;
+      const int grid = (int)((items + 255) / 256);
+      switch (h->cfg.nu) {
+        case 1: perturbed_kernel<1><<<grid, 256, 0, h->stream>>>(p); break;
+        case 2: perturbed_kernel<2><<<grid, 256, 0, h->stream>>>(p); break;
+        case 3: perturbed_kernel<3><<<grid, 256, 0, h->stream>>>(p); break;
+        default: perturbed_kernel<4><<<grid, 256, 0, h->stream>>>(p); break;
+      }
+      CUDA_TRY(h, cudaGetLastError());
+      h->launches++;
+      CUDA_TRY(h, cudaMemcpyAsync(out, h->d_scratch, sizeof(double) * total, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      return TAMPC_OK;
+    }
+    case TAMPC_Q_STATES: {
+      if (!h->states_valid) { h->err = "last command did not keep states"; return TAMPC_ERR_STATE; }
+      const size_t total = K * h->last_T * h->cfg.nx;
+      if (n < total) { h->err = "query buffer too small"; return TAMPC_ERR_INVALID; }
+      CUDA_TRY(h, cudaMemcpyAsync(out, h->d_states, sizeof(double) * total, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      return TAMPC_OK;
+    }
+    default: h->err = "unknown query"; return TAMPC_ERR_INVALID;
+  }
+}
+
+TAMPC_API int tampc_mppi_device_costs(tampc_mppi* h, void** dev_ptr) {
+  if (!h || !dev_ptr) return TAMPC_ERR_INVALID;
+  *dev_ptr = h->d_costs;
+  return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_synchronize(tampc_mppi* h) {
+  if (!h) return TAMPC_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return TAMPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+// reduce_kernels.cuh — softmax weighting of the sampled trajectories and update of the nominal sequence.
+//
+// Replaces the tail of pytorch_mppi `MPPI.command` (restated in oracle/shim/pytorch_mppi/mppi.py; called from
+// tampc/controller/online_controller.py:497):  beta = min cost;  w = exp(-(cost-beta)/lambda);  eta = sum w;
+// U[t] += sum_k (w_k/eta) * noise[k,t]  with the POST-clamp noise of controller.py:394.
+//
+// Two stages so that one design serves one GPU and a K-sharded multi-GPU run:
+//   partials_kernel : each CTA reduces a chunk of samples to a tampc_partial relative to its own local minimum
+//   combine_kernel  : one CTA merges P partials (CTA partials, or one per rank after the all-gather) in index
+//                     order with the log-sum-exp rescale s_p = exp(-(beta_p - beta)/lambda); deterministic, so
+//                     every rank obtains bitwise-identical U.
+// The post-clamp noise is regenerated (Philox) or re-read (injected) rather than stored by the rollout kernel.
+#pragma once
+#include "device_common.cuh"
+
+namespace tampc {
+
+struct ReduceArgs {
+  const double* cost;   // (K_local,)
+  const SamplerD* sampler;
+  const double* U;      // nominal sequence BEFORE the shift (T, nu)
+  SampleSrc src;
+  int K_local, chunk, nu;
+  tampc_partial* partials;  // (n_chunks,)
+};
+
+constexpr int kReduceThreads = 256;
+
+template <int NU>
+__global__ void __launch_bounds__(kReduceThreads) partials_kernel(const ReduceArgs a) {
+  __shared__ double s_w[kReduceThreads];      // costs, then weights, of the chunk (chunk <= kReduceThreads)
+  __shared__ double s_red[kReduceThreads];
+  __shared__ int s_idx[kReduceThreads];
+  __shared__ SamplerS<double> sp;
+  __shared__ double Ush[TAMPC_MAX_HORIZON * kMaxNu];
+  __shared__ double s_acc[kReduceThreads * NU];
+
+  const int tid = threadIdx.x;
+  const int T = a.src.T;
+  const int k0 = blockIdx.x * a.chunk;
+  const int n = min(a.chunk, a.K_local - k0);
+  stage_sampler<double>(sp, *a.sampler, tid, kReduceThreads);
+  for (int i = tid; i < T * NU; i += kReduceThreads) {
+    int t = i / NU, d = i % NU, ts = t + 1;
+    Ush[t * kMaxNu + d] = ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d];
+  }
+  // ---- block min / argmin (lowest index wins ties, like torch.min / argmin over a 1-D tensor)
+  double c = tid < n ? a.cost[k0 + tid] : __longlong_as_double(0x7ff0000000000000ll);
+  s_w[tid] = c;
+  s_red[tid] = c;
+  s_idx[tid] = tid;
+  __syncthreads();
+  for (int off = kReduceThreads / 2; off > 0; off >>= 1) {
+    if (tid < off) {
+      double o = s_red[tid + off];
+      int oi = s_idx[tid + off];
+      if (o < s_red[tid] || (o == s_red[tid] && oi < s_idx[tid])) { s_red[tid] = o; s_idx[tid] = oi; }
+    }
+    __syncthreads();
+  }
+  const double beta = s_red[0];
+  const int amin = s_idx[0];
+  __syncthreads();
+  // ---- weights and their sum (fixed-order tree)
+  const double w = tid < n ? exp(-a.sampler->lambda_inv * (c - beta)) : 0.0;
+  s_w[tid] = w;
+  s_red[tid] = w;
+  __syncthreads();
+  for (int off = kReduceThreads / 2; off > 0; off >>= 1) {
+    if (tid < off) s_red[tid] += s_red[tid + off];
+    __syncthreads();
+  }
+  const double eta = s_red[0];
+  // ---- weighted post-clamp noise: thread (t, g) sums samples g, g+G, ... of the chunk for step t  (T <= 128)
+  const int G = kReduceThreads / T;
+  if (tid < G * T) {
+    const int t = tid % T, g = tid / T;
+    double acc[NU];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) acc[i] = 0.0;
+    for (int j = g; j < n; j += G) {
+      const double wj = s_w[j];
+      if (wj == 0.0) continue;  // exp underflow: contributes exactly nothing
+      double u[NU], npost[NU];
+      sample_action<double, NU>(a.src, sp, Ush + t * kMaxNu, k0 + j, t, u, npost);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) acc[i] = __fma_rn(wj, npost[i], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NU; ++i) s_acc[tid * NU + i] = acc[i];
+  }
+  __syncthreads();
+  tampc_partial& out = a.partials[blockIdx.x];
+  for (int i = tid; i < T * NU; i += kReduceThreads) {
+    const int t = i / NU, d = i % NU;
+    double sum = 0.0;
+    for (int g = 0; g < G; ++g) sum += s_acc[(g * T + t) * NU + d];
+    out.wsum[t * NU + d] = sum;
+  }
+  if (tid == 0) {
+    out.beta = beta;
+    out.eta = eta;
+    out.argmin = (int64_t)a.src.sample_offset + k0 + amin;
+    out.count = n;
+  }
+}
+
+struct CombineArgs {
+  const tampc_partial* partials;
+  int n_partials;
+  const SamplerD* sampler;
+  const double* U;       // nominal BEFORE the shift
+  int T, nu;
+  int finalize;          // 1: write U_out / action / stats; 0: write one merged tampc_partial to partial_out
+  double* U_out;         // (T, nu) updated nominal sequence
+  double* action_out;    // (nu,) = U_out[0]
+  double* stats_out;     // beta, eta, argmin
+  tampc_partial* partial_out;
+};
+
+constexpr int kCombineThreads = 512;
+
+__global__ void __launch_bounds__(kCombineThreads) combine_kernel(const CombineArgs a) {
+  __shared__ double s_beta;
+  __shared__ double s_eta;
+  __shared__ long long s_arg;
+  const int tid = threadIdx.x;
+  const double li = a.sampler->lambda_inv;
+  if (tid == 0) {
+    double beta = a.partials[0].beta;
+    long long arg = a.partials[0].argmin;
+    for (int p = 1; p < a.n_partials; ++p) {
+      double b = a.partials[p].beta;
+      long long g = a.partials[p].argmin;
+      if (b < beta || (b == beta && g < arg)) { beta = b; arg = g; }
+    }
+    double eta = 0.0;
+    for (int p = 0; p < a.n_partials; ++p) eta = __fma_rn(exp(-li * (a.partials[p].beta - beta)), a.partials[p].eta, eta);
+    s_beta = beta;
+    s_eta = eta;
+    s_arg = arg;
+  }
+  __syncthreads();
+  const double beta = s_beta, eta = s_eta;
+  const int n = a.T * a.nu;
+  for (int i = tid; i < n; i += kCombineThreads) {
+    double sum = 0.0;
+    for (int p = 0; p < a.n_partials; ++p) {
+      const double s = exp(-li * (a.partials[p].beta - beta));
+      if (s != 0.0) sum = __fma_rn(s, a.partials[p].wsum[i], sum);
+    }
+    if (a.finalize) {
+      const int t = i / a.nu, d = i % a.nu, ts = t + 1;
+      const double base = ts < a.T ? a.U[ts * a.nu + d] : a.sampler->u_init[d];
+      const double v = base + sum / eta;
+      a.U_out[i] = v;
+      if (t == 0) a.action_out[d] = v;
+    } else {
+      a.partial_out->wsum[i] = sum;
+    }
+  }
+  if (tid == 0) {
+    if (a.finalize) {
+      a.stats_out[0] = beta;
+      a.stats_out[1] = eta;
+      a.stats_out[2] = (double)s_arg;
+    } else {
+      long long cnt = 0;
+      for (int p = 0; p < a.n_partials; ++p) cnt += a.partials[p].count;
+      a.partial_out->beta = beta;
+      a.partial_out->eta = eta;
+      a.partial_out->argmin = s_arg;
+      a.partial_out->count = cnt;
+    }
+  }
+}
+
+// ExperimentalMPPI.perturbed_action (K, T, nu), regenerated on request (tampc/env/pybullet_sim.py:127 reads it)
+struct PerturbedArgs {
+  const SamplerD* sampler;
+  const double* U;  // nominal the rollout used, BEFORE the shift
+  SampleSrc src;
+  int K_local;
+  double* out;
+};
+
+template <int NU>
+__global__ void perturbed_kernel(const PerturbedArgs a) {
+  __shared__ SamplerS<double> sp;
+  stage_sampler<double>(sp, *a.sampler, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int T = a.src.T;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)a.K_local * T) return;
+  const int k = (int)(i / T), t = (int)(i % T), ts = t + 1;
+  double Ut[NU], u[NU], npost[NU];
+#pragma unroll
+  for (int d = 0; d < NU; ++d) Ut[d] = ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d];
+  sample_action<double, NU>(a.src, sp, Ut, k, t, u, npost);
+#pragma unroll
+  for (int d = 0; d < NU; ++d) a.out[i * NU + d] = u[d];
+}
+
+}  // namespace tampc

@@ -1,0 +1,165 @@
+// rollout_kernel.cuh — the fused K x T rollout kernel (one launch per MPPI command).
+//
+// Replaces ExperimentalMPPI._compute_total_cost_batch + _compute_rollout_costs
+// (tampc/controller/controller.py:340-402): every thread owns S samples, keeps their state in registers for the
+// whole horizon, and writes one float64 cost per sample; no trajectory is written unless states_out is given
+// (the reference stacks M*K*T*nx float64 states, controller.py:367-373).
+#pragma once
+#include "device_common.cuh"
+
+namespace tampc {
+
+struct RolloutArgs {
+  const void* weights;  // packed network block in the kernel's network type
+  int n_weight_elems;
+  double slope;
+  const tampc_cost_desc* cost;
+  const SamplerD* sampler;
+  const double* U;      // nominal sequence (T, nu) BEFORE the shift
+  int shift;            // 1: step t uses U[t+1] (u_init at the tail) = MPPI.command's roll; 0: U[t]
+  const double* state;  // (nx,) start state shared by all samples
+  SampleSrc src;
+  int K_local;
+  double* cost_out;     // (K_local,)
+  double* states_out;   // optional (K_local, T, nx)
+  uint32_t wrap_mask;
+  int has_guard;
+  double bad_norm;
+};
+
+template <typename T> __host__ __device__ constexpr size_t align16(size_t n) { return (n + 15) & ~size_t(15); }
+
+template <class Model, typename NT, typename ST>
+struct RolloutSmem {
+  static constexpr size_t kWeights = 0;
+  static constexpr size_t kCost = align16<int>(sizeof(NT) * Model::kElems);
+  static constexpr size_t kSampler = kCost + align16<int>(sizeof(CostS<ST>));
+  static constexpr size_t kU = kSampler + align16<int>(sizeof(SamplerS<ST>));
+  static __host__ __device__ constexpr size_t bytes(int T) { return kU + align16<int>(sizeof(ST) * (size_t)T * kMaxNu); }
+};
+
+template <class Model, typename NT, typename ST, int S>
+__global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
+  constexpr int NX = Model::NX, NU = Model::NU;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using L = RolloutSmem<Model, NT, ST>;
+  NT* w = reinterpret_cast<NT*>(smem_raw + L::kWeights);
+  CostS<ST>& cs = *reinterpret_cast<CostS<ST>*>(smem_raw + L::kCost);
+  SamplerS<ST>& sp = *reinterpret_cast<SamplerS<ST>*>(smem_raw + L::kSampler);
+  ST* Ush = reinterpret_cast<ST*>(smem_raw + L::kU);  // [T][kMaxNu] shifted nominal sequence
+
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int T = a.src.T;
+  {  // ---- stage weights (16-byte copies), constants and the (shifted) nominal sequence
+    const int4* gw = reinterpret_cast<const int4*>(a.weights);
+    int4* sw = reinterpret_cast<int4*>(w);
+    const int n16 = (int)((sizeof(NT) * (size_t)a.n_weight_elems) / 16);
+    for (int i = tid; i < n16; i += nthr) sw[i] = gw[i];
+    stage_cost<ST>(cs, *a.cost, tid, nthr);
+    stage_sampler<ST>(sp, *a.sampler, tid, nthr);
+    for (int i = tid; i < T * NU; i += nthr) {
+      int t = i / NU, d = i % NU;
+      int ts = t + a.shift;
+      Ush[t * kMaxNu + d] = (ST)(ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d]);
+    }
+  }
+  __syncthreads();
+
+  const int g = blockIdx.x * nthr + tid;
+  int k[S];
+  bool live[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    int kk = g * S + s;
+    live[s] = kk < a.K_local;
+    k[s] = live[s] ? kk : a.K_local - 1;  // idle lanes recompute the last sample, never write
+  }
+
+  ST x[S][NX];
+  ST cost[S], pert[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[s][i] = (ST)a.state[i];
+    cost[s] = (ST)0;
+    pert[s] = (ST)0;
+  }
+  const NT slope = (NT)a.slope;
+  const ST bad2 = (ST)(a.bad_norm * a.bad_norm);
+
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    ST u[S][NU];
+    bool bad[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      ST npost[NU];
+      pert[s] += sample_action<ST, NU>(a.src, sp, Ush + t * kMaxNu, k[s], t, u[s], npost);
+      bad[s] = false;
+      if (a.has_guard) {  // OnlineMPC._apply_dynamics bad-state hack (online_controller.py:62-66)
+        ST n2 = (ST)0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) n2 = t_fma(x[s][i], x[s][i], n2);
+        bad[s] = n2 > bad2;
+        if (bad[s]) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) x[s][i] = (ST)0;
+#pragma unroll
+          for (int i = 0; i < NU; ++i) u[s][i] = (ST)0;
+        }
+      }
+    }
+    Model::template predict<ST, S>(w, slope, x, u);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        if ((a.wrap_mask >> i) & 1u) x[s][i] = angle_normalize<ST>(x[s][i]);  // constrain_state
+        if (bad[s]) x[s][i] = (ST)0;                                           // next_state[bad] = state[bad] (= 0)
+      }
+      cost[s] += running_cost<ST, NX, NU>(cs, x[s], u[s]);
+      if (a.states_out != nullptr && live[s]) {
+        double* so = a.states_out + ((size_t)k[s] * T + t) * NX;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) so[i] = (double)x[s][i];
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    ST total = cost[s] + terminal_cost<ST, NX>(cs, x[s]);
+    total += pert[s];
+    if (live[s]) a.cost_out[k[s]] = (double)total;
+  }
+}
+
+// host-callable launcher signature shared by all variants
+typedef cudaError_t (*rollout_launch_fn)(const RolloutArgs& a, int block, cudaStream_t stream);
+
+template <class Model, typename NT, typename ST, int S>
+cudaError_t launch_rollout(const RolloutArgs& a, int block, cudaStream_t stream) {
+  auto kern = rollout_kernel<Model, NT, ST, S>;
+  const size_t smem = RolloutSmem<Model, NT, ST>::bytes(a.src.T);
+  static size_t configured = 0;  // per instantiation
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const int per_block = block * S;
+  const int grid = (a.K_local + per_block - 1) / per_block;
+  kern<<<grid, block, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// One dynamics shape = the set of kernels compiled for it.
+struct ModelVariant {
+  const char* name;
+  int kind, nx, nu;
+  int dims[12];            // kind-specific layer widths, see match() in mppi_api.cu
+  int elems_f32, elems_f64;
+  int macs;
+  rollout_launch_fn f64_s1, mixed_s1, mixed_s2, f32_s1, f32_s2;
+};
+
+}  // namespace tampc

@@ -1,0 +1,13 @@
+#include "variants.cuh"
+namespace tampc {
+const ModelVariant* variant_mlp_5_3_32() {
+  static const ModelVariant v = make_variant<ModelMlp<float, 5, 3, 32, 32>, ModelMlp<double, 5, 3, 32, 32>, true>(
+      "mlp_nx5_nu3_h32-32", TAMPC_DYN_MLP, {32, 32});
+  return &v;
+}
+const ModelVariant* variant_pendulum() {
+  static const ModelVariant v = make_variant<ModelPendulum<float>, ModelPendulum<double>, true>(
+      "pendulum_analytic", TAMPC_DYN_PENDULUM, {});
+  return &v;
+}
+}  // namespace tampc

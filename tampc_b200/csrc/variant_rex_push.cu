@@ -1,0 +1,9 @@
+#include "variants.cuh"
+namespace tampc {
+const ModelVariant* variant_rex_push() {
+  static const ModelVariant v = make_variant<ModelRex<float, 5, 3, 16, 32, 5, 32, 32, 5, 16, 32>,
+                                             ModelRex<double, 5, 3, 16, 32, 5, 32, 32, 5, 16, 32>, true>(
+      "rex_nx5_nu3_e16-32-5_d32-32-5_c16-32", TAMPC_DYN_REX, {16, 32, 5, 32, 32, 5, 16, 32});
+  return &v;
+}
+}  // namespace tampc

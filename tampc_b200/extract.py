@@ -97,6 +97,28 @@ def _is_invariant_transformer(t):
     return hasattr(t, 'tsf') and hasattr(t.tsf, 'xu_to_z') and hasattr(t.tsf, 'get_dx')
 
 
+_PROBE_CACHE = {}
+
+
+def _cached_probe(fn):
+    """Probing costs a few host milliseconds; the env callables never change, so remember the answer per callable
+    (the cache holds a reference to the callable, which keeps its id unique)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(f, n):
+        key = (fn.__name__, id(getattr(f, '__func__', f)), id(getattr(f, '__self__', None)), n)
+        hit = _PROBE_CACHE.get(key)
+        if hit is not None:
+            return hit[1]
+        val = fn(f, n)
+        _PROBE_CACHE[key] = (f, val)
+        return val
+
+    return wrapper
+
+
+@_cached_probe
 def probe_wrap_dims(constrain_state, nx):
     """Which state dims `constrain_state` passes through angle_normalize (push_main.py:190-193)."""
     if constrain_state is None:
@@ -120,6 +142,7 @@ def probe_wrap_dims(constrain_state, nx):
     return tuple(dims)
 
 
+@_cached_probe
 def probe_ang_dims(compare_to_goal, nx):
     """Which dims of `compare_to_goal(x, goal)` are single-wrap angular differences (block_push.py:954-960)."""
     dims = []
@@ -148,6 +171,7 @@ def probe_ang_dims(compare_to_goal, nx):
     return tuple(dims)
 
 
+@_cached_probe
 def probe_dist_scale(state_dist, nx):
     """`state_dist(diff)` as a weighted 2-norm: returns s with dist = ||diff * s|| (block_push.py:663-666)."""
     s = np.zeros(nx)
@@ -163,6 +187,7 @@ def probe_dist_scale(state_dist, nx):
     return s
 
 
+@_cached_probe
 def probe_usim_dims(u_similarity, nu):
     """`u_similarity(u1,u2)` as cosine similarity over a subset of action dims, clamped to [0,1]."""
     if u_similarity is None:

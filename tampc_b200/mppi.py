@@ -1,0 +1,298 @@
+"""B200MPPI — drop-in for the `pytorch_mppi.MPPI` / `ExperimentalMPPI` object that tampc's controllers hold as
+`ctrl.mpc` (tampc/controller/controller.py:316-435; plug point :418-421; methods and attributes touched from
+outside listed in SURVEY.md §8b).
+
+The object keeps the reference's surface — `command(state)`, `reset()`, `get_rollouts(state)`,
+`change_horizon(T)`, `_compute_rollout_costs(actions)`, attributes `K, T, U, nx, nu, M, lambda_, noise_*,
+running_cost, terminal_state_cost, cost_total, omega, perturbed_action, state, d, dtype` — but the rollout and the
+softmax update run in the hand-written sm_100a kernels behind the C ABI of include/tampc_mppi.h.  Tensors at the
+API are float64 torch tensors on the host, like the reference's `self.dtype = torch.double`
+(controller.py:197); conversion happens at the edge.
+
+There is no CPU path: constructing a B200MPPI without the CUDA library or a B200 raises.
+"""
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import extract
+from . import spec as S
+
+
+class TampcError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("libtampc_mppi error {}: {}".format(code, message))
+        self.code = code
+
+
+def shard_bounds(K, rank, world):
+    """Contiguous K-shard of `rank`: sizes differ by at most one; offsets are a function of (K, world) only."""
+    base, rem = divmod(K, world)
+    lo = rank * base + min(rank, rem)
+    return lo, base + (1 if rank < rem else 0)
+
+
+class B200MPPI:
+    def __init__(self, spec: S.RolloutSpec, precision='mixed', device=0, seed=1234, max_horizon=None,
+                 rank=0, world_size=1, process_group=None, controller=None, U_init=None):
+        """
+        :param spec: flattened problem (dynamics, cost, sampler constants)
+        :param precision: 'f64' (reference arithmetic), 'mixed' (float32 networks, float64 state/cost), 'f32'
+        :param rank, world_size, process_group: K-sharding over torch.distributed ranks (one process per GPU);
+               every rank holds the full U and obtains bitwise-identical updates
+        :param controller: live tampc controller to re-read the cost program from on every command()
+        """
+        self._lib = L.load()
+        self.spec = spec
+        self.precision = precision
+        self.device_index = device
+        self.rank, self.world_size, self.group = rank, world_size, process_group
+        self._ctrl = controller
+        s = spec.sampler
+        self.K, self.T = s.K, s.T
+        self.nx, self.nu = spec.dynamics.nx, s.nu
+        self.M = s.rollout_samples
+        self.rollout_var_cost, self.rollout_var_discount = s.rollout_var_cost, s.rollout_var_discount
+        self.lambda_ = s.lambda_
+        self.dtype = torch.double
+        self.d = torch.device('cpu')  # tensors at the API live on the host, like MPC.command's numpy edge
+        self.noise_mu = torch.from_numpy(s.noise_mu.copy())
+        self.noise_sigma = torch.from_numpy(s.noise_sigma.copy())
+        self.noise_sigma_inv = torch.from_numpy(s.noise_sigma_inv.copy())
+        self.noise_dist = torch.distributions.MultivariateNormal(self.noise_mu, covariance_matrix=self.noise_sigma)
+        self.u_min = None if s.u_min is None else torch.from_numpy(s.u_min.copy())
+        self.u_max = None if s.u_max is None else torch.from_numpy(s.u_max.copy())
+        self.u_init = torch.from_numpy(s.u_init.copy())
+        self.sample_null_action = s.sample_null_action
+        self.u_per_command = 1
+        self.running_cost = None
+        self.terminal_state_cost = None
+        self.state = None
+        self.step_dependency = True
+
+        self.sample_offset, self.K_local = shard_bounds(self.K, rank, world_size)
+        if self.K_local < 1:
+            raise ValueError("rank {} of {} has no samples (K={})".format(rank, world_size, self.K))
+        stream = None
+        if world_size > 1:
+            torch.cuda.set_device(device)
+            stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        cfg = L.mppi_config(s, self.nx, precision, device=device, sample_offset=self.sample_offset,
+                            num_local=self.K_local, max_horizon=max_horizon or max(s.T, 64), seed=seed, stream=stream)
+        self.max_horizon = cfg.max_horizon
+        h = C.c_void_p()
+        rc = self._lib.tampc_mppi_create(C.byref(cfg), C.byref(h))
+        if rc != L.OK:
+            raise TampcError(rc, self._lib.tampc_mppi_last_error(None).decode())
+        self._h = h
+        self._cfg = cfg
+        self._cost_spec = None
+        self._dyn_spec = None
+        self.set_dynamics(spec.dynamics)
+        self.set_cost(spec.cost)
+        if U_init is None:
+            U_init = self.noise_dist.sample((self.T,))
+        self.U = U_init
+        self._gather = None
+        self._last_noise = None
+        self._cost_cache = None
+        self._probe_cache = {}
+
+    # ------------------------------------------------------------------ construction from a live controller
+    @classmethod
+    def from_controller(cls, ctrl, **kwargs):
+        """Build from a tampc MPPI_MPC / OnlineMPPI controller (reads ctrl.mpc for the sampler constants)."""
+        spec = extract.spec_from_controller(ctrl)
+        old = ctrl.mpc
+        obj = cls(spec, controller=ctrl, U_init=old.U.detach().to('cpu', torch.double), **kwargs)
+        obj.running_cost = old.running_cost
+        obj.terminal_state_cost = old.terminal_state_cost
+        return obj
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc != L.OK:
+            raise TampcError(rc, self._lib.tampc_mppi_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self._lib.tampc_mppi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_dynamics(self, dyn: S.DynamicsSpec):
+        desc, params = L.model_desc(dyn)
+        self._check(self._lib.tampc_mppi_set_model(self._h, C.byref(desc), L.dptr(params) if params.size else None,
+                                                   params.size))
+        self._dyn_spec = dyn
+        self.spec.dynamics = dyn
+
+    def set_cost(self, cost: S.CostSpec):
+        desc = L.cost_desc(cost)
+        self._check(self._lib.tampc_mppi_set_cost(self._h, C.byref(desc)))
+        self._cost_spec = cost
+        self.spec.cost = cost
+
+    def _refresh_from_controller(self):
+        """Re-read the mutable parts of the problem from the bound controller: cost program (trap set, trap weight,
+        goal, recovery sets / MAB weights: online_controller.py:353,400-402,416-418,461-478)."""
+        if self._ctrl is None:
+            return
+        cost = extract.cost_from_controller(self._ctrl, self.running_cost, self.terminal_state_cost)
+        self.set_cost(cost)
+
+    # ------------------------------------------------------------------ nominal sequence
+    @property
+    def U(self):
+        out = np.empty((self.T, self.nu))
+        self._check(self._lib.tampc_mppi_get_nominal(self._h, L.dptr(out)))
+        return torch.from_numpy(out)
+
+    @U.setter
+    def U(self, value):
+        a = np.ascontiguousarray(torch.as_tensor(value).detach().to('cpu', torch.double).numpy().reshape(-1, self.nu))
+        if a.shape[0] > self.max_horizon:
+            raise ValueError("horizon {} exceeds max_horizon {}".format(a.shape[0], self.max_horizon))
+        self._check(self._lib.tampc_mppi_set_nominal(self._h, L.dptr(a), a.shape[0]))
+        self.T = a.shape[0]
+
+    def change_horizon(self, horizon):
+        """ExperimentalMPPI.change_horizon (controller.py:323-330): truncate, or pad with fresh noise samples."""
+        U = self.U
+        if horizon < self.T:
+            U = U[:horizon]
+        elif horizon > self.T:
+            pad = self.noise_dist.sample((horizon,))
+            pad[:self.T] = U
+            U = pad
+        self.U = U
+
+    def reset(self):
+        """MPPI.reset: U = noise_dist.sample((T,))."""
+        self.U = self.noise_dist.sample((self.T,))
+
+    # ------------------------------------------------------------------ command
+    def _state_array(self, state):
+        if not torch.is_tensor(state):
+            state = torch.as_tensor(np.asarray(state))
+        self.state = state.detach().to('cpu', torch.double)
+        a = np.ascontiguousarray(self.state.numpy().reshape(-1))
+        if a.shape != (self.nx,):
+            raise ValueError("state must have {} entries (per-sample start states are not supported)".format(self.nx))
+        return a
+
+    def command(self, state, noise=None):
+        """MPPI.command(state) -> action (nu,) float64 tensor.
+
+        noise: optional (K,T,nu) draw N(mu, Sigma) to use instead of the on-device Philox stream — the equivalent of
+        patching `noise_dist.sample((K,T))` in the reference, used by the parity tests."""
+        self._refresh_from_controller()
+        x = self._state_array(state)
+        mode, nptr, local = L.NOISE_PHILOX, None, None
+        if noise is not None:
+            n = torch.as_tensor(noise).detach().to('cpu', torch.double).numpy()
+            if n.shape != (self.K, self.T, self.nu):
+                raise ValueError("noise must be (K,T,nu) = {}".format((self.K, self.T, self.nu)))
+            local = np.ascontiguousarray(n[self.sample_offset:self.sample_offset + self.K_local])
+            mode, nptr = L.NOISE_INJECTED, L.dptr(local)
+        action = np.empty(self.nu)
+        if self.world_size == 1:
+            self._check(self._lib.tampc_mppi_command(self._h, L.dptr(x), mode, nptr, L.dptr(action)))
+        else:
+            self._command_sharded(x, mode, nptr, action)
+        return torch.from_numpy(action)
+
+    def _command_sharded(self, x, mode, nptr, action):
+        """K-sharded command: local rollout + partial, one all_gather of tampc_partial (NCCL over NVLink), identical
+        combine on every rank."""
+        import torch.distributed as dist
+        if self._gather is None:
+            dev = torch.device('cuda', self.device_index)
+            self._gather = torch.zeros(self.world_size, L.PARTIAL_DOUBLES, dtype=torch.double, device=dev)
+            self._mine = torch.zeros(L.PARTIAL_DOUBLES, dtype=torch.double, device=dev)
+        self._check(self._lib.tampc_mppi_command_begin(self._h, L.dptr(x), mode, nptr, 0,
+                                                       C.c_void_p(self._mine.data_ptr())))
+        dist.all_gather_into_tensor(self._gather, self._mine, group=self.group)
+        self._check(self._lib.tampc_mppi_command_finish(self._h, C.c_void_p(self._gather.data_ptr()),
+                                                        self.world_size, L.dptr(action)))
+
+    # ------------------------------------------------------------------ results of the last command
+    def _query(self, what, n):
+        out = np.empty(n)
+        self._check(self._lib.tampc_mppi_query(self._h, what, L.dptr(out), n))
+        return out
+
+    @property
+    def cost_total(self):
+        """Per-sample total cost of the last rollout (this rank's shard when sharded)."""
+        return torch.from_numpy(self._query(L.Q_COST_TOTAL, self.K_local))
+
+    @property
+    def omega(self):
+        return torch.from_numpy(self._query(L.Q_OMEGA, self.K_local))
+
+    @property
+    def perturbed_action(self):
+        return torch.from_numpy(self._query(L.Q_PERTURBED, self.K_local * self.T * self.nu).reshape(self.K_local, self.T, self.nu))
+
+    @property
+    def noise(self):
+        """Post-clamp noise perturbed_action - U_shifted of the last command (controller.py:394)."""
+        raise NotImplementedError("query perturbed_action; the post-clamp noise is regenerated on the device")
+
+    @property
+    def stats(self):
+        s = self._query(L.Q_STATS, 4)
+        return {'beta': s[0], 'eta': s[1], 'argmin': int(s[2]), 'launches': int(s[3])}
+
+    # ------------------------------------------------------------------ other reference entry points
+    def get_rollouts(self, state, num_rollouts=1):
+        """MPPI.get_rollouts: (num_rollouts, T, nx) states reached by the current nominal U (controller.py:434-435)."""
+        x = self._state_array(state)
+        out = np.empty((self.T, self.nx))
+        self._check(self._lib.tampc_mppi_get_rollouts(self._h, L.dptr(x), L.dptr(out)))
+        return torch.from_numpy(out).unsqueeze(0).repeat(num_rollouts, 1, 1)
+
+    def _compute_rollout_costs(self, perturbed_actions, state=None):
+        """ExperimentalMPPI._compute_rollout_costs (controller.py:340-381): (cost_total (K,), states (M,K,T,nx),
+        actions (M,K,T,nu)) for caller-given actions.  M replicas of a deterministic model are identical, so M=1
+        is returned."""
+        self._refresh_from_controller()
+        a = np.ascontiguousarray(torch.as_tensor(perturbed_actions).detach().to('cpu', torch.double).numpy())
+        K, T, nu = a.shape
+        if K != self.K_local or nu != self.nu:
+            raise ValueError("actions must be (K,T,nu) with K={} nu={}".format(self.K_local, self.nu))
+        x = self._state_array(self.state if state is None else state)
+        cost = np.empty(K)
+        states = np.empty((K, T, self.nx))
+        self._check(self._lib.tampc_mppi_rollout_costs(self._h, L.dptr(x), L.dptr(a), T, L.dptr(cost), L.dptr(states)))
+        return torch.from_numpy(cost), torch.from_numpy(states).unsqueeze(0), torch.from_numpy(a).unsqueeze(0)
+
+    # kernel-only timing helpers (bench.py): inputs resident in HBM, no host copies, no synchronisation
+    def set_state_resident(self, state):
+        x = self._state_array(state)
+        self._check(self._lib.tampc_mppi_set_state_resident(self._h, L.dptr(x)))
+
+    def command_resident(self):
+        self._check(self._lib.tampc_mppi_command_resident(self._h, L.NOISE_PHILOX))
+
+    def synchronize(self):
+        self._check(self._lib.tampc_mppi_synchronize(self._h))
+
+
+def install(ctrl, **kwargs):
+    """Swap `ctrl.mpc` (an ExperimentalMPPI built at controller.py:418-421) for a B200MPPI bound to `ctrl`.
+
+    The controller's own state machine (trap detection, recovery, MAB; online_controller.py:437-515) is untouched:
+    it keeps assigning `ctrl.mpc.running_cost / terminal_state_cost`, calling `change_horizon` and `command`."""
+    mpc = B200MPPI.from_controller(ctrl, **kwargs)
+    ctrl.mpc = mpc
+    return mpc
