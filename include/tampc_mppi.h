@@ -218,6 +218,9 @@ TAMPC_API int tampc_mppi_synchronize(tampc_mppi* h);
  * Equivalent to command() minus the H2D of `state` and the D2H of the action. */
 TAMPC_API int tampc_mppi_command_resident(tampc_mppi* h, int32_t noise_mode);
 TAMPC_API int tampc_mppi_set_state_resident(tampc_mppi* h, const double* state);
+/* Only the fused rollout kernel of a resident command (no reduction, U untouched): what bench.py times for the
+ * roofline of the dominant kernel. */
+TAMPC_API int tampc_mppi_rollout_resident(tampc_mppi* h, int32_t noise_mode);
 
 #ifdef __cplusplus
 }

@@ -280,3 +280,25 @@ def sample_noise(spec: S.RolloutSpec, seed, K=None, T=None):
     g = torch.Generator().manual_seed(seed)
     eps = torch.randn(K, T, s.nu, dtype=DT, generator=g)
     return _t(s.noise_mu) + eps @ _t(s.noise_chol).T
+
+
+# ------------------------------------------------------------------------------------------------
+# K-sharded form of the softmax update (what the multi-GPU path computes)
+
+def shard_partial(spec: S.RolloutSpec, cost, noise_post, global_offset=0):
+    """One shard's contribution relative to ITS OWN minimum: (beta_g, eta_g, argmin_g (global index), W_g[T,nu])."""
+    beta = torch.min(cost)
+    w = torch.exp(-(1.0 / spec.sampler.lambda_) * (cost - beta))
+    return {'beta': float(beta), 'eta': float(w.sum()), 'argmin': int(torch.argmin(cost)) + global_offset,
+            'wsum': torch.einsum('k,kti->ti', w, noise_post)}
+
+
+def combine_partials(spec: S.RolloutSpec, partials, U_shifted):
+    """Merge shard partials in rank order with the log-sum-exp rescale s_g = exp(-(beta_g - beta)/lambda)."""
+    beta = min(p['beta'] for p in partials)
+    argmin = min(p['argmin'] for p in partials if p['beta'] == beta)
+    scale = [math.exp(-(1.0 / spec.sampler.lambda_) * (p['beta'] - beta)) for p in partials]
+    eta = sum(s * p['eta'] for s, p in zip(scale, partials))
+    wsum = sum(s * p['wsum'] for s, p in zip(scale, partials))
+    U_new = U_shifted + wsum / eta
+    return {'beta': beta, 'eta': eta, 'argmin': argmin, 'U': U_new, 'action': U_new[0].clone()}

@@ -726,6 +726,14 @@ TAMPC_API int tampc_mppi_command_resident(tampc_mppi* h, int32_t noise_mode) {
   return run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/1);
 }
 
+TAMPC_API int tampc_mppi_rollout_resident(tampc_mppi* h, int32_t noise_mode) {
+  if (!h) return TAMPC_ERR_INVALID;
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (noise_mode != kModePhilox && !h->d_noise) { h->err = "resident rollout with injected noise needs a previous upload"; return TAMPC_ERR_STATE; }
+  return launch_rollout_for(h, noise_mode, /*shift=*/1, h->d_U[h->cur], h->T, h->call + 1, false);
+}
+
 TAMPC_API int tampc_mppi_rollout_costs(tampc_mppi* h, const double* state, const double* actions, int32_t horizon, double* cost_out, double* states_out) {
   if (!h || !state || !actions || !cost_out) return TAMPC_ERR_INVALID;
   if (!h->has_model || !h->has_cost) { h->err = "set_model / set_cost first"; return TAMPC_ERR_STATE; }

@@ -37,7 +37,7 @@ def shard_bounds(K, rank, world):
 
 class B200MPPI:
     def __init__(self, spec: S.RolloutSpec, precision='mixed', device=0, seed=1234, max_horizon=None,
-                 rank=0, world_size=1, process_group=None, controller=None, U_init=None):
+                 rank=0, world_size=1, process_group=None, controller=None, U_init=None, use_torch_stream=False):
         """
         :param spec: flattened problem (dynamics, cost, sampler constants)
         :param precision: 'f64' (reference arithmetic), 'mixed' (float32 networks, float64 state/cost), 'f32'
@@ -77,9 +77,14 @@ class B200MPPI:
         if self.K_local < 1:
             raise ValueError("rank {} of {} has no samples (K={})".format(rank, world_size, self.K))
         stream = None
-        if world_size > 1:
+        self.torch_stream = None
+        if world_size > 1 or use_torch_stream:
+            # a torch-owned side stream shared with the library: NCCL collectives and torch.cuda.Event timing issued
+            # under `with torch.cuda.stream(self.torch_stream)` are ordered with the kernels (the legacy default
+            # stream has handle 0, which the C ABI reads as "create your own")
             torch.cuda.set_device(device)
-            stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            self.torch_stream = torch.cuda.Stream(device=device)
+            stream = C.c_void_p(self.torch_stream.cuda_stream)
         cfg = L.mppi_config(s, self.nx, precision, device=device, sample_offset=self.sample_offset,
                             num_local=self.K_local, max_horizon=max_horizon or max(s.T, 64), seed=seed, stream=stream)
         self.max_horizon = cfg.max_horizon
@@ -216,11 +221,13 @@ class B200MPPI:
         import torch.distributed as dist
         if self._gather is None:
             dev = torch.device('cuda', self.device_index)
-            self._gather = torch.zeros(self.world_size, L.PARTIAL_DOUBLES, dtype=torch.double, device=dev)
-            self._mine = torch.zeros(L.PARTIAL_DOUBLES, dtype=torch.double, device=dev)
+            with torch.cuda.stream(self.torch_stream):
+                self._gather = torch.zeros(self.world_size, L.PARTIAL_DOUBLES, dtype=torch.double, device=dev)
+                self._mine = torch.zeros(L.PARTIAL_DOUBLES, dtype=torch.double, device=dev)
         self._check(self._lib.tampc_mppi_command_begin(self._h, L.dptr(x), mode, nptr, 0,
                                                        C.c_void_p(self._mine.data_ptr())))
-        dist.all_gather_into_tensor(self._gather, self._mine, group=self.group)
+        with torch.cuda.stream(self.torch_stream):
+            dist.all_gather_into_tensor(self._gather, self._mine, group=self.group)
         self._check(self._lib.tampc_mppi_command_finish(self._h, C.c_void_p(self._gather.data_ptr()),
                                                         self.world_size, L.dptr(action)))
 
@@ -283,6 +290,10 @@ class B200MPPI:
 
     def command_resident(self):
         self._check(self._lib.tampc_mppi_command_resident(self._h, L.NOISE_PHILOX))
+
+    def rollout_resident(self):
+        """Only the fused rollout kernel (roofline timing)."""
+        self._check(self._lib.tampc_mppi_rollout_resident(self._h, L.NOISE_PHILOX))
 
     def synchronize(self):
         self._check(self._lib.tampc_mppi_synchronize(self._h))

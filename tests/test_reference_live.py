@@ -1,0 +1,90 @@
+"""CPU, only where /root/reference exists: spec extraction from the reference's live controllers and the oracle
+against the reference's own classes on fresh inputs (the committed goldens cover the GPU box)."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import ref_harness as rh  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not rh.available(), reason="reference tree not present (GPU box)")
+
+from oracle import mppi_oracle as O  # noqa: E402
+from tampc_b200 import extract, spec as S  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def push_ctrl():
+    torch.manual_seed(0)
+    ctrl, ds, env = rh.build_task('push', num_samples=96, rollout_samples=2, horizon=15)
+    ctrl.set_goal(np.array([0.55, -0.65, 0., 0., 0.]))
+    return ctrl
+
+
+def _run_ref(ctrl, spec, state, U0, noise):
+    mpc = ctrl.mpc
+    mpc.U = U0.clone()
+    orig = mpc.noise_dist.sample
+    mpc.noise_dist.sample = lambda shape=(): noise.clone() if tuple(shape) == (spec.sampler.K, spec.sampler.T) else orig(shape)
+    try:
+        with torch.no_grad():
+            return mpc.command(state.clone())
+    finally:
+        mpc.noise_dist.sample = orig
+
+
+def test_extraction_reads_the_reference_objects(push_ctrl):
+    spec = extract.spec_from_controller(push_ctrl)
+    d, c = spec.dynamics, spec.cost
+    assert d.kind == S.DYN_REX and d.macs_per_step == 3523 and d.wrap_dims == (2,) and d.bad_state_norm == 1e5
+    assert d.encoder.dims == [8, 16, 32, 5] and d.net.dims == [5, 32, 32, 5] and d.decoder.dims == [2, 16, 32, 25]
+    assert c.ang_dims == (2,) and c.usim_dims == (0, 2) and c.terminal_multiplier == 50.0
+    np.testing.assert_allclose(c.dist_scale, [1, 1, math.sqrt(0.3 ** 2 * 2 / 12), 0, 0])
+    assert spec.sampler.lambda_ == 0.01 and spec.sampler.rollout_samples == 2
+
+
+@pytest.mark.parametrize('seed', [3, 4])
+def test_oracle_matches_live_reference_on_fresh_inputs(push_ctrl, seed):
+    ctrl = push_ctrl
+    g = torch.Generator().manual_seed(seed)
+    ctrl.trap_set.clear()
+    for _ in range(seed):
+        ctrl.trap_set.append((torch.randn(5, dtype=torch.double, generator=g) * 0.5,
+                              torch.randn(3, dtype=torch.double, generator=g)))
+    ctrl.trap_set_weight = 0.1 * seed
+    spec = extract.spec_from_controller(ctrl)
+    state = torch.randn(5, dtype=torch.double, generator=g) * 0.4
+    U0 = torch.rand(spec.sampler.T, 3, dtype=torch.double, generator=g) * 0.5
+    noise = O.sample_noise(spec, seed)
+    a_ref = _run_ref(ctrl, spec, state, U0, noise)
+    out = O.command(spec, state, U0, noise)
+    rel = ((out['cost_total'] - ctrl.mpc.cost_total).abs() / ctrl.mpc.cost_total.abs()).max().item()
+    assert rel < 1e-12 and out['argmin'] == int(ctrl.mpc.cost_total.argmin())
+    assert (out['action'] - a_ref).abs().max().item() < 1e-12
+
+
+def test_unrecognised_callbacks_are_errors_not_fallbacks(push_ctrl):
+    ctrl = push_ctrl
+    with pytest.raises(extract.UnsupportedSpec):
+        extract.cost_from_controller(ctrl, running_cost=lambda x, u: x.sum(dim=1))
+    with pytest.raises(extract.UnsupportedSpec):
+        extract.probe_dist_scale(lambda d: d.abs().sum(dim=1), 5)
+    with pytest.raises(extract.UnsupportedSpec):
+        extract.probe_wrap_dims(lambda s: s * 2, 5)
+    with pytest.raises(extract.UnsupportedSpec):
+        extract.mlp_from_module(torch.nn.Sequential(torch.nn.Linear(3, 3), torch.nn.Tanh(), torch.nn.Linear(3, 1)))
+
+
+def test_peg_env_functions_probe_correctly():
+    ctrl, ds, env = rh.build_task('peg', num_samples=16, rollout_samples=2)
+    ctrl.set_goal(np.array([0, 0.2, 0.19, 0, 0]))
+    spec = extract.spec_from_controller(ctrl)
+    assert spec.cost.ang_dims == () and spec.cost.usim_dims == (0, 1) and spec.dynamics.wrap_dims == ()
+    np.testing.assert_array_equal(spec.cost.dist_scale, [1, 1, 0, 0, 0])
+    assert spec.dynamics.macs_per_step == 3507
