@@ -59,9 +59,12 @@ typedef enum tampc_status {
 
 /* arithmetic of the rollout kernel */
 typedef enum tampc_precision {
-  TAMPC_PREC_F64 = 0,   /* networks, state and cost in float64 — the reference's arithmetic (controller.py:197) */
+  TAMPC_PREC_F64 = 0,   /* networks, state and cost in float64 — the reference's arithmetic (controller.py:197);
+                           network layers run on the FP64 tensor pipe (DMMA) where the shape has an mma kernel */
   TAMPC_PREC_MIXED = 1, /* networks in float32 (packed FFMA2), state + cost accumulation in float64 */
-  TAMPC_PREC_F32 = 2    /* everything in float32 */
+  TAMPC_PREC_F32 = 2,   /* everything in float32 */
+  TAMPC_PREC_TF32X3 = 3 /* networks on the tensor cores as 3xTF32 (error-compensated split, ~float32 accuracy),
+                           state + cost in float64 */
 } tampc_precision;
 
 /* where the per-sample action perturbations come from */

@@ -40,19 +40,23 @@ struct SamplerS {
   int has_bounds, null_action;
 };
 
-template <typename T>
+// Cost program staged in shared memory.  ST = state type (positions are differenced in the state's precision),
+// CT = arithmetic type of the cost terms (float for the float32-network modes, double for F64).
+template <typename ST, typename CT>
 struct CostS {
   int kind, use_trap, n_traps, has_terminal, n_sets;
   int set_size[TAMPC_MAX_GOAL_SETS];
   uint32_t ang_mask, usim_mask;
-  T dist_scale[kMaxNx];
-  T Q[kMaxNx * kMaxNx], R[kMaxNu * kMaxNu], goal[kMaxNx];
-  T trap_x[TAMPC_MAX_TRAPS][kMaxNx], trap_u[TAMPC_MAX_TRAPS][kMaxNu];
-  T trap_u_norm[TAMPC_MAX_TRAPS];  // max(||trap_u[usim dims]||, eps), precomputed once per CTA
-  T trap_weight, terminal_multiplier;
-  T set_goals[TAMPC_MAX_GOAL_SETS][TAMPC_MAX_SET_GOALS][kMaxNx];
-  T set_weight[TAMPC_MAX_GOAL_SETS];
-  T recovery_scale;
+  ST goal[kMaxNx];
+  ST trap_x[TAMPC_MAX_TRAPS][kMaxNx];
+  ST set_goals[TAMPC_MAX_GOAL_SETS][TAMPC_MAX_SET_GOALS][kMaxNx];
+  CT dist_scale[kMaxNx];
+  CT Q[kMaxNx * kMaxNx], R[kMaxNu * kMaxNu];
+  CT trap_u[TAMPC_MAX_TRAPS][kMaxNu];
+  CT trap_u_norm[TAMPC_MAX_TRAPS];  // max(||trap_u[usim dims]||, eps), precomputed once per CTA
+  CT trap_weight, terminal_multiplier;
+  CT set_weight[TAMPC_MAX_GOAL_SETS];
+  CT recovery_scale;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -70,12 +74,19 @@ __device__ __forceinline__ double t_max(double a, double b) { return fmax(a, b);
 __device__ __forceinline__ float t_sin(float a) { return sinf(a); }
 __device__ __forceinline__ double t_sin(double a) { return sin(a); }
 
-// torch.remainder(a + pi, 2pi) - pi  (math_utils.angle_normalize; scripts/push_main.py:192)
+__device__ __forceinline__ float t_floor(float a) { return floorf(a); }
+__device__ __forceinline__ double t_floor(double a) { return floor(a); }
+
+// torch.remainder(a + pi, 2pi) - pi  (math_utils.angle_normalize; scripts/push_main.py:192), computed as
+// y - 2pi*floor(y/2pi) with one correction step instead of the (slow, looping) fmod; agrees with the fmod form
+// to an ulp of 2pi.
 template <typename T>
 __device__ __forceinline__ T angle_normalize(T a) {
   const T two_pi = (T)(2.0 * kPi);
-  T r = t_fmod(a + (T)kPi, two_pi);
-  if (r != (T)0 && r < (T)0) r += two_pi;
+  const T y = a + (T)kPi;
+  T r = t_fma(-t_floor(y * (T)(1.0 / (2.0 * kPi))), two_pi, y);
+  if (r < (T)0) r += two_pi;
+  else if (r >= two_pi) r -= two_pi;
   return r - (T)kPi;
 }
 
@@ -111,10 +122,12 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t call, uin
   float u2 = __fmaf_rn((float)r.z, s, 0.5f * s), u3 = __fmaf_rn((float)r.w, s, 0.5f * s);
   u0 = fminf(u0, 0.99999994f);
   u2 = fminf(u2, 0.99999994f);
-  float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+  // fast intrinsics (MUFU): |error| ~ 2^-21, far below anything a Gaussian perturbation can resolve; the phase is
+  // taken in [-pi, pi) where __sincosf is most accurate (a uniform phase shifted by pi is still uniform)
+  float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
   float s0, c0, s1, c1;
-  sincospif(2.0f * u1, &s0, &c0);
-  sincospif(2.0f * u3, &s1, &c1);
+  __sincosf(6.2831853071795865f * u1 - 3.14159265358979324f, &s0, &c0);
+  __sincosf(6.2831853071795865f * u3 - 3.14159265358979324f, &s1, &c1);
   z[0] = r0 * c0;
   z[1] = r0 * s0;
   z[2] = r1 * c1;
@@ -398,66 +411,70 @@ struct ModelPendulum {
 
 // ---------------------------------------------------------------------------------------------
 // cost
-template <typename T, int NX>
-__device__ __forceinline__ void state_diff(const CostS<T>& c, const T (&x)[NX], const T* __restrict__ goal, T (&d)[NX]) {
+// env.state_difference: x - goal in the state's precision, single-wrap angular dims, then handed to the cost type
+template <typename ST, typename CT, int NX>
+__device__ __forceinline__ void state_diff(uint32_t ang_mask, const ST (&x)[NX], const ST* __restrict__ goal, CT (&d)[NX]) {
 #pragma unroll
   for (int i = 0; i < NX; ++i) {
-    T v = x[i] - goal[i];
-    if ((c.ang_mask >> i) & 1u) v = angular_wrap_once(v);
-    d[i] = v;
+    ST v = x[i] - goal[i];
+    if ((ang_mask >> i) & 1u) v = angular_wrap_once(v);
+    d[i] = (CT)v;
   }
 }
 
 // squared state distance  ||diff * dist_scale||^2.  The reference takes the norm and squares it again
 // (cost.py:135,175); the sqrt/square round trip (<= 2 ulp) is not reproduced.
-template <typename T, int NX>
-__device__ __forceinline__ T dist_sq(const CostS<T>& c, const T (&d)[NX]) {
-  T s = (T)0;
+template <typename CT, int NX>
+__device__ __forceinline__ CT dist_sq(const CT* __restrict__ dist_scale, const CT (&d)[NX]) {
+  CT s = (CT)0;
 #pragma unroll
   for (int i = 0; i < NX; ++i) {
-    T v = d[i] * c.dist_scale[i];
+    CT v = d[i] * dist_scale[i];
     s = t_fma(v, v, s);
   }
   return s;
 }
 
-template <typename T, int NX>
-__device__ __forceinline__ T quad_form_x(const CostS<T>& c, const T (&d)[NX]) {
-  T total = (T)0;
+template <typename CT, int NX>
+__device__ __forceinline__ CT quad_form_x(const CT* __restrict__ Q, const CT (&d)[NX]) {
+  CT total = (CT)0;
 #pragma unroll
   for (int j = 0; j < NX; ++j) {
-    T col = (T)0;  // (d @ Q)_j
+    CT col = (CT)0;  // (d @ Q)_j
 #pragma unroll
-    for (int i = 0; i < NX; ++i) col = t_fma(d[i], c.Q[i * kMaxNx + j], col);
+    for (int i = 0; i < NX; ++i) col = t_fma(d[i], Q[i * kMaxNx + j], col);
     total = t_fma(col, d[j], total);
   }
   return total;
 }
 
 // running cost of (x_next, u)      [controller.py:248-249 -> cost.py:213-235]
-template <typename T, int NX, int NU>
-__device__ __forceinline__ T running_cost(const CostS<T>& c, const T (&x)[NX], const T (&u)[NU]) {
-  T d[NX];
+template <typename ST, typename CT, int NX, int NU>
+__device__ __forceinline__ CT running_cost(const CostS<ST, CT>& c, const ST (&x)[NX], const ST (&us)[NU]) {
+  CT d[NX];
   if (c.kind == TAMPC_COST_RECOVERY) {
-    T total = (T)0;
+    CT total = (CT)0;
     for (int j = 0; j < c.n_sets; ++j) {
-      T best = (T)0;
+      CT best = (CT)0;
       for (int g = 0; g < c.set_size[j]; ++g) {
-        state_diff<T, NX>(c, x, c.set_goals[j][g], d);
-        T v = dist_sq<T, NX>(c, d) * c.recovery_scale;
+        state_diff<ST, CT, NX>(c.ang_mask, x, c.set_goals[j][g], d);
+        CT v = dist_sq<CT, NX>(c.dist_scale, d) * c.recovery_scale;
         best = (g == 0) ? v : t_min(best, v);
       }
       total += best * c.set_weight[j];
     }
     return total;
   }
-  state_diff<T, NX>(c, x, c.goal, d);
-  T cost = quad_form_x<T, NX>(c, d);
+  CT u[NU];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) u[i] = (CT)us[i];
+  state_diff<ST, CT, NX>(c.ang_mask, x, c.goal, d);
+  CT cost = quad_form_x<CT, NX>(c.Q, d);
   {
-    T ru = (T)0;
+    CT ru = (CT)0;
 #pragma unroll
     for (int j = 0; j < NU; ++j) {
-      T col = (T)0;
+      CT col = (CT)0;
 #pragma unroll
       for (int i = 0; i < NU; ++i) col = t_fma(u[i], c.R[i * kMaxNu + j], col);
       ru = t_fma(col, u[j], ru);
@@ -466,20 +483,20 @@ __device__ __forceinline__ T running_cost(const CostS<T>& c, const T (&x)[NX], c
   }
   if (c.use_trap && c.n_traps > 0) {
     // ||u[usim dims]|| once per step
-    T un = (T)0;
+    CT un = (CT)0;
 #pragma unroll
     for (int i = 0; i < NU; ++i)
       if ((c.usim_mask >> i) & 1u) un = t_fma(u[i], u[i], un);
-    un = t_max(t_sqrt(un), (T)kCosSimEps);
-    T tsum = (T)0;
+    un = t_max(t_sqrt(un), (CT)kCosSimEps);
+    CT tsum = (CT)0;
     for (int p = 0; p < c.n_traps; ++p) {
-      state_diff<T, NX>(c, x, c.trap_x[p], d);
-      T cx = t_max(t_min((T)1 / dist_sq<T, NX>(c, d), (T)kTrapMaxCost), (T)0);
-      T dot = (T)0;
+      state_diff<ST, CT, NX>(c.ang_mask, x, c.trap_x[p], d);
+      CT cx = t_max(t_min((CT)1 / dist_sq<CT, NX>(c.dist_scale, d), (CT)kTrapMaxCost), (CT)0);
+      CT dot = (CT)0;
 #pragma unroll
       for (int i = 0; i < NU; ++i)
         if ((c.usim_mask >> i) & 1u) dot = t_fma(u[i], c.trap_u[p][i], dot);
-      T cu = t_max(t_min(dot / (un * c.trap_u_norm[p]), (T)1), (T)0);
+      CT cu = t_max(t_min(dot / (un * c.trap_u_norm[p]), (CT)1), (CT)0);
       tsum = t_fma(cx, cu, tsum);
     }
     cost = t_fma(tsum, c.trap_weight, cost);
@@ -489,12 +506,12 @@ __device__ __forceinline__ T running_cost(const CostS<T>& c, const T (&x)[NX], c
 
 // terminal_cost_multiplier * cost(x_T, terminal=True): QR on the state only; the trap term is multiplied by
 // c_u = 0 when terminal (cost.py:177)      [controller.py:251-259]
-template <typename T, int NX>
-__device__ __forceinline__ T terminal_cost(const CostS<T>& c, const T (&x)[NX]) {
-  if (c.kind == TAMPC_COST_RECOVERY || !c.has_terminal) return (T)0;
-  T d[NX];
-  state_diff<T, NX>(c, x, c.goal, d);
-  return c.terminal_multiplier * quad_form_x<T, NX>(c, d);
+template <typename ST, typename CT, int NX>
+__device__ __forceinline__ CT terminal_cost(const CostS<ST, CT>& c, const ST (&x)[NX]) {
+  if (c.kind == TAMPC_COST_RECOVERY || !c.has_terminal) return (CT)0;
+  CT d[NX];
+  state_diff<ST, CT, NX>(c.ang_mask, x, c.goal, d);
+  return c.terminal_multiplier * quad_form_x<CT, NX>(c.Q, d);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -513,30 +530,30 @@ __device__ __forceinline__ void stage_sampler(SamplerS<T>& dst, const SamplerD& 
   if (tid == 0) { dst.has_bounds = src.has_bounds; dst.null_action = src.null_action; }
 }
 
-template <typename T>
-__device__ __forceinline__ void stage_cost(CostS<T>& dst, const tampc_cost_desc& src, int tid, int nthreads) {
+template <typename ST, typename CT>
+__device__ __forceinline__ void stage_cost(CostS<ST, CT>& dst, const tampc_cost_desc& src, int tid, int nthreads) {
   if (tid == 0) {
     dst.kind = src.kind; dst.use_trap = src.use_trap_cost; dst.n_traps = src.n_traps;
     dst.has_terminal = src.has_terminal; dst.n_sets = src.n_sets;
-    for (int j = 0; j < TAMPC_MAX_GOAL_SETS; ++j) { dst.set_size[j] = src.set_size[j]; dst.set_weight[j] = (T)src.set_weight[j]; }
+    for (int j = 0; j < TAMPC_MAX_GOAL_SETS; ++j) { dst.set_size[j] = src.set_size[j]; dst.set_weight[j] = (CT)src.set_weight[j]; }
     dst.ang_mask = src.ang_mask; dst.usim_mask = src.usim_mask;
-    dst.trap_weight = (T)src.trap_weight; dst.terminal_multiplier = (T)src.terminal_multiplier;
-    dst.recovery_scale = (T)src.recovery_scale;
+    dst.trap_weight = (CT)src.trap_weight; dst.terminal_multiplier = (CT)src.terminal_multiplier;
+    dst.recovery_scale = (CT)src.recovery_scale;
   }
-  for (int i = tid; i < kMaxNx; i += nthreads) { dst.dist_scale[i] = (T)src.dist_scale[i]; dst.goal[i] = (T)src.goal[i]; }
-  for (int i = tid; i < kMaxNx * kMaxNx; i += nthreads) dst.Q[i] = (T)src.Q[i];
-  for (int i = tid; i < kMaxNu * kMaxNu; i += nthreads) dst.R[i] = (T)src.R[i];
-  for (int i = tid; i < TAMPC_MAX_TRAPS * kMaxNx; i += nthreads) dst.trap_x[i / kMaxNx][i % kMaxNx] = (T)src.trap_x[i / kMaxNx][i % kMaxNx];
-  for (int i = tid; i < TAMPC_MAX_TRAPS * kMaxNu; i += nthreads) dst.trap_u[i / kMaxNu][i % kMaxNu] = (T)src.trap_u[i / kMaxNu][i % kMaxNu];
+  for (int i = tid; i < kMaxNx; i += nthreads) { dst.dist_scale[i] = (CT)src.dist_scale[i]; dst.goal[i] = (ST)src.goal[i]; }
+  for (int i = tid; i < kMaxNx * kMaxNx; i += nthreads) dst.Q[i] = (CT)src.Q[i];
+  for (int i = tid; i < kMaxNu * kMaxNu; i += nthreads) dst.R[i] = (CT)src.R[i];
+  for (int i = tid; i < TAMPC_MAX_TRAPS * kMaxNx; i += nthreads) dst.trap_x[i / kMaxNx][i % kMaxNx] = (ST)src.trap_x[i / kMaxNx][i % kMaxNx];
+  for (int i = tid; i < TAMPC_MAX_TRAPS * kMaxNu; i += nthreads) dst.trap_u[i / kMaxNu][i % kMaxNu] = (CT)src.trap_u[i / kMaxNu][i % kMaxNu];
   for (int p = tid; p < TAMPC_MAX_TRAPS; p += nthreads) {
-    T n = (T)0;
+    CT n = (CT)0;
     for (int i = 0; i < kMaxNu; ++i)
-      if ((src.usim_mask >> i) & 1u) { T v = (T)src.trap_u[p][i]; n = t_fma(v, v, n); }
-    dst.trap_u_norm[p] = t_max(t_sqrt(n), (T)kCosSimEps);
+      if ((src.usim_mask >> i) & 1u) { CT v = (CT)src.trap_u[p][i]; n = t_fma(v, v, n); }
+    dst.trap_u_norm[p] = t_max(t_sqrt(n), (CT)kCosSimEps);
   }
   for (int i = tid; i < TAMPC_MAX_GOAL_SETS * TAMPC_MAX_SET_GOALS * kMaxNx; i += nthreads) {
     int j = i / (TAMPC_MAX_SET_GOALS * kMaxNx), g = (i / kMaxNx) % TAMPC_MAX_SET_GOALS, d = i % kMaxNx;
-    dst.set_goals[j][g][d] = (T)src.set_goals[j][g][d];
+    dst.set_goals[j][g][d] = (ST)src.set_goals[j][g][d];
   }
 }
 

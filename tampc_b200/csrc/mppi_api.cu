@@ -60,12 +60,15 @@ struct tampc_mppi {
   double* d_states = nullptr;   // optional trajectories (K_local, Tmax, nx)
   double* d_scratch = nullptr;  // perturbed-action readback
   tampc_partial* d_partials = nullptr;
+  tampc_partial* d_partials2 = nullptr;  // second-level combine scratch
+  int n_partials2 = 0;
   tampc_partial* d_rank_partial = nullptr;
   double* d_action = nullptr;
   double* d_stats = nullptr;
   void* d_weights = nullptr;
   size_t weights_bytes = 0;
   int n_weight_elems = 0;
+  bool use_mma = false;  // the staged weights are in the mma-path layout
 
   double* h_pin = nullptr;  // pinned staging: [0..15] in, [16..31] out
   int n_chunks = 0, chunk = 0;
@@ -160,6 +163,57 @@ void pack_mlp(std::vector<NT>& blob, const std::vector<HostLayer>& m) {
   for (const HostLayer& L : m) pack_layer<NT>(blob, L);
 }
 
+// ---- mma-path layout (mma_rollout.cuh): per layer  bias[out8*8]  then  in8*out8 blocks of 32 lanes x 16 bytes.
+// Lane (g = lane/4, t = lane%4) of block (n, o) holds W[8o+g][8n+2t] and W[8o+g][8n+2t+1]: as two doubles (DMMA
+// k-steps 2n, 2n+1) or as {hi0, hi1, lo0, lo1} TF32 pieces for the 3xTF32 split.
+float tf32_rna(double v) {
+  float f = (float)v;
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+template <typename T>
+void append(std::vector<unsigned char>& blob, T v) {
+  const unsigned char* p = reinterpret_cast<const unsigned char*>(&v);
+  blob.insert(blob.end(), p, p + sizeof(T));
+}
+
+void pack_layer_mma(std::vector<unsigned char>& blob, const HostLayer& L, int in8, int out8, bool f64) {
+  auto W = [&](int o, int i) { return (o < L.out && i < L.in) ? L.W[(size_t)o * L.in + i] : 0.0; };
+  for (int j = 0; j < out8 * 8; ++j) {
+    const double b = j < L.out ? L.b[j] : 0.0;
+    if (f64) append<double>(blob, b); else append<float>(blob, (float)b);
+  }
+  for (int n = 0; n < in8; ++n)
+    for (int o = 0; o < out8; ++o)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3;
+        const double w0 = W(8 * o + g, 8 * n + 2 * t), w1 = W(8 * o + g, 8 * n + 2 * t + 1);
+        if (f64) {
+          append<double>(blob, w0);
+          append<double>(blob, w1);
+        } else {
+          const float h0 = tf32_rna(w0), h1 = tf32_rna(w1);
+          append<float>(blob, h0);
+          append<float>(blob, h1);
+          append<float>(blob, tf32_rna(w0 - (double)h0));
+          append<float>(blob, tf32_rna(w1 - (double)h1));
+        }
+      }
+}
+
+void pack_mlp_mma(std::vector<unsigned char>& blob, const std::vector<HostLayer>& m, int out8_last, bool f64) {
+  int in8 = 1;
+  for (size_t l = 0; l < m.size(); ++l) {
+    const int out8 = (l + 1 == m.size()) ? out8_last : m[l].out / 8;
+    pack_layer_mma(blob, m[l], in8, out8, f64);
+    in8 = out8;
+  }
+}
+
 bool dims_are(const std::vector<HostLayer>& m, std::initializer_list<int> dims) {
   if (m.size() + 1 != dims.size()) return false;
   auto it = dims.begin();
@@ -172,8 +226,10 @@ bool dims_are(const std::vector<HostLayer>& m, std::initializer_list<int> dims) 
 
 struct PackedModel {
   const ModelVariant* variant = nullptr;
-  std::vector<float> f32;
+  std::vector<float> f32;              // FMA-path layouts
   std::vector<double> f64;
+  std::vector<unsigned char> mma_f64;  // mma-path layouts
+  std::vector<unsigned char> mma_tf32;
 };
 
 int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t n, PackedModel& out) {
@@ -217,6 +273,10 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
     }
     pack_mlp<float>(out.f32, net);
     pack_mlp<double>(out.f64, net);
+    if (out.variant->bytes_mma_f64) {
+      pack_mlp_mma(out.mma_f64, net, 1, true);
+      pack_mlp_mma(out.mma_tf32, net, 1, false);
+    }
     return TAMPC_OK;
   }
   if (d.kind != TAMPC_DYN_REX) { h->err = "unknown dynamics kind"; return TAMPC_ERR_INVALID; }
@@ -296,33 +356,62 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
     out.f32.push_back(i < nx ? (float)d0[i] : 0.f);
     out.f64.push_back(i < nx ? d0[i] : 0.0);
   }
+  if (out.variant->bytes_mma_f64) {
+    for (int f64 = 0; f64 < 2; ++f64) {
+      std::vector<unsigned char>& blob = f64 ? out.mma_f64 : out.mma_tf32;
+      pack_mlp_mma(blob, enc, 1, f64);
+      pack_mlp_mma(blob, dyn, 1, f64);
+      pack_mlp_mma(blob, dec, (nx * nv + 7) / 8, f64);
+      for (int i = 0; i < 8; ++i) {
+        const double v = i < nx ? d0[i] : 0.0;
+        if (f64) append<double>(blob, v); else append<float>(blob, (float)v);
+      }
+    }
+  }
   return TAMPC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 
-void choose_launch(const tampc_mppi* h, int& S, int& block) {
-  const int K = h->cfg.num_local;
-  const bool f64 = h->cfg.precision == TAMPC_PREC_F64;
-  const bool has_s2 = !f64 && h->variant->mixed_s2 != nullptr;
-  // two samples per thread halves the LDS:FFMA2 ratio (tools/peaks) but needs >= ~2 CTAs of 128 threads per SM
-  S = (has_s2 && K >= 2 * 148 * 128 * 2) ? 2 : 1;
-  const int threads = (K + S - 1) / S;
-  if (threads >= 2 * 148 * 128) block = 128;
-  else if (threads >= 2 * 148 * 64) block = 64;
-  else block = 32;
-  const int es = env_int("TAMPC_SAMPLES_PER_THREAD", 0), eb = env_int("TAMPC_BLOCK", 0);
-  if (es == 1 || (es == 2 && has_s2)) S = es;
-  if (eb == 32 || eb == 64 || eb == 128) block = eb;
-}
+// Launch shape.  FMA kernels: S samples per thread.  mma kernels: NM m-tiles (8 or 16 samples each) per warp.
+// Small K is latency-bound: spread samples over as many warps / SMs as possible; large K is throughput-bound:
+// more samples per warp re-use each weight fragment.  TAMPC_SAMPLES_PER_THREAD / TAMPC_MMA_NM / TAMPC_BLOCK override.
+struct LaunchPlan {
+  rollout_launch_fn fn = nullptr;
+  int block = 128;
+};
 
-rollout_launch_fn pick_kernel(const tampc_mppi* h, int S) {
+LaunchPlan choose_launch(const tampc_mppi* h, int K) {
   const ModelVariant* v = h->variant;
-  switch (h->cfg.precision) {
-    case TAMPC_PREC_F64: return v->f64_s1;
-    case TAMPC_PREC_MIXED: return S == 2 ? v->mixed_s2 : v->mixed_s1;
-    default: return S == 2 ? v->f32_s2 : v->f32_s1;
+  LaunchPlan p;
+  const int eb = env_int("TAMPC_BLOCK", 0);
+  if (h->use_mma) {
+    const bool f64 = h->cfg.precision == TAMPC_PREC_F64;
+    const int mt = f64 ? 8 : 16, max_idx = f64 ? 2 : 1;
+    int idx = 0;  // NM = 1 << idx
+    while (idx < max_idx && K / (mt << (idx + 1)) >= 2 * 148 * 4) ++idx;
+    const int en = env_int("TAMPC_MMA_NM", 0);
+    if (en == 1) idx = 0; else if (en == 2) idx = 1; else if (en == 4 && f64) idx = 2;
+    const int warps = (K + (mt << idx) - 1) / (mt << idx);
+    p.block = warps >= 2 * 148 * 4 ? 128 : (warps >= 2 * 148 * 2 ? 64 : 32);
+    p.fn = f64 ? v->f64_mma[idx] : v->tf32_mma[idx];
+  } else {
+    const bool f64 = h->cfg.precision == TAMPC_PREC_F64;
+    const bool has_s2 = !f64 && v->mixed_s2 != nullptr;
+    int S = (has_s2 && K >= 2 * 148 * 128 * 2) ? 2 : 1;
+    const int es = env_int("TAMPC_SAMPLES_PER_THREAD", 0);
+    if (es == 1 || (es == 2 && has_s2)) S = es;
+    const int threads = (K + S - 1) / S;
+    p.block = threads >= 2 * 148 * 128 ? 128 : (threads >= 2 * 148 * 64 ? 64 : 32);
+    switch (h->cfg.precision) {
+      case TAMPC_PREC_F64: p.fn = v->f64_s1; break;
+      case TAMPC_PREC_MIXED:
+      case TAMPC_PREC_TF32X3: p.fn = S == 2 ? v->mixed_s2 : v->mixed_s1; break;
+      default: p.fn = S == 2 ? v->f32_s2 : v->f32_s1; break;
+    }
   }
+  if (eb == 32 || eb == 64 || eb == 128) p.block = eb;
+  return p;
 }
 
 SampleSrc make_src(const tampc_mppi* h, int mode, uint64_t call, int T) {
@@ -362,11 +451,9 @@ int launch_rollout_for(tampc_mppi* h, int mode, int shift, const double* d_U, in
   a.wrap_mask = h->model.wrap_mask;
   a.has_guard = h->model.has_bad_state_guard;
   a.bad_norm = h->model.bad_state_norm;
-  int S, block;
-  choose_launch(h, S, block);
-  rollout_launch_fn fn = pick_kernel(h, S);
-  if (!fn) { h->err = "no kernel compiled for this precision / samples-per-thread"; return TAMPC_ERR_UNSUPPORTED; }
-  CUDA_TRY(h, fn(a, block, h->stream));
+  const LaunchPlan plan = choose_launch(h, a.K_local);
+  if (!plan.fn) { h->err = "no kernel compiled for this precision"; return TAMPC_ERR_UNSUPPORTED; }
+  CUDA_TRY(h, plan.fn(a, plan.block, h->stream));
   h->launches++;
   return TAMPC_OK;
 }
@@ -421,18 +508,36 @@ int run_rollout_and_partials(tampc_mppi* h, int mode, bool keep_states) {
   return TAMPC_OK;
 }
 
+// Merge n partials.  More than one group of kCombineThreads is first reduced group-wise into d_partials2 (a
+// deterministic two-level tree), then a single CTA finishes: finalize=1 writes the new U / action / stats,
+// finalize=0 writes one merged partial (this rank's contribution) to partial_out.
 int run_combine(tampc_mppi* h, const tampc_partial* partials, int n, int finalize, tampc_partial* partial_out = nullptr) {
   CombineArgs c{};
-  c.partials = partials;
-  c.n_partials = n;
   c.sampler = h->d_sampler;
   c.U = h->d_U[h->cur];
   c.T = h->T;
   c.nu = h->cfg.nu;
-  c.finalize = finalize;
   c.U_out = h->d_U[h->cur ^ 1];
   c.action_out = h->d_action;
   c.stats_out = h->d_stats;
+  while (n > kCombineThreads) {
+    const int groups = (n + kCombineThreads - 1) / kCombineThreads;
+    if (groups > h->n_partials2) { h->err = "internal: too many partials for the combine scratch"; return TAMPC_ERR_INVALID; }
+    c.partials = partials;
+    c.n_partials = n;
+    c.group = kCombineThreads;
+    c.finalize = 0;
+    c.partial_out = h->d_partials2;
+    combine_kernel<<<groups, kCombineThreads, 0, h->stream>>>(c);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    partials = h->d_partials2;
+    n = groups;
+  }
+  c.partials = partials;
+  c.n_partials = n;
+  c.group = n;
+  c.finalize = finalize;
   c.partial_out = partial_out ? partial_out : h->d_rank_partial;
   combine_kernel<<<1, kCombineThreads, 0, h->stream>>>(c);
   CUDA_TRY(h, cudaGetLastError());
@@ -486,7 +591,7 @@ TAMPC_API int tampc_mppi_create(const tampc_mppi_config* cfg, tampc_mppi** out) 
     return TAMPC_ERR_INVALID;
   }
   if (cfg->max_horizon < 1 || cfg->max_horizon > TAMPC_MAX_HORIZON) { g_create_error = "max_horizon out of range (1..128)"; return TAMPC_ERR_INVALID; }
-  if (cfg->precision < TAMPC_PREC_F64 || cfg->precision > TAMPC_PREC_F32) { g_create_error = "unknown precision"; return TAMPC_ERR_INVALID; }
+  if (cfg->precision < TAMPC_PREC_F64 || cfg->precision > TAMPC_PREC_TF32X3) { g_create_error = "unknown precision"; return TAMPC_ERR_INVALID; }
   if (!(cfg->lambda_ > 0.0)) { g_create_error = "lambda_ must be positive"; return TAMPC_ERR_INVALID; }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -563,6 +668,9 @@ TAMPC_API int tampc_mppi_create(const tampc_mppi_config* cfg, tampc_mppi** out) 
   CREATE_TRY(cudaMalloc(&h->d_state, sizeof(double) * kMaxNx));
   CREATE_TRY(cudaMalloc(&h->d_costs, sizeof(double) * K));
   CREATE_TRY(cudaMalloc(&h->d_partials, sizeof(tampc_partial) * h->n_chunks));
+  h->n_partials2 = (h->n_chunks + kCombineThreads - 1) / kCombineThreads;
+  if (h->n_partials2 > kCombineThreads) return fail("num_local too large for the two-level combine", TAMPC_ERR_INVALID);
+  CREATE_TRY(cudaMalloc(&h->d_partials2, sizeof(tampc_partial) * h->n_partials2));
   CREATE_TRY(cudaMalloc(&h->d_rank_partial, sizeof(tampc_partial)));
   CREATE_TRY(cudaMalloc(&h->d_action, sizeof(double) * kMaxNu));
   CREATE_TRY(cudaMalloc(&h->d_stats, sizeof(double) * 4));
@@ -592,7 +700,7 @@ TAMPC_API void tampc_mppi_destroy(tampc_mppi* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_sampler); cudaFree(h->d_cost); cudaFree(h->d_U[0]); cudaFree(h->d_U[1]); cudaFree(h->d_state);
-  cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_partials);
+  cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_partials2);
   cudaFree(h->d_rank_partial); cudaFree(h->d_action); cudaFree(h->d_stats); cudaFree(h->d_weights);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -605,15 +713,42 @@ TAMPC_API int tampc_mppi_set_model(tampc_mppi* h, const tampc_model_desc* desc, 
   PackedModel pm;
   int rc = pack_model(h, *desc, params, n_params, pm);
   if (rc) return rc;
-  const bool f64 = h->cfg.precision == TAMPC_PREC_F64;
-  const void* src = f64 ? (const void*)pm.f64.data() : (const void*)pm.f32.data();
-  const size_t elems = f64 ? pm.f64.size() : pm.f32.size();
-  const int expect = f64 ? pm.variant->elems_f64 : pm.variant->elems_f32;
-  if ((int)elems != expect) {
-    h->err = "internal: packed size " + std::to_string(elems) + " != kernel layout " + std::to_string(expect) + " for " + pm.variant->name;
-    return TAMPC_ERR_INVALID;
+  // arithmetic -> layout:  F64 = DMMA layout (FMA layout if the shape has no mma kernel or TAMPC_F64_IMPL=fma),
+  // TF32X3 = mma layout, MIXED / F32 = float32 FMA layout
+  const int prec = h->cfg.precision;
+  const bool f64 = prec == TAMPC_PREC_F64;
+  const char* f64_impl = getenv("TAMPC_F64_IMPL");
+  bool use_mma = false;
+  if (prec == TAMPC_PREC_TF32X3) {
+    // shapes without network layers (analytic pendulum) have nothing to put on the tensor cores: the float64
+    // state/cost arithmetic of TF32X3 is exactly the MIXED kernel there
+    use_mma = pm.variant->bytes_mma_tf32 != 0;
+    if (!use_mma && pm.variant->kind != TAMPC_DYN_PENDULUM) { h->err = std::string("no tensor-core kernel for ") + pm.variant->name; return TAMPC_ERR_UNSUPPORTED; }
+  } else if (f64 && pm.variant->bytes_mma_f64 && !(f64_impl && !strcmp(f64_impl, "fma"))) {
+    use_mma = true;
   }
-  const size_t bytes = ((f64 ? 8 : 4) * elems + 15) & ~size_t(15);
+  const void* src;
+  size_t raw_bytes;
+  if (use_mma) {
+    const std::vector<unsigned char>& blob = f64 ? pm.mma_f64 : pm.mma_tf32;
+    const int expect = f64 ? pm.variant->bytes_mma_f64 : pm.variant->bytes_mma_tf32;
+    if ((int)blob.size() != expect) {
+      h->err = "internal: packed mma size " + std::to_string(blob.size()) + " != kernel layout " + std::to_string(expect) + " for " + pm.variant->name;
+      return TAMPC_ERR_INVALID;
+    }
+    src = blob.data();
+    raw_bytes = blob.size();
+  } else {
+    src = f64 ? (const void*)pm.f64.data() : (const void*)pm.f32.data();
+    const size_t elems = f64 ? pm.f64.size() : pm.f32.size();
+    const int expect = f64 ? pm.variant->elems_f64 : pm.variant->elems_f32;
+    if ((int)elems != expect) {
+      h->err = "internal: packed size " + std::to_string(elems) + " != kernel layout " + std::to_string(expect) + " for " + pm.variant->name;
+      return TAMPC_ERR_INVALID;
+    }
+    raw_bytes = (f64 ? 8 : 4) * elems;
+  }
+  const size_t bytes = (raw_bytes + 15) & ~size_t(15);
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   if (bytes > h->weights_bytes) {
@@ -623,8 +758,9 @@ TAMPC_API int tampc_mppi_set_model(tampc_mppi* h, const tampc_model_desc* desc, 
     h->weights_bytes = bytes;
   }
   CUDA_TRY(h, cudaMemset(h->d_weights, 0, h->weights_bytes));
-  CUDA_TRY(h, cudaMemcpy(h->d_weights, src, (f64 ? 8 : 4) * elems, cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->d_weights, src, raw_bytes, cudaMemcpyHostToDevice));
   h->n_weight_elems = (int)(bytes / (f64 ? 8 : 4));
+  h->use_mma = use_mma;
   h->variant = pm.variant;
   h->model = *desc;
   h->has_model = true;
@@ -777,8 +913,9 @@ TAMPC_API int tampc_mppi_get_rollouts(tampc_mppi* h, const double* state, double
   a.wrap_mask = h->model.wrap_mask;
   a.has_guard = h->model.has_bad_state_guard;
   a.bad_norm = h->model.bad_state_norm;
-  rollout_launch_fn fn = pick_kernel(h, 1);
-  CUDA_TRY(h, fn(a, 32, h->stream));
+  const LaunchPlan plan = choose_launch(h, 1);
+  if (!plan.fn) { h->err = "no kernel compiled for this precision"; return TAMPC_ERR_UNSUPPORTED; }
+  CUDA_TRY(h, plan.fn(a, 32, h->stream));
   h->launches++;
   CUDA_TRY(h, cudaMemcpyAsync(states_out, h->d_states, sizeof(double) * h->T * h->cfg.nx, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));

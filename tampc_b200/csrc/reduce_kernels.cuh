@@ -108,46 +108,69 @@ __global__ void __launch_bounds__(kReduceThreads) partials_kernel(const ReduceAr
 struct CombineArgs {
   const tampc_partial* partials;
   int n_partials;
+  int group;             // partials per CTA: CTA b merges [b*group, min((b+1)*group, n_partials))
   const SamplerD* sampler;
   const double* U;       // nominal BEFORE the shift
   int T, nu;
-  int finalize;          // 1: write U_out / action / stats; 0: write one merged tampc_partial to partial_out
+  int finalize;          // 1 (single CTA): write U_out / action / stats; 0: write merged tampc_partial b to partial_out[b]
   double* U_out;         // (T, nu) updated nominal sequence
   double* action_out;    // (nu,) = U_out[0]
   double* stats_out;     // beta, eta, argmin
   tampc_partial* partial_out;
 };
 
-constexpr int kCombineThreads = 512;
+constexpr int kCombineThreads = 512;  // also the largest group
 
 __global__ void __launch_bounds__(kCombineThreads) combine_kernel(const CombineArgs a) {
-  __shared__ double s_beta;
-  __shared__ double s_eta;
-  __shared__ long long s_arg;
+  __shared__ double s_beta[kCombineThreads];
+  __shared__ double s_scale[kCombineThreads];
+  __shared__ double s_sum[kCombineThreads];
+  __shared__ long long s_arg[kCombineThreads];
+  __shared__ long long s_cnt[kCombineThreads];
   const int tid = threadIdx.x;
+  const int p0 = blockIdx.x * a.group;
+  const int n = min(a.group, a.n_partials - p0);
+  const tampc_partial* part = a.partials + p0;
   const double li = a.sampler->lambda_inv;
-  if (tid == 0) {
-    double beta = a.partials[0].beta;
-    long long arg = a.partials[0].argmin;
-    for (int p = 1; p < a.n_partials; ++p) {
-      double b = a.partials[p].beta;
-      long long g = a.partials[p].argmin;
-      if (b < beta || (b == beta && g < arg)) { beta = b; arg = g; }
-    }
-    double eta = 0.0;
-    for (int p = 0; p < a.n_partials; ++p) eta = __fma_rn(exp(-li * (a.partials[p].beta - beta)), a.partials[p].eta, eta);
-    s_beta = beta;
-    s_eta = eta;
-    s_arg = arg;
-  }
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  // ---- min / argmin over the group (lowest global sample index wins ties), fixed-shape tree
+  const double my_beta = tid < n ? part[tid].beta : inf;
+  const double my_eta = tid < n ? part[tid].eta : 0.0;
+  s_beta[tid] = my_beta;
+  s_arg[tid] = tid < n ? part[tid].argmin : 0x7fffffffffffffffll;
+  s_cnt[tid] = tid < n ? part[tid].count : 0;
   __syncthreads();
-  const double beta = s_beta, eta = s_eta;
-  const int n = a.T * a.nu;
-  for (int i = tid; i < n; i += kCombineThreads) {
+  for (int off = kCombineThreads / 2; off > 0; off >>= 1) {
+    if (tid < off) {
+      const double o = s_beta[tid + off];
+      const long long oi = s_arg[tid + off];
+      if (o < s_beta[tid] || (o == s_beta[tid] && oi < s_arg[tid])) { s_beta[tid] = o; s_arg[tid] = oi; }
+      s_cnt[tid] += s_cnt[tid + off];
+    }
+    __syncthreads();
+  }
+  const double beta = s_beta[0];
+  const long long arg = s_arg[0];
+  const long long cnt = s_cnt[0];
+  __syncthreads();
+  // ---- log-sum-exp rescale of every partial to the common minimum, normaliser by a fixed-shape tree
+  const double sc = tid < n ? exp(-li * (my_beta - beta)) : 0.0;
+  s_scale[tid] = sc;
+  s_sum[tid] = sc * my_eta;
+  __syncthreads();
+  for (int off = kCombineThreads / 2; off > 0; off >>= 1) {
+    if (tid < off) s_sum[tid] += s_sum[tid + off];
+    __syncthreads();
+  }
+  const double eta = s_sum[0];
+  // ---- weighted sums, one thread per (t, i), partials in index order
+  const int nw = a.T * a.nu;
+  for (int i = tid; i < nw; i += kCombineThreads) {
     double sum = 0.0;
-    for (int p = 0; p < a.n_partials; ++p) {
-      const double s = exp(-li * (a.partials[p].beta - beta));
-      if (s != 0.0) sum = __fma_rn(s, a.partials[p].wsum[i], sum);
+#pragma unroll 4
+    for (int p = 0; p < n; ++p) {
+      const double s = s_scale[p];
+      if (s != 0.0) sum = __fma_rn(s, part[p].wsum[i], sum);
     }
     if (a.finalize) {
       const int t = i / a.nu, d = i % a.nu, ts = t + 1;
@@ -156,21 +179,20 @@ __global__ void __launch_bounds__(kCombineThreads) combine_kernel(const CombineA
       a.U_out[i] = v;
       if (t == 0) a.action_out[d] = v;
     } else {
-      a.partial_out->wsum[i] = sum;
+      a.partial_out[blockIdx.x].wsum[i] = sum;
     }
   }
   if (tid == 0) {
     if (a.finalize) {
       a.stats_out[0] = beta;
       a.stats_out[1] = eta;
-      a.stats_out[2] = (double)s_arg;
+      a.stats_out[2] = (double)arg;
     } else {
-      long long cnt = 0;
-      for (int p = 0; p < a.n_partials; ++p) cnt += a.partials[p].count;
-      a.partial_out->beta = beta;
-      a.partial_out->eta = eta;
-      a.partial_out->argmin = s_arg;
-      a.partial_out->count = cnt;
+      tampc_partial& o = a.partial_out[blockIdx.x];
+      o.beta = beta;
+      o.eta = eta;
+      o.argmin = arg;
+      o.count = cnt;
     }
   }
 }

@@ -29,22 +29,22 @@ struct RolloutArgs {
 
 template <typename T> __host__ __device__ constexpr size_t align16(size_t n) { return (n + 15) & ~size_t(15); }
 
-template <class Model, typename NT, typename ST>
+template <class Model, typename NT, typename ST, typename CT>
 struct RolloutSmem {
   static constexpr size_t kWeights = 0;
   static constexpr size_t kCost = align16<int>(sizeof(NT) * Model::kElems);
-  static constexpr size_t kSampler = kCost + align16<int>(sizeof(CostS<ST>));
+  static constexpr size_t kSampler = kCost + align16<int>(sizeof(CostS<ST, CT>));
   static constexpr size_t kU = kSampler + align16<int>(sizeof(SamplerS<ST>));
   static __host__ __device__ constexpr size_t bytes(int T) { return kU + align16<int>(sizeof(ST) * (size_t)T * kMaxNu); }
 };
 
-template <class Model, typename NT, typename ST, int S>
+template <class Model, typename NT, typename ST, typename CT, int S>
 __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
   constexpr int NX = Model::NX, NU = Model::NU;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using L = RolloutSmem<Model, NT, ST>;
+  using L = RolloutSmem<Model, NT, ST, CT>;
   NT* w = reinterpret_cast<NT*>(smem_raw + L::kWeights);
-  CostS<ST>& cs = *reinterpret_cast<CostS<ST>*>(smem_raw + L::kCost);
+  CostS<ST, CT>& cs = *reinterpret_cast<CostS<ST, CT>*>(smem_raw + L::kCost);
   SamplerS<ST>& sp = *reinterpret_cast<SamplerS<ST>*>(smem_raw + L::kSampler);
   ST* Ush = reinterpret_cast<ST*>(smem_raw + L::kU);  // [T][kMaxNu] shifted nominal sequence
 
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
     int4* sw = reinterpret_cast<int4*>(w);
     const int n16 = (int)((sizeof(NT) * (size_t)a.n_weight_elems) / 16);
     for (int i = tid; i < n16; i += nthr) sw[i] = gw[i];
-    stage_cost<ST>(cs, *a.cost, tid, nthr);
+    stage_cost<ST, CT>(cs, *a.cost, tid, nthr);
     stage_sampler<ST>(sp, *a.sampler, tid, nthr);
     for (int i = tid; i < T * NU; i += nthr) {
       int t = i / NU, d = i % NU;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
         if ((a.wrap_mask >> i) & 1u) x[s][i] = angle_normalize<ST>(x[s][i]);  // constrain_state
         if (bad[s]) x[s][i] = (ST)0;                                           // next_state[bad] = state[bad] (= 0)
       }
-      cost[s] += running_cost<ST, NX, NU>(cs, x[s], u[s]);
+      cost[s] += (ST)running_cost<ST, CT, NX, NU>(cs, x[s], u[s]);
       if (a.states_out != nullptr && live[s]) {
         double* so = a.states_out + ((size_t)k[s] * T + t) * NX;
 #pragma unroll
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
   }
 #pragma unroll
   for (int s = 0; s < S; ++s) {
-    ST total = cost[s] + terminal_cost<ST, NX>(cs, x[s]);
+    ST total = cost[s] + (ST)terminal_cost<ST, CT, NX>(cs, x[s]);
     total += pert[s];
     if (live[s]) a.cost_out[k[s]] = (double)total;
   }
@@ -136,10 +136,10 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
 // host-callable launcher signature shared by all variants
 typedef cudaError_t (*rollout_launch_fn)(const RolloutArgs& a, int block, cudaStream_t stream);
 
-template <class Model, typename NT, typename ST, int S>
+template <class Model, typename NT, typename ST, typename CT, int S>
 cudaError_t launch_rollout(const RolloutArgs& a, int block, cudaStream_t stream) {
-  auto kern = rollout_kernel<Model, NT, ST, S>;
-  const size_t smem = RolloutSmem<Model, NT, ST>::bytes(a.src.T);
+  auto kern = rollout_kernel<Model, NT, ST, CT, S>;
+  const size_t smem = RolloutSmem<Model, NT, ST, CT>::bytes(a.src.T);
   static size_t configured = 0;  // per instantiation
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -151,15 +151,5 @@ cudaError_t launch_rollout(const RolloutArgs& a, int block, cudaStream_t stream)
   kern<<<grid, block, smem, stream>>>(a);
   return cudaGetLastError();
 }
-
-// One dynamics shape = the set of kernels compiled for it.
-struct ModelVariant {
-  const char* name;
-  int kind, nx, nu;
-  int dims[12];            // kind-specific layer widths, see match() in mppi_api.cu
-  int elems_f32, elems_f64;
-  int macs;
-  rollout_launch_fn f64_s1, mixed_s1, mixed_s2, f32_s1, f32_s2;
-};
 
 }  // namespace tampc

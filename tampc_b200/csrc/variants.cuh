@@ -1,9 +1,22 @@
 // variants.cuh — the compiled dynamics shapes.  Each lives in its own translation unit (parallel nvcc).
 #pragma once
 #include <initializer_list>
-#include "rollout_kernel.cuh"
+#include "mma_rollout.cuh"
 
 namespace tampc {
+
+// One dynamics shape = the set of kernels compiled for it.
+struct ModelVariant {
+  const char* name;
+  int kind, nx, nu;
+  int dims[12];            // kind-specific layer widths, see pack_model() in mppi_api.cu
+  int elems_f32, elems_f64;  // packed sizes of the FMA-path layouts (elements)
+  int bytes_mma_f64, bytes_mma_tf32;  // packed sizes of the mma-path layouts (bytes); 0 = not compiled
+  int macs;
+  rollout_launch_fn f64_s1, mixed_s1, mixed_s2, f32_s1, f32_s2;  // one-thread-per-sample FMA kernels
+  rollout_launch_fn f64_mma[3];   // DMMA kernels, NM = 1, 2, 4 m-tiles (8, 16, 32 samples) per warp
+  rollout_launch_fn tf32_mma[2];  // 3xTF32 kernels, NM = 1, 2 (16, 32 samples per warp); float64 state and cost
+};
 
 template <class MF, class MD, bool WITH_S2>
 ModelVariant make_variant(const char* name, int kind, std::initializer_list<int> dims) {
@@ -17,17 +30,25 @@ ModelVariant make_variant(const char* name, int kind, std::initializer_list<int>
   v.elems_f32 = MF::kElems;
   v.elems_f64 = MD::kElems;
   v.macs = MF::kMacs;
-  v.f64_s1 = &launch_rollout<MD, double, double, 1>;
-  v.mixed_s1 = &launch_rollout<MF, float, double, 1>;
-  v.f32_s1 = &launch_rollout<MF, float, float, 1>;
+  v.f64_s1 = &launch_rollout<MD, double, double, double, 1>;
+  v.mixed_s1 = &launch_rollout<MF, float, double, float, 1>;
+  v.f32_s1 = &launch_rollout<MF, float, float, float, 1>;
   if constexpr (WITH_S2) {
-    v.mixed_s2 = &launch_rollout<MF, float, double, 2>;
-    v.f32_s2 = &launch_rollout<MF, float, float, 2>;
-  } else {
-    v.mixed_s2 = nullptr;
-    v.f32_s2 = nullptr;
+    v.mixed_s2 = &launch_rollout<MF, float, double, float, 2>;
+    v.f32_s2 = &launch_rollout<MF, float, float, float, 2>;
   }
   return v;
+}
+
+template <class MM64, class MM32>
+void add_mma(ModelVariant& v) {
+  v.bytes_mma_f64 = MM64::kBytes;
+  v.bytes_mma_tf32 = MM32::kBytes;
+  v.f64_mma[0] = &launch_rollout_mma<MM64, double, double, 1>;
+  v.f64_mma[1] = &launch_rollout_mma<MM64, double, double, 2>;
+  v.f64_mma[2] = &launch_rollout_mma<MM64, double, double, 4>;
+  v.tf32_mma[0] = &launch_rollout_mma<MM32, double, float, 1>;
+  v.tf32_mma[1] = &launch_rollout_mma<MM32, double, float, 2>;
 }
 
 const ModelVariant* variant_rex_push();   // nx5 nu3, enc 8-16-32-5, dyn 5-32-32-5, dec 5(2)-16-32-25
