@@ -64,7 +64,7 @@ typedef enum tampc_precision {
   TAMPC_PREC_MIXED = 1, /* networks in float32 (packed FFMA2), state + cost accumulation in float64 */
   TAMPC_PREC_F32 = 2,   /* everything in float32 */
   TAMPC_PREC_TF32X3 = 3 /* networks on the tensor cores as 3xTF32 (error-compensated split, ~float32 accuracy),
-                           state + cost in float64 */
+                           state and cost terms in float32, cost accumulated in float64 */
 } tampc_precision;
 
 /* where the per-sample action perturbations come from */

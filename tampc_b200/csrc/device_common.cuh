@@ -74,6 +74,11 @@ __device__ __forceinline__ double t_max(double a, double b) { return fmax(a, b);
 __device__ __forceinline__ float t_sin(float a) { return sinf(a); }
 __device__ __forceinline__ double t_sin(double a) { return sin(a); }
 
+// cost-term division and square root.  float: MUFU-based (<= 2 ulp); double: IEEE
+__device__ __forceinline__ float t_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double t_div(double a, double b) { return a / b; }
+__device__ __forceinline__ float t_sqrt_fast(float a) { return a * rsqrtf(fmaxf(a, 1e-30f)); }
+__device__ __forceinline__ double t_sqrt_fast(double a) { return sqrt(a); }
 __device__ __forceinline__ float t_floor(float a) { return floorf(a); }
 __device__ __forceinline__ double t_floor(double a) { return floor(a); }
 
@@ -82,20 +87,19 @@ __device__ __forceinline__ double t_floor(double a) { return floor(a); }
 // to an ulp of 2pi.
 template <typename T>
 __device__ __forceinline__ T angle_normalize(T a) {
+  // branch-free; an input already in [-pi, pi) takes k = 0 and comes back as (a + pi) - pi, the reference's rounding
   const T two_pi = (T)(2.0 * kPi);
   const T y = a + (T)kPi;
   T r = t_fma(-t_floor(y * (T)(1.0 / (2.0 * kPi))), two_pi, y);
-  if (r < (T)0) r += two_pi;
-  else if (r >= two_pi) r -= two_pi;
+  r = r < (T)0 ? r + two_pi : (r >= two_pi ? r - two_pi : r);
   return r - (T)kPi;
 }
 
 // math_utils.angular_diff_batch: one wrap into [-pi, pi] (tampc/env/block_push.py:957)
 template <typename T>
 __device__ __forceinline__ T angular_wrap_once(T d) {
-  if (d > (T)kPi) d -= (T)(2.0 * kPi);
-  else if (d < (T)(-kPi)) d += (T)(2.0 * kPi);
-  return d;
+  const T shift = d > (T)kPi ? (T)(-2.0 * kPi) : (d < (T)(-kPi) ? (T)(2.0 * kPi) : (T)0);  // selects, no branches
+  return d + shift;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -148,7 +152,7 @@ struct SampleSrc {
 // increment  sum_i perturbed_i * (lambda * npost @ Sigma^-1)_i   (controller.py:395,400)
 template <typename T, int NU>
 __device__ __forceinline__ T sample_action(const SampleSrc& src, const SamplerS<T>& sp, const T* __restrict__ Ut,
-                                           int k_local, int t, T (&u)[NU], T (&npost)[NU]) {
+                                           int k_local, int t, T (&u)[NU], T (&npost)[NU], const float* __restrict__ zpre = nullptr) {
   if (src.mode == kModeNominal) {
 #pragma unroll
     for (int i = 0; i < NU; ++i) { u[i] = Ut[i]; npost[i] = (T)0; }
@@ -167,7 +171,12 @@ __device__ __forceinline__ T sample_action(const SampleSrc& src, const SamplerS<
     for (int i = 0; i < NU; ++i) n[i] = (T)p[i];
   } else {
     float z[4];
-    philox_normal4(src.seed, src.call, (uint32_t)(src.sample_offset + k_local), (uint32_t)t, z);
+    if (zpre != nullptr) {  // standard normals drawn ahead of the horizon loop (same Philox stream)
+#pragma unroll
+      for (int i = 0; i < NU; ++i) z[i] = zpre[i];
+    } else {
+      philox_normal4(src.seed, src.call, (uint32_t)(src.sample_offset + k_local), (uint32_t)t, z);
+    }
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
       T acc = sp.mu[i];
@@ -449,10 +458,13 @@ __device__ __forceinline__ CT quad_form_x(const CT* __restrict__ Q, const CT (&d
 }
 
 // running cost of (x_next, u)      [controller.py:248-249 -> cost.py:213-235]
+// `part` of `nparts`: lanes that mirror the same sample share the work — the trap-set terms are dealt round-robin,
+// everything else goes to part 0; the caller adds the parts' sums (once, after the horizon loop).
 template <typename ST, typename CT, int NX, int NU>
-__device__ __forceinline__ CT running_cost(const CostS<ST, CT>& c, const ST (&x)[NX], const ST (&us)[NU]) {
+__device__ __forceinline__ CT running_cost(const CostS<ST, CT>& c, const ST (&x)[NX], const ST (&us)[NU], int part = 0, int nparts = 1) {
   CT d[NX];
   if (c.kind == TAMPC_COST_RECOVERY) {
+    if (part != 0) return (CT)0;
     CT total = (CT)0;
     for (int j = 0; j < c.n_sets; ++j) {
       CT best = (CT)0;
@@ -468,9 +480,10 @@ __device__ __forceinline__ CT running_cost(const CostS<ST, CT>& c, const ST (&x)
   CT u[NU];
 #pragma unroll
   for (int i = 0; i < NU; ++i) u[i] = (CT)us[i];
-  state_diff<ST, CT, NX>(c.ang_mask, x, c.goal, d);
-  CT cost = quad_form_x<CT, NX>(c.Q, d);
-  {
+  CT cost = (CT)0;
+  if (part == 0) {
+    state_diff<ST, CT, NX>(c.ang_mask, x, c.goal, d);
+    cost = quad_form_x<CT, NX>(c.Q, d);
     CT ru = (CT)0;
 #pragma unroll
     for (int j = 0; j < NU; ++j) {
@@ -487,16 +500,16 @@ __device__ __forceinline__ CT running_cost(const CostS<ST, CT>& c, const ST (&x)
 #pragma unroll
     for (int i = 0; i < NU; ++i)
       if ((c.usim_mask >> i) & 1u) un = t_fma(u[i], u[i], un);
-    un = t_max(t_sqrt(un), (CT)kCosSimEps);
+    un = t_max(t_sqrt_fast(un), (CT)kCosSimEps);
     CT tsum = (CT)0;
-    for (int p = 0; p < c.n_traps; ++p) {
+    for (int p = part; p < c.n_traps; p += nparts) {
       state_diff<ST, CT, NX>(c.ang_mask, x, c.trap_x[p], d);
-      CT cx = t_max(t_min((CT)1 / dist_sq<CT, NX>(c.dist_scale, d), (CT)kTrapMaxCost), (CT)0);
+      CT cx = t_max(t_min(t_div((CT)1, dist_sq<CT, NX>(c.dist_scale, d)), (CT)kTrapMaxCost), (CT)0);
       CT dot = (CT)0;
 #pragma unroll
       for (int i = 0; i < NU; ++i)
         if ((c.usim_mask >> i) & 1u) dot = t_fma(u[i], c.trap_u[p][i], dot);
-      CT cu = t_max(t_min(dot / (un * c.trap_u_norm[p]), (CT)1), (CT)0);
+      CT cu = t_max(t_min(t_div(dot, un * c.trap_u_norm[p]), (CT)1), (CT)0);
       tsum = t_fma(cx, cu, tsum);
     }
     cost = t_fma(tsum, c.trap_weight, cost);

@@ -13,35 +13,48 @@
 //
 // Per-sample work (noise, clamp, guard, cost: controller.py:386-395, online_controller.py:60-79, cost.py) stays
 // one-thread-per-sample; rows move between the two layouts through a small per-warp shared-memory staging tile.
+// With fewer than 32 samples per warp (small K: latency-bound) the spare lanes mirror a sample and take a share
+// of its trap-set cost terms, and the horizon's standard normals are drawn up front by all 32 lanes.
 #pragma once
 #include "rollout_kernel.cuh"
 
 namespace tampc {
 
+// Section timing for development (-DTAMPC_PROFILE): per-warp cycle counts summed into g_prof[section].
+#ifdef TAMPC_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_T0() long long prof_t = clock64()
+#define PROF_RESET() prof_t = clock64()
+#define PROF(sec) do { long long now_ = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&g_prof[sec], (unsigned long long)(now_ - prof_t)); prof_t = clock64(); } while (0)
+#else
+#define PROF_T0() do {} while (0)
+#define PROF_RESET() do {} while (0)
+#define PROF(sec) do {} while (0)
+#endif
+
 struct PolicyF64 {
   using T = double;
   static constexpr int MT = 8;  // rows per m-tile
   static constexpr int R = 2;   // accumulator registers per (m-tile, 8-feature block) per lane
+  static constexpr int PROD = 2;  // mma instructions per (8-feature input block, output block)
   static constexpr int kBlockBytes = 512;
 };
 struct PolicyTF32x3 {
   using T = float;
   static constexpr int MT = 16;
   static constexpr int R = 4;
+  static constexpr int PROD = 3;
   static constexpr int kBlockBytes = 512;
 };
 
-__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+// d = a*b + c with separate c (first product of an accumulation chain: c = bias or zero)
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b, double c0, double c1) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};" : "=d"(d[0]), "=d"(d[1]) : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
-__device__ __forceinline__ void mma1688_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
+__device__ __forceinline__ void mma1688_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, float c0, float c1, float c2, float c3) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
 }
 
 // bytes of one packed layer: bias[OUT8*8] then IN8*OUT8 blocks of 32 lanes x 16 B
@@ -50,23 +63,22 @@ template <class P> __host__ __device__ constexpr int mma_layer_bytes(int in8, in
 }
 
 // out = act(W in + b) for NM m-tiles.  in/out: [m-tile][8-feature block][R] accumulator-layout registers.
+// Narrow outputs (OUT8 < 4) would be one long dependent mma chain per tile; their products are dealt over NS
+// independent accumulators that are added at the end.
 template <class P, int NM, int IN8, int OUT8, bool ACT>
 __device__ __forceinline__ void mma_layer(const typename P::T (&in)[NM][IN8][P::R], typename P::T (&out)[NM][OUT8][P::R],
                                           const unsigned char* __restrict__ wl, typename P::T slope, int lane) {
   using T = typename P::T;
+  constexpr int NPROD = P::PROD * IN8;                       // products accumulated per output tile
+  constexpr int NS_WANT = OUT8 >= 4 ? 1 : (OUT8 == 2 ? 2 : 4);
+  constexpr int NS = NS_WANT < NPROD ? NS_WANT : NPROD;      // accumulators per output tile
   const int t = lane & 3;
   const T* bias = reinterpret_cast<const T*>(wl);
   const unsigned char* blocks = wl + OUT8 * 8 * sizeof(T);
+  T acc[NS][NM][OUT8][P::R];
+  T b0[OUT8], b1[OUT8];
 #pragma unroll
-  for (int o = 0; o < OUT8; ++o) {
-    const T b0 = bias[o * 8 + 2 * t], b1 = bias[o * 8 + 2 * t + 1];
-#pragma unroll
-    for (int m = 0; m < NM; ++m) {
-      out[m][o][0] = b0;
-      out[m][o][1] = b1;
-      if constexpr (P::R == 4) { out[m][o][2] = b0; out[m][o][3] = b1; }
-    }
-  }
+  for (int o = 0; o < OUT8; ++o) { b0[o] = bias[o * 8 + 2 * t]; b1[o] = bias[o * 8 + 2 * t + 1]; }
 #pragma unroll
   for (int n = 0; n < IN8; ++n) {
     if constexpr (P::R == 2) {
@@ -75,8 +87,13 @@ __device__ __forceinline__ void mma_layer(const typename P::T (&in)[NM][IN8][P::
         const double2 w = *reinterpret_cast<const double2*>(blocks + ((n * OUT8 + o) * 32 + lane) * 16);
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
-          dmma884(out[m][o], in[m][n][0], w.x);  // k-step 2n   : features 8n + {0,2,4,6}
-          dmma884(out[m][o], in[m][n][1], w.y);  // k-step 2n+1 : features 8n + {1,3,5,7}
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {  // k-step 2n+j: features 8n + {j, j+2, j+4, j+6}
+            const int q = 2 * n + j, s = q % NS;
+            const double a = in[m][n][j], b = j ? w.y : w.x;
+            if (q < NS) dmma884(acc[s][m][o], a, b, s == 0 ? b0[o] : 0.0, s == 0 ? b1[o] : 0.0);
+            else dmma884(acc[s][m][o], a, b, acc[s][m][o][0], acc[s][m][o][1]);
+          }
         }
       }
     } else {
@@ -98,38 +115,34 @@ __device__ __forceinline__ void mma_layer(const typename P::T (&in)[NM][IN8][P::
         const uint4 w = *reinterpret_cast<const uint4*>(blocks + ((n * OUT8 + o) * 32 + lane) * 16);  // b0hi b1hi b0lo b1lo
 #pragma unroll
         for (int m = 0; m < NM; ++m) {
-          mma1688_tf32(out[m][o], alo[m][0], alo[m][1], alo[m][2], alo[m][3], w.x, w.y);
-          mma1688_tf32(out[m][o], ahi[m][0], ahi[m][1], ahi[m][2], ahi[m][3], w.z, w.w);
-          mma1688_tf32(out[m][o], ahi[m][0], ahi[m][1], ahi[m][2], ahi[m][3], w.x, w.y);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {  // small terms first: A_lo*B_hi, A_hi*B_lo, A_hi*B_hi
+            const int q = 3 * n + j, s = q % NS;
+            const uint32_t wb0 = j == 1 ? w.z : w.x, wb1 = j == 1 ? w.w : w.y;
+            const uint32_t(&af)[4] = j == 0 ? alo[m] : ahi[m];
+            if (q < NS) {
+              const float c0 = s == 0 ? b0[o] : 0.f, c1 = s == 0 ? b1[o] : 0.f;
+              mma1688_tf32(acc[s][m][o], af, wb0, wb1, c0, c1, c0, c1);
+            } else {
+              mma1688_tf32(acc[s][m][o], af, wb0, wb1, acc[s][m][o][0], acc[s][m][o][1], acc[s][m][o][2], acc[s][m][o][3]);
+            }
+          }
         }
       }
     }
   }
-  if (ACT) {
 #pragma unroll
-    for (int m = 0; m < NM; ++m)
+  for (int m = 0; m < NM; ++m)
 #pragma unroll
-      for (int o = 0; o < OUT8; ++o)
+    for (int o = 0; o < OUT8; ++o)
 #pragma unroll
-        for (int r = 0; r < P::R; ++r) out[m][o][r] = t_max(out[m][o][r], slope * out[m][o][r]);
-  }
+      for (int r = 0; r < P::R; ++r) {
+        T v = acc[0][m][o][r];
+#pragma unroll
+        for (int s = 1; s < NS; ++s) v += acc[s][m][o][r];
+        out[m][o][r] = ACT ? t_max(v, slope * v) : v;
+      }
 }
-
-template <class P, int I8, int A8, int B8, int O8>
-struct Mlp3Mma {
-  static constexpr int kOff1 = mma_layer_bytes<P>(I8, A8);
-  static constexpr int kOff2 = kOff1 + mma_layer_bytes<P>(A8, B8);
-  static constexpr int kBytes = kOff2 + mma_layer_bytes<P>(B8, O8);
-  template <int NM>
-  static __device__ __forceinline__ void eval(const unsigned char* __restrict__ w, const typename P::T (&x)[NM][I8][P::R],
-                                              typename P::T (&y)[NM][O8][P::R], typename P::T slope, int lane) {
-    typename P::T h1[NM][A8][P::R];
-    mma_layer<P, NM, I8, A8, true>(x, h1, w, slope, lane);
-    typename P::T h2[NM][B8][P::R];
-    mma_layer<P, NM, A8, B8, true>(h1, h2, w + kOff1, slope, lane);
-    mma_layer<P, NM, B8, O8, false>(h2, y, w + kOff2, slope, lane);
-  }
-};
 
 // ---- staging between one-thread-per-sample rows and the accumulator layout --------------------------------
 // stage[row][F] of T (F features, padded row stride FS); lane (g,t) of m-tile m holds features (8n+2t, 8n+2t+1)
@@ -161,9 +174,26 @@ __device__ __forceinline__ void store_blocks(typename P::T* __restrict__ stage, 
     }
 }
 
+// three-layer MLP layout  I8 -> A8 -> B8 -> O8 (in 8-feature blocks)
+template <class P, int I8, int A8, int B8, int O8>
+struct Mlp3Mma {
+  static constexpr int kOff1 = mma_layer_bytes<P>(I8, A8);
+  static constexpr int kOff2 = kOff1 + mma_layer_bytes<P>(A8, B8);
+  static constexpr int kBytes = kOff2 + mma_layer_bytes<P>(B8, O8);
+  template <int NM>
+  static __device__ __forceinline__ void eval(const unsigned char* __restrict__ w, const typename P::T (&x)[NM][I8][P::R],
+                                              typename P::T (&y)[NM][O8][P::R], typename P::T slope, int lane) {
+    typename P::T h1[NM][A8][P::R];
+    mma_layer<P, NM, I8, A8, true>(x, h1, w, slope, lane);
+    typename P::T h2[NM][B8][P::R];
+    mma_layer<P, NM, A8, B8, true>(h1, h2, w + kOff1, slope, lane);
+    mma_layer<P, NM, B8, O8, false>(h2, y, w + kOff2, slope, lane);
+  }
+};
+
 // ---- models ---------------------------------------------------------------------------------------------
-// Warp-cooperative predict(): every lane passes its own sample's (x,u) (lanes >= NM*MT pass anything), all lanes
-// take part in the mma tiles, and each lane gets its sample's state advanced in place.
+// Warp-cooperative predict(): every lane passes the (x,u) of the sample row it holds (rows >= NM*MT are mirrors or
+// don't-cares), all lanes take part in the mma tiles, and each lane gets its row's state advanced in place.
 template <class P, int NX_, int NU_, int H1, int H2>
 struct ModelMlpMma {
   static_assert(NX_ + NU_ <= 8 && NX_ <= 8, "one 8-feature input/output block");
@@ -175,12 +205,14 @@ struct ModelMlpMma {
   static constexpr int kStageElems = 32 * kInStride + 32 * kOutStride;
   static constexpr int kMacs = (NX_ + NU_) * H1 + H1 * H2 + H2 * NX_;
   template <typename ST, int NM>
-  static __device__ __forceinline__ void predict(const unsigned char* __restrict__ w, T slope, T* __restrict__ stage, int lane,
+  static __device__ __forceinline__ void predict(const unsigned char* __restrict__ w, T slope, T* __restrict__ stage, int lane, int row,
                                                  ST (&x)[NX], const ST (&u)[NU]) {
     T* sin = stage;
     T* sout = stage + 32 * kInStride;
+    if (lane == row) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sin[lane * kInStride + i] = i < NX ? (T)x[i] : (i < NX + NU ? (T)u[i - NX] : (T)0);
+      for (int i = 0; i < 8; ++i) sin[row * kInStride + i] = i < NX ? (T)x[i] : (i < NX + NU ? (T)u[i - NX] : (T)0);
+    }
     __syncwarp();
     T in[NM][1][P::R], dx[NM][1][P::R];
     load_blocks<P, NM, 1, kInStride>(sin, in, lane);
@@ -188,7 +220,7 @@ struct ModelMlpMma {
     store_blocks<P, NM, 1, kOutStride>(sout, dx, 0, lane);
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] += (ST)sout[lane * kOutStride + i];
+    for (int i = 0; i < NX; ++i) x[i] += (ST)sout[row * kOutStride + i];
     __syncwarp();
   }
 };
@@ -211,41 +243,54 @@ struct ModelRexMma {
   static constexpr int kStageElems = 32 * kInStride + 32 * kOutStride;
   static constexpr int kMacs = (NX_ + NU_) * E1 + E1 * E2 + E2 * NZ + NZ * D1 + D1 * D2 + D2 * NV + NX_ * C1 + C1 * C2 + C2 * NX_ * NV + NX_ * NV;
   template <typename ST, int NM>
-  static __device__ __forceinline__ void predict(const unsigned char* __restrict__ w, T slope, T* __restrict__ stage, int lane,
+  static __device__ __forceinline__ void predict(const unsigned char* __restrict__ w, T slope, T* __restrict__ stage, int lane, int row,
                                                  ST (&x)[NX], const ST (&u)[NU]) {
     T* sin = stage;
     T* sout = stage + 32 * kInStride;
+    PROF_T0();
+    if (lane == row) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sin[lane * kInStride + i] = i < NX ? (T)x[i] : (i < NX + NU ? (T)u[i - NX] : (T)0);
+      for (int i = 0; i < 8; ++i) sin[row * kInStride + i] = i < NX ? (T)x[i] : (i < NX + NU ? (T)u[i - NX] : (T)0);
+    }
     __syncwarp();
     T in[NM][1][P::R];
     load_blocks<P, NM, 1, kInStride>(sin, in, lane);
+    PROF(2);
     {
-      T v[NM][1][P::R];
+      // The encoder->latent-dynamics chain and the decoder are independent until dx = C v: their layers are
+      // issued alternately so that the tensor pipe always has a second dependency chain to run.
+      // (The decoder's extractor-folded first layer has zero weights on the action features: same input block.)
+      T e1[NM][E1 / 8][P::R], c1[NM][C1 / 8][P::R];
+      mma_layer<P, NM, 1, E1 / 8, true>(in, e1, w, slope, lane);
+      mma_layer<P, NM, 1, C1 / 8, true>(in, c1, w + kOffDec, slope, lane);
+      T e2[NM][E2 / 8][P::R], c2[NM][C2 / 8][P::R];
+      mma_layer<P, NM, E1 / 8, E2 / 8, true>(e1, e2, w + Enc::kOff1, slope, lane);
+      mma_layer<P, NM, C1 / 8, C2 / 8, true>(c1, c2, w + kOffDec + Dec::kOff1, slope, lane);
+      T z[NM][1][P::R];
+      mma_layer<P, NM, E2 / 8, 1, false>(e2, z, w + Enc::kOff2, slope, lane);
       {
-        T z[NM][1][P::R];
-        Enc::template eval<NM>(w, in, z, slope, lane);
-        Dyn::template eval<NM>(w + kOffDyn, z, v, slope, lane);
+        T C[NM][CO8][P::R];
+        mma_layer<P, NM, C2 / 8, CO8, false>(c2, C, w + kOffDec + Dec::kOff2, slope, lane);
+        store_blocks<P, NM, CO8, kOutStride>(sout, C, 0, lane);
       }
+      PROF(3);
+      T v[NM][1][P::R];
+      Dyn::template eval<NM>(w + kOffDyn, z, v, slope, lane);
       store_blocks<P, NM, 1, kOutStride>(sout, v, 8 * CO8, lane);
-    }
-    {
-      // the decoder's (extractor-folded) first layer has zero weights on the action features: same input block
-      T C[NM][CO8][P::R];
-      Dec::template eval<NM>(w + kOffDec, in, C, slope, lane);
-      store_blocks<P, NM, CO8, kOutStride>(sout, C, 0, lane);
+      PROF(4);
     }
     __syncwarp();
-    const T* row = sout + lane * kOutStride;
+    const T* r = sout + row * kOutStride;
     const T* d0 = reinterpret_cast<const T*>(w + kOffD0);
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       T dx = d0[i];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) dx = t_fma(row[i * NV + j], row[8 * CO8 + j], dx);
+      for (int j = 0; j < NV; ++j) dx = t_fma(r[i * NV + j], r[8 * CO8 + j], dx);
       x[i] += (ST)dx;
     }
     __syncwarp();
+    PROF(6);
   }
 };
 
@@ -257,16 +302,20 @@ struct MmaSmem {
   static constexpr size_t kSampler = kCost + align16<int>(sizeof(CostS<ST, CT>));
   static constexpr size_t kU = kSampler + align16<int>(sizeof(SamplerS<ST>));
   static __host__ __device__ constexpr size_t stage_off(int T_) { return kU + align16<int>(sizeof(ST) * (size_t)T_ * kMaxNu); }
-  static __host__ __device__ constexpr size_t bytes(int T_, int warps) {
-    return stage_off(T_) + (size_t)warps * align16<int>(sizeof(T) * Model::kStageElems);
+  static __host__ __device__ constexpr size_t warp_bytes(int T_, int sw, bool pre) {
+    return align16<int>(sizeof(T) * Model::kStageElems) + (pre ? align16<int>(sizeof(float) * (size_t)T_ * sw * Model::NU) : 0);
   }
+  static __host__ __device__ constexpr size_t bytes(int T_, int warps, int sw, bool pre) { return stage_off(T_) + (size_t)warps * warp_bytes(T_, sw, pre); }
 };
 
-template <class Model, typename ST, typename CT, int NM>
+// PRE: draw the whole horizon's standard normals into shared memory before the loop (all 32 lanes, independent
+// Philox blocks -> instruction-level parallelism), instead of one dependent Philox + Box-Muller chain per step.
+template <class Model, typename ST, typename CT, int NM, bool PRE>
 __global__ void __launch_bounds__(128) rollout_mma_kernel(const RolloutArgs a) {
   using P_T = typename Model::T;
   constexpr int NX = Model::NX, NU = Model::NU;
   constexpr int SW = NM * (sizeof(P_T) == 8 ? PolicyF64::MT : PolicyTF32x3::MT);  // samples per warp
+  constexpr int NPARTS = 32 / SW;                                                  // lanes holding the same sample
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using L = MmaSmem<Model, ST, CT>;
   unsigned char* w = smem_raw;
@@ -275,7 +324,9 @@ __global__ void __launch_bounds__(128) rollout_mma_kernel(const RolloutArgs a) {
   ST* Ush = reinterpret_cast<ST*>(smem_raw + L::kU);
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int T = a.src.T;
-  P_T* stage = reinterpret_cast<P_T*>(smem_raw + L::stage_off(T) + (size_t)warp * align16<int>(sizeof(P_T) * Model::kStageElems));
+  unsigned char* wbase = smem_raw + L::stage_off(T) + (size_t)warp * L::warp_bytes(T, SW, PRE);
+  P_T* stage = reinterpret_cast<P_T*>(wbase);
+  float* zpre = reinterpret_cast<float*>(wbase + align16<int>(sizeof(P_T) * Model::kStageElems));  // [T][SW][NU]
   {
     const int4* gw = reinterpret_cast<const int4*>(a.weights);
     int4* sw = reinterpret_cast<int4*>(w);
@@ -287,22 +338,38 @@ __global__ void __launch_bounds__(128) rollout_mma_kernel(const RolloutArgs a) {
       Ush[t * kMaxNu + d] = (ST)(ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d]);
     }
   }
+  const int row = lane % SW, part = lane / SW;
+  const int kbase = (blockIdx.x * (nthr >> 5) + warp) * SW;
+  const bool live = kbase + row < a.K_local;
+  const int k = live ? kbase + row : a.K_local - 1;
+  const bool use_pre = PRE && a.src.mode == kModePhilox;
+  if (use_pre) {
+#pragma unroll 2
+    for (int item = lane; item < T * SW; item += 32) {
+      const int t = item / SW, r = item % SW;
+      const int kr = min(kbase + r, a.K_local - 1);
+      float z[4];
+      philox_normal4(a.src.seed, a.src.call, (uint32_t)(a.src.sample_offset + kr), (uint32_t)t, z);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) zpre[item * NU + i] = z[i];
+    }
+  }
   __syncthreads();
 
-  const int kk = (blockIdx.x * (nthr >> 5) + warp) * SW + lane;
-  const bool live = lane < SW && kk < a.K_local;
-  const int k = live ? kk : a.K_local - 1;
   ST x[NX];
 #pragma unroll
   for (int i = 0; i < NX; ++i) x[i] = (ST)a.state[i];
-  ST cost = (ST)0, pert = (ST)0;
+  double cost = 0.0;  // running-cost accumulator: float64 in every mode (one add per step)
+  ST pert = (ST)0;
   const P_T slope = (P_T)a.slope;
   const ST bad2 = (ST)(a.bad_norm * a.bad_norm);
 
 #pragma unroll 1
   for (int t = 0; t < T; ++t) {
     ST u[NU], npost[NU];
-    pert += sample_action<ST, NU>(a.src, sp, Ush + t * kMaxNu, k, t, u, npost);
+    PROF_T0();
+    pert += sample_action<ST, NU>(a.src, sp, Ush + t * kMaxNu, k, t, u, npost, use_pre ? zpre + (t * SW + row) * NU : nullptr);
+    PROF(0);
     bool bad = false;
     if (a.has_guard) {
       ST n2 = (ST)0;
@@ -316,30 +383,40 @@ __global__ void __launch_bounds__(128) rollout_mma_kernel(const RolloutArgs a) {
         for (int i = 0; i < NU; ++i) u[i] = (ST)0;
       }
     }
-    Model::template predict<ST, NM>(w, slope, stage, lane, x, u);
+    PROF(1);
+    Model::template predict<ST, NM>(w, slope, stage, lane, row, x, u);
+    PROF_RESET();
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       if ((a.wrap_mask >> i) & 1u) x[i] = angle_normalize<ST>(x[i]);
       if (bad) x[i] = (ST)0;
     }
-    cost += (ST)running_cost<ST, CT, NX, NU>(cs, x, u);
-    if (a.states_out != nullptr && live) {
+    PROF(7);
+    cost += (double)running_cost<ST, CT, NX, NU>(cs, x, u, part, NPARTS);
+    PROF(8);
+    if (a.states_out != nullptr && live && part == 0) {
       double* so = a.states_out + ((size_t)k * T + t) * NX;
 #pragma unroll
       for (int i = 0; i < NX; ++i) so[i] = (double)x[i];
     }
   }
-  ST total = cost + (ST)terminal_cost<ST, CT, NX>(cs, x);
-  total += pert;
-  if (live) a.cost_out[k] = (double)total;
+  // the mirror lanes' shares of the running cost (fixed order: part 1, 2, 3 added to part 0)
+  if (NPARTS > 1) {
+    const double mine = cost;
+#pragma unroll
+    for (int p = 1; p < NPARTS; ++p) cost += __shfl_sync(0xffffffffu, mine, (row + p * SW) & 31);
+  }
+  double total = cost + (double)terminal_cost<ST, CT, NX>(cs, x);
+  total += (double)pert;
+  if (live && part == 0) a.cost_out[k] = total;
 }
 
-template <class Model, typename ST, typename CT, int NM>
+template <class Model, typename ST, typename CT, int NM, bool PRE>
 cudaError_t launch_rollout_mma(const RolloutArgs& a, int block, cudaStream_t stream) {
-  auto kern = rollout_mma_kernel<Model, ST, CT, NM>;
+  auto kern = rollout_mma_kernel<Model, ST, CT, NM, PRE>;
   constexpr int SW = NM * (sizeof(typename Model::T) == 8 ? PolicyF64::MT : PolicyTF32x3::MT);
   const int warps = block / 32;
-  const size_t smem = MmaSmem<Model, ST, CT>::bytes(a.src.T, warps);
+  const size_t smem = MmaSmem<Model, ST, CT>::bytes(a.src.T, warps, SW, PRE);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -15,7 +15,7 @@ struct ModelVariant {
   int macs;
   rollout_launch_fn f64_s1, mixed_s1, mixed_s2, f32_s1, f32_s2;  // one-thread-per-sample FMA kernels
   rollout_launch_fn f64_mma[3];   // DMMA kernels, NM = 1, 2, 4 m-tiles (8, 16, 32 samples) per warp
-  rollout_launch_fn tf32_mma[2];  // 3xTF32 kernels, NM = 1, 2 (16, 32 samples per warp); float64 state and cost
+  rollout_launch_fn tf32_mma[2];  // 3xTF32 kernels, NM = 1, 2 (16, 32 samples per warp); float32 state and cost terms, float64 cost sum
 };
 
 template <class MF, class MD, bool WITH_S2>
@@ -44,11 +44,11 @@ template <class MM64, class MM32>
 void add_mma(ModelVariant& v) {
   v.bytes_mma_f64 = MM64::kBytes;
   v.bytes_mma_tf32 = MM32::kBytes;
-  v.f64_mma[0] = &launch_rollout_mma<MM64, double, double, 1>;
-  v.f64_mma[1] = &launch_rollout_mma<MM64, double, double, 2>;
-  v.f64_mma[2] = &launch_rollout_mma<MM64, double, double, 4>;
-  v.tf32_mma[0] = &launch_rollout_mma<MM32, double, float, 1>;
-  v.tf32_mma[1] = &launch_rollout_mma<MM32, double, float, 2>;
+  v.f64_mma[0] = &launch_rollout_mma<MM64, double, double, 1, true>;
+  v.f64_mma[1] = &launch_rollout_mma<MM64, double, double, 2, true>;
+  v.f64_mma[2] = &launch_rollout_mma<MM64, double, double, 4, false>;
+  v.tf32_mma[0] = &launch_rollout_mma<MM32, float, float, 1, true>;
+  v.tf32_mma[1] = &launch_rollout_mma<MM32, float, float, 2, false>;
 }
 
 const ModelVariant* variant_rex_push();   // nx5 nu3, enc 8-16-32-5, dyn 5-32-32-5, dec 5(2)-16-32-25
