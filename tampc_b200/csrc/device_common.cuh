@@ -570,4 +570,25 @@ __device__ __forceinline__ void stage_cost(CostS<ST, CT>& dst, const tampc_cost_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Shared-memory image.  Everything a rollout CTA needs that does not change between commands — packed network
+// weights, CostS and SamplerS already converted to the kernel's types — sits contiguously in global memory in
+// exactly the shared-memory layout (prep_image_kernel, run on set_model / set_cost), so a CTA's prologue is one
+// flat asynchronous copy (LDGSTS, 16 bytes per request, all requests in flight at once) instead of dozens of
+// dependent global round trips.
+__device__ __forceinline__ void copy_image_async(unsigned char* smem_dst, const void* __restrict__ gsrc, int bytes, int tid, int nthreads) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(gsrc);
+  for (int off = tid * 16; off < bytes; off += nthreads * 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void copy_image_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <typename ST, typename CT>
+__global__ void prep_image_kernel(unsigned char* image, int cost_off, int sampler_off, const tampc_cost_desc* cost, const SamplerD* sampler) {
+  stage_cost<ST, CT>(*reinterpret_cast<CostS<ST, CT>*>(image + cost_off), *cost, threadIdx.x, blockDim.x);
+  stage_sampler<ST>(*reinterpret_cast<SamplerS<ST>*>(image + sampler_off), *sampler, threadIdx.x, blockDim.x);
+}
+
 }  // namespace tampc

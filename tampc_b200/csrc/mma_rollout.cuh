@@ -328,15 +328,12 @@ __global__ void __launch_bounds__(128) rollout_mma_kernel(const RolloutArgs a) {
   P_T* stage = reinterpret_cast<P_T*>(wbase);
   float* zpre = reinterpret_cast<float*>(wbase + align16<int>(sizeof(P_T) * Model::kStageElems));  // [T][SW][NU]
   {
-    const int4* gw = reinterpret_cast<const int4*>(a.weights);
-    int4* sw = reinterpret_cast<int4*>(w);
-    for (int i = tid; i < Model::kBytes / 16; i += nthr) sw[i] = gw[i];
-    stage_cost<ST, CT>(cs, *a.cost, tid, nthr);
-    stage_sampler<ST>(sp, *a.sampler, tid, nthr);
+    copy_image_async(smem_raw, a.image, (int)L::kU, tid, nthr);
     for (int i = tid; i < T * NU; i += nthr) {
       int t = i / NU, d = i % NU, ts = t + a.shift;
       Ush[t * kMaxNu + d] = (ST)(ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d]);
     }
+    copy_image_wait();
   }
   const int row = lane % SW, part = lane / SW;
   const int kbase = (blockIdx.x * (nthr >> 5) + warp) * SW;
@@ -409,6 +406,180 @@ __global__ void __launch_bounds__(128) rollout_mma_kernel(const RolloutArgs a) {
   double total = cost + (double)terminal_cost<ST, CT, NX>(cs, x);
   total += (double)pert;
   if (live && part == 0) a.cost_out[k] = total;
+}
+
+// ---- two-warp pipelined variant for small K (latency-bound) ----------------------------------------------
+// One CTA = one m-tile of 16 samples and two warps:
+//   warp 0 ("dynamics")  guard -> network chain -> state update -> wrap, and publishes x_{t+1} into a small ring;
+//   warp 1 ("cost")      trails by a step: running cost, perturbation cost, terminal cost, final write.
+// The perturbed actions of the whole horizon are drawn by both warps before the loop (they do not depend on the
+// state), so the horizon loop's critical path is only what the recurrence x_{t+1} = f(x_t, u_t) really needs.
+template <class Model, int RING>
+struct PipeSmem {
+  using T = typename Model::T;
+  static constexpr int SW = PolicyTF32x3::MT;
+  static constexpr size_t kCost = align16<int>(Model::kBytes);
+  static constexpr size_t kSampler = kCost + align16<int>(sizeof(CostS<float, float>));
+  static constexpr size_t kU = kSampler + align16<int>(sizeof(SamplerS<float>));
+  static __host__ __device__ constexpr size_t stage_off(int T_) { return kU + align16<int>(sizeof(float) * (size_t)T_ * kMaxNu); }
+  static __host__ __device__ constexpr size_t upre_off(int T_) { return stage_off(T_) + align16<int>(sizeof(T) * Model::kStageElems); }
+  static __host__ __device__ constexpr size_t ring_off(int T_) { return upre_off(T_) + align16<int>(sizeof(float) * (size_t)T_ * SW * Model::NU); }
+  static __host__ __device__ constexpr size_t flags_off(int T_) { return ring_off(T_) + align16<int>(sizeof(float) * RING * SW * (Model::NX + 1)); }
+  static __host__ __device__ constexpr size_t bytes(int T_) { return flags_off(T_) + 16; }
+};
+
+template <class Model>
+__global__ void __launch_bounds__(64) rollout_mma_pipe_kernel(const RolloutArgs a) {
+  static_assert(sizeof(typename Model::T) == 4, "pipelined variant is for the TF32x3 policy");
+  constexpr int NX = Model::NX, NU = Model::NU, SW = PolicyTF32x3::MT, RING = 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using L = PipeSmem<Model, RING>;
+  unsigned char* w = smem_raw;
+  CostS<float, float>& cs = *reinterpret_cast<CostS<float, float>*>(smem_raw + L::kCost);
+  SamplerS<float>& sp = *reinterpret_cast<SamplerS<float>*>(smem_raw + L::kSampler);
+  float* Ush = reinterpret_cast<float*>(smem_raw + L::kU);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = a.src.T;
+  float* stage = reinterpret_cast<float*>(smem_raw + L::stage_off(T));
+  float* upre = reinterpret_cast<float*>(smem_raw + L::upre_off(T));   // [T][SW][NU] actions the dynamics sees
+  float* ring = reinterpret_cast<float*>(smem_raw + L::ring_off(T));   // [RING][SW][NX+1] x_{t+1} and the bad flag
+  volatile int* flags = reinterpret_cast<volatile int*>(smem_raw + L::flags_off(T));  // [0] produced, [1] consumed
+  {
+    copy_image_async(smem_raw, a.image, (int)L::kU, tid, 64);
+    for (int i = tid; i < T * NU; i += 64) {
+      int t = i / NU, d = i % NU, ts = t + a.shift;
+      Ush[t * kMaxNu + d] = (float)(ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d]);
+    }
+    if (tid < 2) flags[tid] = 0;
+    copy_image_wait();
+  }
+  __syncthreads();
+  const int row = lane % SW, part = lane / SW;
+  const int kbase = blockIdx.x * SW;
+  const bool live = kbase + row < a.K_local;
+  const int k = live ? kbase + row : a.K_local - 1;
+  // ---- every perturbed action of the horizon, drawn by all 64 threads (independent items)
+#pragma unroll 2
+  for (int item = tid; item < T * SW; item += 64) {
+    const int t = item / SW, r = item % SW;
+    float u[NU], npost[NU];
+    sample_action<float, NU>(a.src, sp, Ush + t * kMaxNu, min(kbase + r, a.K_local - 1), t, u, npost);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) upre[item * NU + i] = u[i];
+  }
+  __syncthreads();
+  const float slope = (float)a.slope;
+  // Warps are bound to SM sub-partitions by their index in the CTA: alternate the roles with the CTA parity so that
+  // the dynamics warps (tensor-pipe heavy) of co-resident CTAs do not all share one sub-partition.
+  if (((warp ^ blockIdx.x) & 1) == 0) {
+    // ================= dynamics warp
+    float x[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = (float)a.state[i];
+    const float bad2 = (float)(a.bad_norm * a.bad_norm);
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+      float u[NU];
+      PROF_T0();
+#pragma unroll
+      for (int i = 0; i < NU; ++i) u[i] = upre[(t * SW + row) * NU + i];
+      bool bad = false;
+      if (a.has_guard) {
+        float n2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) n2 = __fmaf_rn(x[i], x[i], n2);
+        bad = n2 > bad2;
+        if (bad) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) x[i] = 0.f;
+#pragma unroll
+          for (int i = 0; i < NU; ++i) u[i] = 0.f;
+        }
+      }
+      PROF(1);
+      Model::template predict<float, 1>(w, slope, stage, lane, row, x, u);
+      PROF_RESET();
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        if ((a.wrap_mask >> i) & 1u) x[i] = angle_normalize<float>(x[i]);
+        if (bad) x[i] = 0.f;
+      }
+      PROF(7);
+      if (t >= RING) {  // never ahead of the cost warp by a whole ring (it is the faster of the two)
+        while (flags[1] < t - RING + 1) __nanosleep(64);
+      }
+      if (part == 0) {
+        float* slot = ring + ((t % RING) * SW + row) * (NX + 1);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) slot[i] = x[i];
+        slot[NX] = bad ? 1.f : 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); flags[0] = t + 1; }
+      PROF(9);
+      if (a.states_out != nullptr && live && part == 0) {
+        double* so = a.states_out + ((size_t)k * T + t) * NX;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) so[i] = (double)x[i];
+      }
+    }
+  } else {
+    // ================= cost warp (two lanes per sample share the trap-set terms)
+    double cost = 0.0;
+    float pert = 0.f;
+    float x[NX];
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+      float u[NU];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) u[i] = upre[(t * SW + row) * NU + i];
+      // perturbation cost of this step: sum_i u_i (lambda * (u - U_t) @ Sigma^-1)_i  (controller.py:395,400)
+      if (a.src.mode == kModePhilox || a.src.mode == kModeInjected) {
+        float pc = 0.f;
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          float ac = 0.f;
+#pragma unroll
+          for (int j = 0; j < NU; ++j) ac = __fmaf_rn(u[j] - Ush[t * kMaxNu + j], sp.lsi[j * kMaxNu + i], ac);
+          pc = __fmaf_rn(u[i], ac, pc);
+        }
+        pert += pc;
+      }
+      while (flags[0] <= t) __nanosleep(64);
+      __threadfence_block();
+      const float* slot = ring + ((t % RING) * SW + row) * (NX + 1);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = slot[i];
+      const bool bad = slot[NX] != 0.f;
+      __syncwarp();
+      if (lane == 0) flags[1] = t + 1;
+      if (bad) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) u[i] = 0.f;
+      }
+      cost += (double)running_cost<float, float, NX, NU>(cs, x, u, part, 2);
+    }
+    const double mine = cost;
+    cost += __shfl_sync(0xffffffffu, mine, (row + SW) & 31);
+    double total = cost + (double)terminal_cost<float, float, NX>(cs, x);
+    total += (double)pert;
+    if (live && part == 0) a.cost_out[k] = total;
+  }
+}
+
+template <class Model>
+cudaError_t launch_rollout_mma_pipe(const RolloutArgs& a, int /*block*/, cudaStream_t stream) {
+  auto kern = rollout_mma_pipe_kernel<Model>;
+  const size_t smem = PipeSmem<Model, 4>::bytes(a.src.T);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const int grid = (a.K_local + PolicyTF32x3::MT - 1) / PolicyTF32x3::MT;
+  kern<<<grid, 64, smem, stream>>>(a);
+  return cudaGetLastError();
 }
 
 template <class Model, typename ST, typename CT, int NM, bool PRE>

@@ -69,6 +69,7 @@ struct tampc_mppi {
   size_t weights_bytes = 0;
   int n_weight_elems = 0;
   bool use_mma = false;  // the staged weights are in the mma-path layout
+  int img_cost_off = 0, img_sampler_off = 0, img_bytes = 0;  // shared-memory image offsets inside d_weights
 
   double* h_pin = nullptr;  // pinned staging: [0..15] in, [16..31] out
   int n_chunks = 0, chunk = 0;
@@ -395,6 +396,12 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     const int warps = (K + (mt << idx) - 1) / (mt << idx);
     p.block = warps >= 2 * 148 * 4 ? 128 : (warps >= 2 * 148 * 2 ? 64 : 32);
     p.fn = f64 ? v->f64_mma[idx] : v->tf32_mma[idx];
+    // latency-bound sizes: the two-warp pipelined kernel (dynamics warp + cost warp per 16-sample tile)
+    // (measured on B200: wins while at most two 16-sample tiles share an SM, i.e. K <= 4736; above that the
+    //  single-warp kernel's lower footprint wins.  TAMPC_PIPE=0/1 forces the choice.)
+    const int tiles = (K + 15) / 16, pipe_env = env_int("TAMPC_PIPE", -1);
+    const bool pipe = pipe_env >= 0 ? pipe_env != 0 : tiles <= 2 * 148;
+    if (!f64 && idx == 0 && v->tf32_pipe && pipe) { p.fn = v->tf32_pipe; p.block = 64; return p; }
   } else {
     const bool f64 = h->cfg.precision == TAMPC_PREC_F64;
     const bool has_s2 = !f64 && v->mixed_s2 != nullptr;
@@ -412,6 +419,20 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
   }
   if (eb == 32 || eb == 64 || eb == 128) p.block = eb;
   return p;
+}
+
+// (re)build the CostS / SamplerS parts of the shared-memory image in the types the selected kernels use
+int prep_image(tampc_mppi* h) {
+  if (!h->has_model || !h->has_cost) return TAMPC_OK;
+  unsigned char* img = reinterpret_cast<unsigned char*>(h->d_weights);
+  const int prec = h->cfg.precision;
+  if (prec == TAMPC_PREC_F64) prep_image_kernel<double, double><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, h->d_cost, h->d_sampler);
+  else if (prec == TAMPC_PREC_MIXED || (prec == TAMPC_PREC_TF32X3 && !h->use_mma))
+    prep_image_kernel<double, float><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, h->d_cost, h->d_sampler);
+  else prep_image_kernel<float, float><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, h->d_cost, h->d_sampler);
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return TAMPC_OK;
 }
 
 SampleSrc make_src(const tampc_mppi* h, int mode, uint64_t call, int T) {
@@ -436,8 +457,8 @@ int check_ready(tampc_mppi* h) {
 
 int launch_rollout_for(tampc_mppi* h, int mode, int shift, const double* d_U, int T, uint64_t call, bool keep_states) {
   RolloutArgs a{};
-  a.weights = h->d_weights;
-  a.n_weight_elems = h->n_weight_elems;
+  a.image = h->d_weights;
+  a.image_bytes = h->img_bytes;
   a.slope = h->model.leaky_slope;
   a.cost = h->d_cost;
   a.sampler = h->d_sampler;
@@ -748,7 +769,14 @@ TAMPC_API int tampc_mppi_set_model(tampc_mppi* h, const tampc_model_desc* desc, 
     }
     raw_bytes = (f64 ? 8 : 4) * elems;
   }
-  const size_t bytes = (raw_bytes + 15) & ~size_t(15);
+  // shared-memory image = packed networks | CostS | SamplerS, each 16-byte aligned (kernel-side layout structs)
+  const size_t wbytes = (raw_bytes + 15) & ~size_t(15);
+  size_t cost_sz, samp_sz;
+  if (f64) { cost_sz = sizeof(CostS<double, double>); samp_sz = sizeof(SamplerS<double>); }
+  else if (prec == TAMPC_PREC_MIXED || (prec == TAMPC_PREC_TF32X3 && !use_mma)) { cost_sz = sizeof(CostS<double, float>); samp_sz = sizeof(SamplerS<double>); }
+  else { cost_sz = sizeof(CostS<float, float>); samp_sz = sizeof(SamplerS<float>); }
+  const size_t cost_off = wbytes, samp_off = cost_off + ((cost_sz + 15) & ~size_t(15));
+  const size_t bytes = samp_off + ((samp_sz + 15) & ~size_t(15));
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   if (bytes > h->weights_bytes) {
@@ -759,12 +787,15 @@ TAMPC_API int tampc_mppi_set_model(tampc_mppi* h, const tampc_model_desc* desc, 
   }
   CUDA_TRY(h, cudaMemset(h->d_weights, 0, h->weights_bytes));
   CUDA_TRY(h, cudaMemcpy(h->d_weights, src, raw_bytes, cudaMemcpyHostToDevice));
-  h->n_weight_elems = (int)(bytes / (f64 ? 8 : 4));
+  h->n_weight_elems = (int)(wbytes / (f64 ? 8 : 4));
   h->use_mma = use_mma;
+  h->img_cost_off = (int)cost_off;
+  h->img_sampler_off = (int)samp_off;
+  h->img_bytes = (int)bytes;
   h->variant = pm.variant;
   h->model = *desc;
   h->has_model = true;
-  return TAMPC_OK;
+  return prep_image(h);
 }
 
 TAMPC_API int tampc_mppi_set_cost(tampc_mppi* h, const tampc_cost_desc* d) {
@@ -785,7 +816,7 @@ TAMPC_API int tampc_mppi_set_cost(tampc_mppi* h, const tampc_cost_desc* d) {
   CUDA_TRY(h, cudaMemcpyAsync(h->d_cost, d, sizeof *d, cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->has_cost = true;
-  return TAMPC_OK;
+  return prep_image(h);
 }
 
 TAMPC_API int tampc_mppi_set_nominal(tampc_mppi* h, const double* U, int32_t horizon) {
@@ -898,8 +929,8 @@ TAMPC_API int tampc_mppi_get_rollouts(tampc_mppi* h, const double* state, double
   if ((rc = ensure_states(h))) return rc;
   // one sample, nominal actions, states dumped; the per-sample cost buffer is left untouched via a K_local=1 view
   RolloutArgs a{};
-  a.weights = h->d_weights;
-  a.n_weight_elems = h->n_weight_elems;
+  a.image = h->d_weights;
+  a.image_bytes = h->img_bytes;
   a.slope = h->model.leaky_slope;
   a.cost = h->d_cost;
   a.sampler = h->d_sampler;

@@ -10,8 +10,8 @@
 namespace tampc {
 
 struct RolloutArgs {
-  const void* weights;  // packed network block in the kernel's network type
-  int n_weight_elems;
+  const void* image;    // shared-memory image: packed networks | CostS | SamplerS in the kernel's types
+  int image_bytes;
   double slope;
   const tampc_cost_desc* cost;
   const SamplerD* sampler;
@@ -50,18 +50,14 @@ __global__ void __launch_bounds__(128) rollout_kernel(const RolloutArgs a) {
 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int T = a.src.T;
-  {  // ---- stage weights (16-byte copies), constants and the (shifted) nominal sequence
-    const int4* gw = reinterpret_cast<const int4*>(a.weights);
-    int4* sw = reinterpret_cast<int4*>(w);
-    const int n16 = (int)((sizeof(NT) * (size_t)a.n_weight_elems) / 16);
-    for (int i = tid; i < n16; i += nthr) sw[i] = gw[i];
-    stage_cost<ST, CT>(cs, *a.cost, tid, nthr);
-    stage_sampler<ST>(sp, *a.sampler, tid, nthr);
+  {  // ---- stage the image (weights, cost program, sampler constants) and the (shifted) nominal sequence
+    copy_image_async(smem_raw, a.image, (int)L::kU, tid, nthr);
     for (int i = tid; i < T * NU; i += nthr) {
       int t = i / NU, d = i % NU;
       int ts = t + a.shift;
       Ush[t * kMaxNu + d] = (ST)(ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d]);
     }
+    copy_image_wait();
   }
   __syncthreads();
 

@@ -15,7 +15,8 @@ struct ModelVariant {
   int macs;
   rollout_launch_fn f64_s1, mixed_s1, mixed_s2, f32_s1, f32_s2;  // one-thread-per-sample FMA kernels
   rollout_launch_fn f64_mma[3];   // DMMA kernels, NM = 1, 2, 4 m-tiles (8, 16, 32 samples) per warp
-  rollout_launch_fn tf32_mma[2];  // 3xTF32 kernels, NM = 1, 2 (16, 32 samples per warp); float32 state and cost terms, float64 cost sum
+  rollout_launch_fn tf32_mma[2];
+  rollout_launch_fn tf32_pipe;    // two-warp pipelined 3xTF32 kernel for small K (16 samples per CTA)  // 3xTF32 kernels, NM = 1, 2 (16, 32 samples per warp); float32 state and cost terms, float64 cost sum
 };
 
 template <class MF, class MD, bool WITH_S2>
@@ -49,6 +50,7 @@ void add_mma(ModelVariant& v) {
   v.f64_mma[2] = &launch_rollout_mma<MM64, double, double, 4, false>;
   v.tf32_mma[0] = &launch_rollout_mma<MM32, float, float, 1, true>;
   v.tf32_mma[1] = &launch_rollout_mma<MM32, float, float, 2, false>;
+  v.tf32_pipe = &launch_rollout_mma_pipe<MM32>;
 }
 
 const ModelVariant* variant_rex_push();   // nx5 nu3, enc 8-16-32-5, dyn 5-32-32-5, dec 5(2)-16-32-25

@@ -20,18 +20,18 @@ int main(int argc, char** argv) {
   double* dU; cudaMalloc(&dU, T * 4 * 8); cudaMemset(dU, 0, T * 4 * 8);
   double hx[8] = {-0.4, 0.23, -0.6, 0, 0}; double* dx; cudaMalloc(&dx, 64); cudaMemcpy(dx, hx, 64, cudaMemcpyHostToDevice);
   double* dcost; cudaMalloc(&dcost, K * 8);
-  RolloutArgs a{}; a.weights = dw; a.slope = 0.01; a.cost = dc; a.sampler = ds; a.U = dU; a.shift = 1; a.state = dx;
+  RolloutArgs a{}; a.image = dw; /* prof tool: image = weights only; cost/sampler parts zero */ a.slope = 0.01; a.cost = dc; a.sampler = ds; a.U = dU; a.shift = 1; a.state = dx;
   a.src.mode = 0; a.src.seed = 1; a.src.call = 1; a.src.k_global = K; a.src.T = T; a.K_local = K; a.cost_out = dcost; a.wrap_mask = 4; a.has_guard = 1; a.bad_norm = 1e5;
   for (int rep = 0; rep < 2; ++rep) {
     unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_prof, z, sizeof z);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0);
-    cudaError_t e = (argc > 4 ? (NM == 1 ? launch_rollout_mma<Model, float, float, 1, true>(a, block, 0) : launch_rollout_mma<Model, float, float, 2, false>(a, block, 0)) : (NM == 1 ? launch_rollout_mma<Model, double, float, 1, true>(a, block, 0) : launch_rollout_mma<Model, double, float, 2, false>(a, block, 0)));
+    cudaError_t e = (argc > 4 && argv[4][0] == 'p') ? launch_rollout_mma_pipe<Model>(a, 64, 0) : (argc > 4 ? (NM == 1 ? launch_rollout_mma<Model, float, float, 1, true>(a, block, 0) : launch_rollout_mma<Model, float, float, 2, false>(a, block, 0)) : (NM == 1 ? launch_rollout_mma<Model, double, float, 1, true>(a, block, 0) : launch_rollout_mma<Model, double, float, 2, false>(a, block, 0)));
     cudaEventRecord(e1); cudaDeviceSynchronize(); float ms; cudaEventElapsedTime(&ms, e0, e1);
     unsigned long long g[16]; cudaMemcpyFromSymbol(g, g_prof, sizeof g);
-    const char* names[] = {"sample_action", "guard", "stage_in", "enc", "dyn", "dec", "stage_out+dx", "wrap", "cost"};
+    const char* names[] = {"sample_action", "guard", "stage_in", "enc", "dyn", "dec", "stage_out+dx", "wrap", "cost", "publish"};
     int SW = NM * 16; double warps = (double)((K + SW - 1) / SW);
     if (rep) { printf("K=%d NM=%d block=%d  %.1f us  err=%d\n", K, NM, block, ms * 1e3, (int)e); double tot = 0;
-      for (int i = 0; i < 9; ++i) { double c = g[i] / warps / T; tot += c; printf("  %-14s %8.0f cycles/step/warp\n", names[i], c); } printf("  %-14s %8.0f\n", "sum", tot); }
+      for (int i = 0; i < 10; ++i) { double c = g[i] / warps / T; tot += c; printf("  %-14s %8.0f cycles/step/warp\n", names[i], c); } printf("  %-14s %8.0f\n", "sum", tot); }
   }
   return 0;
 }
