@@ -125,7 +125,7 @@ def main():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('TAMPC_BENCH_PRECISION', 'mixed'))
+    ap.add_argument('--precision', default=os.environ.get('TAMPC_BENCH_PRECISION', 'tf32x3'))
     ap.add_argument('--cpu-steps', type=int, default=12, help='commands of the CPU baseline sample')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -233,11 +233,23 @@ def main():
         roofline = None
         if roll_ms is not None:
             achieved = K * T * flop_per_step / (roll_ms * 1e-3) * 1e-12
-            roofline = {"bound": "fp32_fma", "achieved": achieved, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-                        "frac": achieved / FP32_PEAK_TFLOPS, "traffic": None, "kernel": "rollout_kernel",
+            # the kernel is compute-bound (it moves ~100 KB of DRAM traffic per launch); which pipe bounds it
+            # depends on the arithmetic: every peak below was measured on this pool's B200 with tools/peaks
+            # (MEASURED_PEAKS.json holds only the HBM copy and the cuBLAS bf16 tcgen05 GEMM)
+            if args.precision == 'tf32x3':
+                bound, peak = "tensor", TF32_MMA_PEAK_TFLOPS / 3.0
+                src = ("mma.sync m16n8k8 tf32 measured {:.0f} TFLOP/s (profiles/mma_peaks_r1.jsonl) / 3 products per "
+                       "algorithmic MAC (error-compensated 3xTF32 split)").format(TF32_MMA_PEAK_TFLOPS)
+            elif args.precision == 'f64':
+                bound, peak = "tensor", FP64_TENSOR_PEAK_TFLOPS
+                src = "mma.sync m8n8k4 f64 (DMMA) measured (profiles/mma_peaks_r1.jsonl)"
+            else:
+                bound, peak = "fp32_fma", FP32_PEAK_TFLOPS
+                src = "FFMA2 register-operand peak measured (profiles/fma_peaks_r1.jsonl)"
+            roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                        "frac": achieved / peak, "traffic": None, "kernel": "rollout (fused K x T)",
                         "kernel_ms": roll_ms, "algorithmic_flop_per_launch": K * T * flop_per_step,
-                        "peak_source": "measured FFMA2 register-operand peak on this pool's B200 (tools/peaks, "
-                                       "profiles/fma_peaks_r1.jsonl); MEASURED_PEAKS.json holds only HBM and bf16 tensor"}
+                        "peak_source": src}
         # CPU baseline: bounded sample of the same workload on the host cores (oracle port, float64)
         torch.set_num_threads(os.cpu_count() or 1)
         zc, spec_c = load_push_spec(K_PER_GPU)
@@ -248,7 +260,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"f64": "f64", "mixed": "f32 networks, f64 state+cost", "f32": "f32"}.get(args.precision, args.precision),
+            "dtype": {"f64": "f64", "mixed": "f32 networks, f64 state+cost", "f32": "f32",
+                      "tf32x3": "3xTF32 (f32-equivalent) networks, f32 state, f64 cost sum"}.get(args.precision, args.precision),
             "data": "synthetic",
             "config": {"workload": "push_rex_extract_K8192_T40_P3", "K_per_gpu": K_PER_GPU, "K": K, "T": T,
                        "precision": args.precision, "noise": "on-device Philox4x32-10", "rollout_replicas_M": 1,

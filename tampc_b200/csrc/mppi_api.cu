@@ -72,6 +72,10 @@ struct tampc_mppi {
   int img_cost_off = 0, img_sampler_off = 0, img_bytes = 0;  // shared-memory image offsets inside d_weights
 
   double* h_pin = nullptr;  // pinned staging: [0..15] in, [16..31] out
+  double* h_map = nullptr;  // mapped pinned result block written by the combine kernel: action[4], stats[3], flag
+  double* d_map = nullptr;  // device alias of h_map
+  unsigned long long seq = 0;
+  double state_host[kMaxNx] = {0};  // start state of the next rollout (passed to the kernels by value)
   int n_chunks = 0, chunk = 0;
 
   // last command bookkeeping (for queries)
@@ -464,7 +468,7 @@ int launch_rollout_for(tampc_mppi* h, int mode, int shift, const double* d_U, in
   a.sampler = h->d_sampler;
   a.U = d_U;
   a.shift = shift;
-  a.state = h->d_state;
+  memcpy(a.state, h->state_host, sizeof a.state);
   a.src = make_src(h, mode, call, T);
   a.K_local = h->cfg.num_local;
   a.cost_out = h->d_costs;
@@ -560,6 +564,11 @@ int run_combine(tampc_mppi* h, const tampc_partial* partials, int n, int finaliz
   c.group = n;
   c.finalize = finalize;
   c.partial_out = partial_out ? partial_out : h->d_rank_partial;
+  if (finalize) {
+    c.host_out = h->d_map;
+    c.host_flag = reinterpret_cast<unsigned long long*>(h->d_map + 8);
+    c.seq = ++h->seq;
+  }
   combine_kernel<<<1, kCombineThreads, 0, h->stream>>>(c);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
@@ -568,8 +577,7 @@ int run_combine(tampc_mppi* h, const tampc_partial* partials, int n, int finaliz
 }
 
 int upload_state(tampc_mppi* h, const double* state) {
-  memcpy(h->h_pin, state, sizeof(double) * h->cfg.nx);
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_state, h->h_pin, sizeof(double) * h->cfg.nx, cudaMemcpyHostToDevice, h->stream));
+  memcpy(h->state_host, state, sizeof(double) * h->cfg.nx);  // travels as a kernel argument
   return TAMPC_OK;
 }
 
@@ -583,13 +591,23 @@ int upload_noise(tampc_mppi* h, int mode, const double* noise, int T) {
   return TAMPC_OK;
 }
 
+// The combine kernel stores action and stats straight into mapped pinned memory and then publishes the sequence
+// number; poll for it (a few microseconds sooner than a stream synchronise), fall back to the synchronise so that a
+// faulted kernel surfaces as an error instead of a hang.
 int download_action(tampc_mppi* h, double* action) {
-  double* out = h->h_pin + 16;
-  CUDA_TRY(h, cudaMemcpyAsync(out, h->d_action, sizeof(double) * h->cfg.nu, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaMemcpyAsync(out + 8, h->d_stats, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  memcpy(action, out, sizeof(double) * h->cfg.nu);
-  memcpy(h->last_stats, out + 8, sizeof(double) * 3);
+  volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(h->h_map + 8);
+  bool seen = false;
+  for (int spin = 0; spin < 200000; ++spin) {
+    if (*flag == h->seq) { seen = true; break; }
+    if ((spin & 1023) == 1023 && cudaStreamQuery(h->stream) != cudaErrorNotReady) break;
+  }
+  if (!seen) {
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (*flag != h->seq) { h->err = "combine kernel did not publish its result"; return TAMPC_ERR_CUDA; }
+  }
+  __sync_synchronize();
+  memcpy(action, h->h_map, sizeof(double) * h->cfg.nu);
+  memcpy(h->last_stats, h->h_map + kMaxNu, sizeof(double) * 3);
   return TAMPC_OK;
 }
 
@@ -696,6 +714,9 @@ TAMPC_API int tampc_mppi_create(const tampc_mppi_config* cfg, tampc_mppi** out) 
   CREATE_TRY(cudaMalloc(&h->d_action, sizeof(double) * kMaxNu));
   CREATE_TRY(cudaMalloc(&h->d_stats, sizeof(double) * 4));
   CREATE_TRY(cudaMallocHost(&h->h_pin, sizeof(double) * 32));
+  CREATE_TRY(cudaHostAlloc(&h->h_map, sizeof(double) * 16, cudaHostAllocMapped));
+  memset(h->h_map, 0, sizeof(double) * 16);
+  CREATE_TRY(cudaHostGetDevicePointer(&h->d_map, h->h_map, 0));
   SamplerD sd{};
   for (int i = 0; i < nu; ++i) {
     sd.mu[i] = cfg->noise_mu[i];
@@ -724,6 +745,7 @@ TAMPC_API void tampc_mppi_destroy(tampc_mppi* h) {
   cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_partials2);
   cudaFree(h->d_rank_partial); cudaFree(h->d_action); cudaFree(h->d_stats); cudaFree(h->d_weights);
   if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->h_map) cudaFreeHost(h->h_map);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -936,7 +958,7 @@ TAMPC_API int tampc_mppi_get_rollouts(tampc_mppi* h, const double* state, double
   a.sampler = h->d_sampler;
   a.U = h->d_U[h->cur];
   a.shift = 0;
-  a.state = h->d_state;
+  memcpy(a.state, h->state_host, sizeof a.state);
   a.src = make_src(h, kModeNominal, 0, h->T);
   a.K_local = 1;
   a.cost_out = h->d_stats + 3;

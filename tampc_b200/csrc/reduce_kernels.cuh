@@ -117,6 +117,9 @@ struct CombineArgs {
   double* action_out;    // (nu,) = U_out[0]
   double* stats_out;     // beta, eta, argmin
   tampc_partial* partial_out;
+  double* host_out;      // optional mapped pinned host memory: action[kMaxNu], stats[3] written straight to the host,
+  unsigned long long* host_flag;  // then the sequence number (after a system-scope fence) the host polls for
+  unsigned long long seq;
 };
 
 constexpr int kCombineThreads = 512;  // also the largest group
@@ -177,7 +180,10 @@ __global__ void __launch_bounds__(kCombineThreads) combine_kernel(const CombineA
       const double base = ts < a.T ? a.U[ts * a.nu + d] : a.sampler->u_init[d];
       const double v = base + sum / eta;
       a.U_out[i] = v;
-      if (t == 0) a.action_out[d] = v;
+      if (t == 0) {
+        a.action_out[d] = v;
+        if (a.host_out != nullptr) a.host_out[d] = v;  // zero-copy: straight into mapped pinned host memory
+      }
     } else {
       a.partial_out[blockIdx.x].wsum[i] = sum;
     }
@@ -187,12 +193,22 @@ __global__ void __launch_bounds__(kCombineThreads) combine_kernel(const CombineA
       a.stats_out[0] = beta;
       a.stats_out[1] = eta;
       a.stats_out[2] = (double)arg;
+      if (a.host_out != nullptr) { a.host_out[kMaxNu] = beta; a.host_out[kMaxNu + 1] = eta; a.host_out[kMaxNu + 2] = (double)arg; }
     } else {
       tampc_partial& o = a.partial_out[blockIdx.x];
       o.beta = beta;
       o.eta = eta;
       o.argmin = arg;
       o.count = cnt;
+    }
+  }
+  if (a.finalize && a.host_out != nullptr) {
+    // publish: order every thread's host stores before the sequence number the host polls for
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      *reinterpret_cast<volatile unsigned long long*>(a.host_flag) = a.seq;
+      __threadfence_system();
     }
   }
 }

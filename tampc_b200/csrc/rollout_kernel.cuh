@@ -17,7 +17,7 @@ struct RolloutArgs {
   const SamplerD* sampler;
   const double* U;      // nominal sequence (T, nu) BEFORE the shift
   int shift;            // 1: step t uses U[t+1] (u_init at the tail) = MPPI.command's roll; 0: U[t]
-  const double* state;  // (nx,) start state shared by all samples
+  double state[kMaxNx];  // start state shared by all samples, passed by value (no H2D copy, no dependent load)
   SampleSrc src;
   int K_local;
   double* cost_out;     // (K_local,)

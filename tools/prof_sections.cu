@@ -20,7 +20,7 @@ int main(int argc, char** argv) {
   double* dU; cudaMalloc(&dU, T * 4 * 8); cudaMemset(dU, 0, T * 4 * 8);
   double hx[8] = {-0.4, 0.23, -0.6, 0, 0}; double* dx; cudaMalloc(&dx, 64); cudaMemcpy(dx, hx, 64, cudaMemcpyHostToDevice);
   double* dcost; cudaMalloc(&dcost, K * 8);
-  RolloutArgs a{}; a.image = dw; /* prof tool: image = weights only; cost/sampler parts zero */ a.slope = 0.01; a.cost = dc; a.sampler = ds; a.U = dU; a.shift = 1; a.state = dx;
+  RolloutArgs a{}; a.image = dw; /* prof tool: image = weights only; cost/sampler parts zero */ a.slope = 0.01; a.cost = dc; a.sampler = ds; a.U = dU; a.shift = 1; memcpy(a.state, hx, sizeof hx);
   a.src.mode = 0; a.src.seed = 1; a.src.call = 1; a.src.k_global = K; a.src.T = T; a.K_local = K; a.cost_out = dcost; a.wrap_mask = 4; a.has_guard = 1; a.bad_norm = 1e5;
   for (int rep = 0; rep < 2; ++rep) {
     unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_prof, z, sizeof z);
