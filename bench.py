@@ -175,6 +175,7 @@ def main():
         clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    launches0 = mppi.stats['launches']
     wall0 = time.perf_counter()
     for e0, e1 in ev:
         with torch.cuda.stream(stream):
@@ -184,6 +185,7 @@ def main():
             e1.record()
     barrier()
     wall = time.perf_counter() - wall0
+    launches = mppi.stats['launches'] - launches0  # kernels of this library launched inside the timed region
     dev_ms = np.array([e0.elapsed_time(e1) for e0, e1 in ev])
     ms_per_step = float(dev_ms.mean())
 
@@ -215,8 +217,16 @@ def main():
         lat.append(time.perf_counter() - t0)
     barrier()
     e2e_wall = time.perf_counter() - t_all0
+    # The timed regions last milliseconds, shorter than nvidia-smi's sampling period: keep the identical load running
+    # for another half second so that the clock / throttle record has samples taken under this load.
+    t_probe = time.perf_counter()
+    while time.perf_counter() - t_probe < 0.6:
+        for _ in range(50):
+            device_step()
+    barrier()
     clk = clocks.stop() if rank == 0 else None
-    launches = mppi.stats['launches']
+    if clk is not None:
+        clk["note"] = "sampled every 100 ms from the first timed step until 0.6 s of the same load after the last one"
 
     # max over ranks
     if world > 1:
