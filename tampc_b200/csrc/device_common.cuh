@@ -585,10 +585,13 @@ __device__ __forceinline__ void copy_image_async(unsigned char* smem_dst, const 
 }
 __device__ __forceinline__ void copy_image_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// sampler_d_off >= 0: additionally a float64 SamplerS (the tensor-core kernels' fused softmax update uses it)
 template <typename ST, typename CT>
-__global__ void prep_image_kernel(unsigned char* image, int cost_off, int sampler_off, const tampc_cost_desc* cost, const SamplerD* sampler) {
+__global__ void prep_image_kernel(unsigned char* image, int cost_off, int sampler_off, int sampler_d_off, const tampc_cost_desc* cost,
+                                  const SamplerD* sampler) {
   stage_cost<ST, CT>(*reinterpret_cast<CostS<ST, CT>*>(image + cost_off), *cost, threadIdx.x, blockDim.x);
   stage_sampler<ST>(*reinterpret_cast<SamplerS<ST>*>(image + sampler_off), *sampler, threadIdx.x, blockDim.x);
+  if (sampler_d_off >= 0) stage_sampler<double>(*reinterpret_cast<SamplerS<double>*>(image + sampler_d_off), *sampler, threadIdx.x, blockDim.x);
 }
 
 }  // namespace tampc

@@ -17,6 +17,7 @@
 // of its trap-set cost terms, and the horizon's standard normals are drawn up front by all 32 lanes.
 #pragma once
 #include "rollout_kernel.cuh"
+#include "fused_reduce.cuh"
 
 namespace tampc {
 
@@ -300,7 +301,8 @@ struct MmaSmem {
   using T = typename Model::T;
   static constexpr size_t kCost = align16<int>(Model::kBytes);
   static constexpr size_t kSampler = kCost + align16<int>(sizeof(CostS<ST, CT>));
-  static constexpr size_t kU = kSampler + align16<int>(sizeof(SamplerS<ST>));
+  static constexpr size_t kSamplerD = kSampler + align16<int>(sizeof(SamplerS<ST>));  // float64 copy for the fused update
+  static constexpr size_t kU = kSamplerD + align16<int>(sizeof(SamplerS<double>));
   static __host__ __device__ constexpr size_t stage_off(int T_) { return kU + align16<int>(sizeof(ST) * (size_t)T_ * kMaxNu); }
   static __host__ __device__ constexpr size_t warp_bytes(int T_, int sw, bool pre) {
     return align16<int>(sizeof(T) * Model::kStageElems) + (pre ? align16<int>(sizeof(float) * (size_t)T_ * sw * Model::NU) : 0);
@@ -406,6 +408,11 @@ __global__ void __launch_bounds__(128) rollout_mma_kernel(const RolloutArgs a) {
   double total = cost + (double)terminal_cost<ST, CT, NX>(cs, x);
   total += (double)pert;
   if (live && part == 0) a.cost_out[k] = total;
+  if (a.fuse) {
+    total = __shfl_sync(0xffffffffu, total, row);  // mirrors take their sample's total from its part-0 lane
+    fused_tail<NU, SW>(a, *reinterpret_cast<const SamplerS<double>*>(smem_raw + L::kSamplerD), total, row, kbase, lane,
+                       blockIdx.x * (nthr >> 5) + warp, gridDim.x * (nthr >> 5));
+  }
 }
 
 // ---- two-warp pipelined variant for small K (latency-bound) ----------------------------------------------
@@ -420,7 +427,8 @@ struct PipeSmem {
   static constexpr int SW = PolicyTF32x3::MT;
   static constexpr size_t kCost = align16<int>(Model::kBytes);
   static constexpr size_t kSampler = kCost + align16<int>(sizeof(CostS<float, float>));
-  static constexpr size_t kU = kSampler + align16<int>(sizeof(SamplerS<float>));
+  static constexpr size_t kSamplerD = kSampler + align16<int>(sizeof(SamplerS<float>));
+  static constexpr size_t kU = kSamplerD + align16<int>(sizeof(SamplerS<double>));
   static __host__ __device__ constexpr size_t stage_off(int T_) { return kU + align16<int>(sizeof(float) * (size_t)T_ * kMaxNu); }
   static __host__ __device__ constexpr size_t upre_off(int T_) { return stage_off(T_) + align16<int>(sizeof(T) * Model::kStageElems); }
   static __host__ __device__ constexpr size_t ring_off(int T_) { return upre_off(T_) + align16<int>(sizeof(float) * (size_t)T_ * SW * Model::NU); }
@@ -564,6 +572,11 @@ __global__ void __launch_bounds__(64) rollout_mma_pipe_kernel(const RolloutArgs 
     double total = cost + (double)terminal_cost<float, float, NX>(cs, x);
     total += (double)pert;
     if (live && part == 0) a.cost_out[k] = total;
+    if (a.fuse) {
+      total = __shfl_sync(0xffffffffu, total, row);
+      fused_tail<NU, SW>(a, *reinterpret_cast<const SamplerS<double>*>(smem_raw + L::kSamplerD), total, row, kbase, lane, blockIdx.x,
+                         gridDim.x);
+    }
   }
 }
 

@@ -60,6 +60,10 @@ struct tampc_mppi {
   double* d_states = nullptr;   // optional trajectories (K_local, Tmax, nx)
   double* d_scratch = nullptr;  // perturbed-action readback
   tampc_partial* d_partials = nullptr;
+  int n_partial_slots = 0;
+  unsigned int* d_ticket = nullptr;      // fused-reduction ticket counter
+  PartialHdr* d_phdr = nullptr;          // fused-reduction per-warp partials (compact)
+  double* d_pwsum = nullptr;
   tampc_partial* d_partials2 = nullptr;  // second-level combine scratch
   int n_partials2 = 0;
   tampc_partial* d_rank_partial = nullptr;
@@ -69,7 +73,7 @@ struct tampc_mppi {
   size_t weights_bytes = 0;
   int n_weight_elems = 0;
   bool use_mma = false;  // the staged weights are in the mma-path layout
-  int img_cost_off = 0, img_sampler_off = 0, img_bytes = 0;  // shared-memory image offsets inside d_weights
+  int img_cost_off = 0, img_sampler_off = 0, img_sampler_d_off = 0, img_bytes = 0;  // shared-memory image offsets inside d_weights
 
   double* h_pin = nullptr;  // pinned staging: [0..15] in, [16..31] out
   double* h_map = nullptr;  // mapped pinned result block written by the combine kernel: action[4], stats[3], flag
@@ -384,7 +388,10 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
 struct LaunchPlan {
   rollout_launch_fn fn = nullptr;
   int block = 128;
+  int fuse_warps = 0;  // > 0: the kernel can run the fused softmax update; number of partial slots (warps) it uses
 };
+
+constexpr int kMaxFusedWarps = 2048;
 
 LaunchPlan choose_launch(const tampc_mppi* h, int K) {
   const ModelVariant* v = h->variant;
@@ -393,19 +400,34 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
   if (h->use_mma) {
     const bool f64 = h->cfg.precision == TAMPC_PREC_F64;
     const int mt = f64 ? 8 : 16, max_idx = f64 ? 2 : 1;
+    // Resident warps per SM are bounded by shared memory (image ~40 KB per CTA + ~14 KB per warp): about 4 one-warp
+    // CTAs, 3 two-warp CTAs or 2 four-warp CTAs.  While everything fits in one wave the kernel is latency-bound and
+    // the smallest tile (most warps) wins; a second wave costs a full kernel time, so beyond one wave of the
+    // smallest tile move to the next tile size (measured on B200, tools/perf_sweep.py).
+    const int cap32 = 148 * 4, cap64 = 148 * 3 * 2, cap128 = 148 * 2 * 4;
     int idx = 0;  // NM = 1 << idx
-    while (idx < max_idx && K / (mt << (idx + 1)) >= 2 * 148 * 4) ++idx;
+    while (idx < max_idx && (K + (mt << idx) - 1) / (mt << idx) > cap128) ++idx;
     const int en = env_int("TAMPC_MMA_NM", 0);
     if (en == 1) idx = 0; else if (en == 2) idx = 1; else if (en == 4 && f64) idx = 2;
     const int warps = (K + (mt << idx) - 1) / (mt << idx);
-    p.block = warps >= 2 * 148 * 4 ? 128 : (warps >= 2 * 148 * 2 ? 64 : 32);
+    p.block = warps <= cap32 ? 32 : (warps <= cap64 ? 64 : 128);
     p.fn = f64 ? v->f64_mma[idx] : v->tf32_mma[idx];
+    if (eb == 32 || eb == 64 || eb == 128) p.block = eb;
+    {
+      const int wpb = p.block / 32, grid = (warps + wpb - 1) / wpb;
+      if (grid * wpb <= kMaxFusedWarps && env_int("TAMPC_FUSE", 1)) p.fuse_warps = grid * wpb;
+    }
     // latency-bound sizes: the two-warp pipelined kernel (dynamics warp + cost warp per 16-sample tile)
     // (measured on B200: wins while at most two 16-sample tiles share an SM, i.e. K <= 4736; above that the
     //  single-warp kernel's lower footprint wins.  TAMPC_PIPE=0/1 forces the choice.)
     const int tiles = (K + 15) / 16, pipe_env = env_int("TAMPC_PIPE", -1);
     const bool pipe = pipe_env >= 0 ? pipe_env != 0 : tiles <= 2 * 148;
-    if (!f64 && idx == 0 && v->tf32_pipe && pipe) { p.fn = v->tf32_pipe; p.block = 64; return p; }
+    if (!f64 && idx == 0 && v->tf32_pipe && pipe) {
+      p.fn = v->tf32_pipe;
+      p.block = 64;
+      p.fuse_warps = env_int("TAMPC_FUSE", 1) ? tiles : 0;
+      return p;
+    }
   } else {
     const bool f64 = h->cfg.precision == TAMPC_PREC_F64;
     const bool has_s2 = !f64 && v->mixed_s2 != nullptr;
@@ -430,10 +452,11 @@ int prep_image(tampc_mppi* h) {
   if (!h->has_model || !h->has_cost) return TAMPC_OK;
   unsigned char* img = reinterpret_cast<unsigned char*>(h->d_weights);
   const int prec = h->cfg.precision;
-  if (prec == TAMPC_PREC_F64) prep_image_kernel<double, double><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, h->d_cost, h->d_sampler);
+  const int sd = h->use_mma ? h->img_sampler_d_off : -1;
+  if (prec == TAMPC_PREC_F64) prep_image_kernel<double, double><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, sd, h->d_cost, h->d_sampler);
   else if (prec == TAMPC_PREC_MIXED || (prec == TAMPC_PREC_TF32X3 && !h->use_mma))
-    prep_image_kernel<double, float><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, h->d_cost, h->d_sampler);
-  else prep_image_kernel<float, float><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, h->d_cost, h->d_sampler);
+    prep_image_kernel<double, float><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, sd, h->d_cost, h->d_sampler);
+  else prep_image_kernel<float, float><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, sd, h->d_cost, h->d_sampler);
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return TAMPC_OK;
@@ -459,7 +482,10 @@ int check_ready(tampc_mppi* h) {
   return TAMPC_OK;
 }
 
-int launch_rollout_for(tampc_mppi* h, int mode, int shift, const double* d_U, int T, uint64_t call, bool keep_states) {
+// fuse: 0 = rollout only; 1 / 2 = ask for the fused softmax update (finalise / rank partial).  Returns in *fused
+// whether the selected kernel did it (small-K tensor-core kernels) or the separate reduction kernels must follow.
+int launch_rollout_for(tampc_mppi* h, int mode, int shift, const double* d_U, int T, uint64_t call, bool keep_states, int fuse = 0,
+                       tampc_partial* partial_out = nullptr, bool* fused = nullptr) {
   RolloutArgs a{};
   a.image = h->d_weights;
   a.image_bytes = h->img_bytes;
@@ -478,6 +504,23 @@ int launch_rollout_for(tampc_mppi* h, int mode, int shift, const double* d_U, in
   a.bad_norm = h->model.bad_state_norm;
   const LaunchPlan plan = choose_launch(h, a.K_local);
   if (!plan.fn) { h->err = "no kernel compiled for this precision"; return TAMPC_ERR_UNSUPPORTED; }
+  if (fused) *fused = false;
+  if (fuse && plan.fuse_warps > 0 && plan.fuse_warps <= kMaxFusedWarps) {
+    a.fuse = fuse;
+    a.phdr = h->d_phdr;
+    a.pwsum = h->d_pwsum;
+    a.ticket = h->d_ticket;
+    a.U_out = h->d_U[h->cur ^ 1];
+    a.action_out = h->d_action;
+    a.stats_out = h->d_stats;
+    a.partial_out = partial_out ? partial_out : h->d_rank_partial;
+    if (fuse == 1) {
+      a.host_out = h->d_map;
+      a.host_flag = reinterpret_cast<unsigned long long*>(h->d_map + 8);
+      a.seq = ++h->seq;
+    }
+    if (fused) *fused = true;
+  }
   CUDA_TRY(h, plan.fn(a, plan.block, h->stream));
   h->launches++;
   return TAMPC_OK;
@@ -500,13 +543,27 @@ void launch_partials(const ReduceArgs& r, int n_chunks, cudaStream_t s) {
   partials_kernel<NU><<<n_chunks, kReduceThreads, 0, s>>>(r);
 }
 
-// rollout of the shard + reduction of the shard to CTA partials
-int run_rollout_and_partials(tampc_mppi* h, int mode, bool keep_states) {
+// rollout of the shard + its reduction.  fuse = 1 (finalise) / 2 (rank partial to partial_out).  *done tells the
+// caller whether the softmax update already happened inside the rollout launch (small-K tensor-core kernels) or the
+// CTA partials are waiting in d_partials for run_combine.
+int run_rollout_and_partials(tampc_mppi* h, int mode, bool keep_states, int fuse, tampc_partial* partial_out, bool* done) {
   const int T = h->T;
   const double* U = h->d_U[h->cur];
   h->call++;
-  int rc = launch_rollout_for(h, mode, /*shift=*/1, U, T, h->call, keep_states);
+  bool fused = false;
+  int rc = launch_rollout_for(h, mode, /*shift=*/1, U, T, h->call, keep_states, fuse, partial_out, &fused);
   if (rc) return rc;
+  h->last_mode = mode;
+  h->last_call = h->call;
+  h->last_T = T;
+  h->last_U = h->cur;
+  h->last_valid = true;
+  h->states_valid = keep_states;
+  *done = fused;
+  if (fused) {
+    if (fuse == 1) h->cur ^= 1;
+    return TAMPC_OK;
+  }
   ReduceArgs r{};
   r.cost = h->d_costs;
   r.sampler = h->d_sampler;
@@ -524,12 +581,6 @@ int run_rollout_and_partials(tampc_mppi* h, int mode, bool keep_states) {
   }
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
-  h->last_mode = mode;
-  h->last_call = h->call;
-  h->last_T = T;
-  h->last_U = h->cur;
-  h->last_valid = true;
-  h->states_valid = keep_states;
   return TAMPC_OK;
 }
 
@@ -706,7 +757,12 @@ TAMPC_API int tampc_mppi_create(const tampc_mppi_config* cfg, tampc_mppi** out) 
   CREATE_TRY(cudaMalloc(&h->d_U[1], sizeof(double) * Tm * kMaxNu));
   CREATE_TRY(cudaMalloc(&h->d_state, sizeof(double) * kMaxNx));
   CREATE_TRY(cudaMalloc(&h->d_costs, sizeof(double) * K));
-  CREATE_TRY(cudaMalloc(&h->d_partials, sizeof(tampc_partial) * h->n_chunks));
+  h->n_partial_slots = h->n_chunks;
+  CREATE_TRY(cudaMalloc(&h->d_partials, sizeof(tampc_partial) * h->n_partial_slots));
+  CREATE_TRY(cudaMalloc(&h->d_phdr, sizeof(PartialHdr) * kMaxFusedWarps));
+  CREATE_TRY(cudaMalloc(&h->d_pwsum, sizeof(double) * (size_t)kMaxFusedWarps * TAMPC_MAX_HORIZON * TAMPC_MAX_NU));
+  CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
+  CREATE_TRY(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
   h->n_partials2 = (h->n_chunks + kCombineThreads - 1) / kCombineThreads;
   if (h->n_partials2 > kCombineThreads) return fail("num_local too large for the two-level combine", TAMPC_ERR_INVALID);
   CREATE_TRY(cudaMalloc(&h->d_partials2, sizeof(tampc_partial) * h->n_partials2));
@@ -742,7 +798,7 @@ TAMPC_API void tampc_mppi_destroy(tampc_mppi* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_sampler); cudaFree(h->d_cost); cudaFree(h->d_U[0]); cudaFree(h->d_U[1]); cudaFree(h->d_state);
-  cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_partials2);
+  cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_partials2); cudaFree(h->d_ticket); cudaFree(h->d_phdr); cudaFree(h->d_pwsum);
   cudaFree(h->d_rank_partial); cudaFree(h->d_action); cudaFree(h->d_stats); cudaFree(h->d_weights);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->h_map) cudaFreeHost(h->h_map);
@@ -798,7 +854,8 @@ TAMPC_API int tampc_mppi_set_model(tampc_mppi* h, const tampc_model_desc* desc, 
   else if (prec == TAMPC_PREC_MIXED || (prec == TAMPC_PREC_TF32X3 && !use_mma)) { cost_sz = sizeof(CostS<double, float>); samp_sz = sizeof(SamplerS<double>); }
   else { cost_sz = sizeof(CostS<float, float>); samp_sz = sizeof(SamplerS<float>); }
   const size_t cost_off = wbytes, samp_off = cost_off + ((cost_sz + 15) & ~size_t(15));
-  const size_t bytes = samp_off + ((samp_sz + 15) & ~size_t(15));
+  const size_t samp_d_off = samp_off + ((samp_sz + 15) & ~size_t(15));  // mma kernels: float64 SamplerS copy
+  const size_t bytes = samp_d_off + (use_mma ? ((sizeof(SamplerS<double>) + 15) & ~size_t(15)) : 0);
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   if (bytes > h->weights_bytes) {
@@ -813,6 +870,7 @@ TAMPC_API int tampc_mppi_set_model(tampc_mppi* h, const tampc_model_desc* desc, 
   h->use_mma = use_mma;
   h->img_cost_off = (int)cost_off;
   h->img_sampler_off = (int)samp_off;
+  h->img_sampler_d_off = (int)samp_d_off;
   h->img_bytes = (int)bytes;
   h->variant = pm.variant;
   h->model = *desc;
@@ -870,8 +928,10 @@ TAMPC_API int tampc_mppi_command_begin(tampc_mppi* h, const double* state, int32
   if ((rc = upload_state(h, state))) return rc;
   if ((rc = upload_noise(h, noise_mode, noise, h->T))) return rc;
   if (keep_states && (rc = ensure_states(h))) return rc;
-  if ((rc = run_rollout_and_partials(h, noise_mode, keep_states != 0))) return rc;
   if (!partial_dev) { h->err = "partial_dev is null"; return TAMPC_ERR_INVALID; }
+  bool done = false;
+  if ((rc = run_rollout_and_partials(h, noise_mode, keep_states != 0, /*fuse=*/2, (tampc_partial*)partial_dev, &done))) return rc;
+  if (done) return TAMPC_OK;
   return run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/0, (tampc_partial*)partial_dev);
 }
 
@@ -892,8 +952,9 @@ TAMPC_API int tampc_mppi_command(tampc_mppi* h, const double* state, int32_t noi
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   if ((rc = upload_state(h, state))) return rc;
   if ((rc = upload_noise(h, noise_mode, noise, h->T))) return rc;
-  if ((rc = run_rollout_and_partials(h, noise_mode, false))) return rc;
-  if ((rc = run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/1))) return rc;
+  bool done = false;
+  if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/1, nullptr, &done))) return rc;
+  if (!done && (rc = run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/1))) return rc;
   return download_action(h, action);
 }
 
@@ -911,7 +972,9 @@ TAMPC_API int tampc_mppi_command_resident(tampc_mppi* h, int32_t noise_mode) {
   int rc = check_ready(h);
   if (rc) return rc;
   if (noise_mode != kModePhilox && !h->d_noise) { h->err = "resident command with injected noise needs a previous upload"; return TAMPC_ERR_STATE; }
-  if ((rc = run_rollout_and_partials(h, noise_mode, false))) return rc;
+  bool done = false;
+  if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/1, nullptr, &done))) return rc;
+  if (done) return TAMPC_OK;
   return run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/1);
 }
 

@@ -25,6 +25,19 @@ struct RolloutArgs {
   uint32_t wrap_mask;
   int has_guard;
   double bad_norm;
+  // fused softmax update (fused_reduce.cuh; small-K tensor-core kernels only).  0: off, separate partials / combine
+  // kernels follow; 1: the last warp finalises U / action; 2: the last warp writes this rank's merged partial.
+  int fuse;
+  struct PartialHdr* phdr;  // per-warp partial headers (one slot per warp of the grid) ...
+  double* pwsum;            // ... and weighted sums, stride T*nu
+  unsigned int* ticket;     // zero-initialised; reset by the last warp
+  double* U_out;
+  double* action_out;
+  double* stats_out;
+  double* host_out;         // mapped pinned host memory (action, stats) or null
+  unsigned long long* host_flag;
+  unsigned long long seq;
+  tampc_partial* partial_out;
 };
 
 template <typename T> __host__ __device__ constexpr size_t align16(size_t n) { return (n + 15) & ~size_t(15); }

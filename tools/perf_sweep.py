@@ -50,8 +50,10 @@ def main():
                     if args.T:
                         spec.sampler.T = args.T
                     T = spec.sampler.T
-                    os.environ['TAMPC_SAMPLES_PER_THREAD'] = str(spt)
-                    os.environ['TAMPC_BLOCK'] = str(block)
+                    if spt:
+                        os.environ['TAMPC_SAMPLES_PER_THREAD'] = str(spt)
+                    if block:
+                        os.environ['TAMPC_BLOCK'] = str(block)
                     m = B200MPPI(spec, precision=prec, use_torch_stream=True,
                                  U_init=torch.from_numpy(np.resize(z['in.U'], (T, spec.sampler.nu))))
                     m.set_state_resident(z['in.state'])
