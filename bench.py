@@ -161,12 +161,17 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-timed throughput (state resident, L2 flushed between steps)
-    def device_step():
-        if world == 1:
-            mppi.command_resident()
-        else:
-            mppi.command(state)  # sharded command needs the collective; H2D of 40 B is inside
+    if world > 1:
+        mppi.set_state_resident(state)
 
+    def device_step():
+        if world == 1 or mppi._p2p:
+            mppi.command_resident()  # sharded: the merge kernel exchanges the partials over peer memory itself
+        else:
+            mppi.command(state)      # NCCL fallback: the all-gather is issued from the host
+
+    if world == 1:
+        mppi.set_state_resident(state)
     for _ in range(args.warmup):
         device_step()
     barrier()

@@ -206,6 +206,16 @@ TAMPC_API int tampc_mppi_command_begin(tampc_mppi* h, const double* state, int32
                              void* partial_dev);
 TAMPC_API int tampc_mppi_command_finish(tampc_mppi* h, const void* partials_dev, int32_t world, double* action);
 
+/* Peer-memory exchange (one node, NVLink): replaces the all-gather between begin() and finish() by P2P stores done
+ * inside the merge kernel.  comm_init allocates this rank's exchange buffer and returns its CUDA IPC handle
+ * (TAMPC_IPC_HANDLE_BYTES); the host plumbing all-gathers the handles of the world (any transport) and passes them
+ * to comm_connect in rank order.  After that tampc_mppi_command() of a sharded handle is complete by itself: every
+ * rank calls it with the same state and obtains the same action. */
+#define TAMPC_IPC_HANDLE_BYTES 64
+#define TAMPC_MAX_RANKS 8
+TAMPC_API int tampc_mppi_comm_init(tampc_mppi* h, int32_t rank, int32_t world, void* handle_out);
+TAMPC_API int tampc_mppi_comm_connect(tampc_mppi* h, const void* handles);
+
 /* ExperimentalMPPI._compute_rollout_costs(perturbed_actions): costs of caller-given actions (K_local,T,nu), no U update */
 TAMPC_API int tampc_mppi_rollout_costs(tampc_mppi* h, const double* state, const double* actions, int32_t horizon, double* cost_out,
                              double* states_out /* may be NULL; (K_local,T,nx) */);

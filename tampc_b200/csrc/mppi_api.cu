@@ -61,6 +61,13 @@ struct tampc_mppi {
   double* d_scratch = nullptr;  // perturbed-action readback
   tampc_partial* d_partials = nullptr;
   int n_partial_slots = 0;
+  // peer-memory exchange (multi-GPU): [parity][slots world | flags world]
+  int comm_rank = 0, comm_world = 0;
+  bool comm_connected = false;
+  unsigned char* comm_local = nullptr;
+  unsigned char* comm_peer[kMaxRanks] = {nullptr};
+  int* d_comm_error = nullptr;
+  unsigned long long comm_seq = 0;
   unsigned int* d_ticket = nullptr;      // fused-reduction ticket counter
   PartialHdr* d_phdr = nullptr;          // fused-reduction per-warp partials (compact)
   double* d_pwsum = nullptr;
@@ -412,7 +419,7 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     const int warps = (K + (mt << idx) - 1) / (mt << idx);
     p.block = warps <= cap32 ? 32 : (warps <= cap64 ? 64 : 128);
     p.fn = f64 ? v->f64_mma[idx] : v->tf32_mma[idx];
-    if (eb == 32 || eb == 64 || eb == 128) p.block = eb;
+    if (eb == 32 || eb == 64 || eb == 128 || eb == 256) p.block = eb;
     {
       const int wpb = p.block / 32, grid = (warps + wpb - 1) / wpb;
       if (grid * wpb <= kMaxFusedWarps && env_int("TAMPC_FUSE", 1)) p.fuse_warps = grid * wpb;
@@ -627,6 +634,41 @@ int run_combine(tampc_mppi* h, const tampc_partial* partials, int n, int finaliz
   return TAMPC_OK;
 }
 
+size_t comm_parity_bytes(int world) { return (sizeof(tampc_partial) * world + sizeof(unsigned long long) * kMaxRanks + 255) & ~size_t(255); }
+
+// exchange + merge in one kernel (reduce_kernels.cuh exchange_combine_kernel); this rank's partial is in d_rank_partial
+int run_exchange_combine(tampc_mppi* h) {
+  ExchangeArgs e{};
+  e.c.sampler = h->d_sampler;
+  e.c.U = h->d_U[h->cur];
+  e.c.T = h->T;
+  e.c.nu = h->cfg.nu;
+  e.c.finalize = 1;
+  e.c.U_out = h->d_U[h->cur ^ 1];
+  e.c.action_out = h->d_action;
+  e.c.stats_out = h->d_stats;
+  e.c.partial_out = h->d_rank_partial;
+  e.c.host_out = h->d_map;
+  e.c.host_flag = reinterpret_cast<unsigned long long*>(h->d_map + 8);
+  e.c.seq = ++h->seq;
+  e.mine = h->d_rank_partial;
+  e.rank = h->comm_rank;
+  e.world = h->comm_world;
+  e.seq = ++h->comm_seq;
+  e.timeout_ns = 2000000000ll * (long long)env_int("TAMPC_COMM_TIMEOUT_S", 2) / 2;
+  e.error_out = h->d_comm_error;
+  const size_t off = (e.seq & 1) * comm_parity_bytes(h->comm_world);
+  for (int p = 0; p < h->comm_world; ++p) {
+    e.peer_slots[p] = reinterpret_cast<tampc_partial*>(h->comm_peer[p] + off);
+    e.peer_flags[p] = reinterpret_cast<unsigned long long*>(h->comm_peer[p] + off + sizeof(tampc_partial) * h->comm_world);
+  }
+  exchange_combine_kernel<<<1, kCombineThreads, 0, h->stream>>>(e);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  h->cur ^= 1;
+  return TAMPC_OK;
+}
+
 int upload_state(tampc_mppi* h, const double* state) {
   memcpy(h->state_host, state, sizeof(double) * h->cfg.nx);  // travels as a kernel argument
   return TAMPC_OK;
@@ -800,6 +842,9 @@ TAMPC_API void tampc_mppi_destroy(tampc_mppi* h) {
   cudaFree(h->d_sampler); cudaFree(h->d_cost); cudaFree(h->d_U[0]); cudaFree(h->d_U[1]); cudaFree(h->d_state);
   cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_partials2); cudaFree(h->d_ticket); cudaFree(h->d_phdr); cudaFree(h->d_pwsum);
   cudaFree(h->d_rank_partial); cudaFree(h->d_action); cudaFree(h->d_stats); cudaFree(h->d_weights);
+  for (int p = 0; p < h->comm_world; ++p)
+    if (h->comm_connected && p != h->comm_rank && h->comm_peer[p]) cudaIpcCloseMemHandle(h->comm_peer[p]);
+  cudaFree(h->comm_local); cudaFree(h->d_comm_error);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->h_map) cudaFreeHost(h->h_map);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -953,9 +998,63 @@ TAMPC_API int tampc_mppi_command(tampc_mppi* h, const double* state, int32_t noi
   if ((rc = upload_state(h, state))) return rc;
   if ((rc = upload_noise(h, noise_mode, noise, h->T))) return rc;
   bool done = false;
+  if (h->comm_connected) {
+    // K-sharded: rank partial (fused into the rollout or via the partial kernels), then exchange + merge in one kernel
+    if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/2, h->d_rank_partial, &done))) return rc;
+    if (!done && (rc = run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/0, h->d_rank_partial))) return rc;
+    if ((rc = run_exchange_combine(h))) return rc;
+    rc = download_action(h, action);
+    if (rc == TAMPC_OK && h->h_map[kMaxNu + 3] < 0.0) {
+      h->h_map[kMaxNu + 3] = 0.0;
+      h->err = "peer exchange timed out: a rank did not reach this command";
+      return TAMPC_ERR_CUDA;
+    }
+    return rc;
+  }
+  if (h->cfg.num_local != h->cfg.num_samples) {
+    h->err = "sharded handle: use command_begin/finish with an all-gather, or connect the peer exchange (comm_init/comm_connect)";
+    return TAMPC_ERR_STATE;
+  }
   if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/1, nullptr, &done))) return rc;
   if (!done && (rc = run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/1))) return rc;
   return download_action(h, action);
+}
+
+TAMPC_API int tampc_mppi_comm_init(tampc_mppi* h, int32_t rank, int32_t world, void* handle_out) {
+  if (!h || !handle_out) return TAMPC_ERR_INVALID;
+  if (world < 2 || world > kMaxRanks || rank < 0 || rank >= world) { h->err = "comm_init: need 2 <= world <= 8 and 0 <= rank < world"; return TAMPC_ERR_INVALID; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == TAMPC_IPC_HANDLE_BYTES, "IPC handle size");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (!h->comm_local) {
+    const size_t bytes = 2 * comm_parity_bytes(world);
+    CUDA_TRY(h, cudaMalloc(&h->comm_local, bytes));
+    CUDA_TRY(h, cudaMemset(h->comm_local, 0, bytes));
+    CUDA_TRY(h, cudaMalloc(&h->d_comm_error, sizeof(int)));
+    CUDA_TRY(h, cudaMemset(h->d_comm_error, 0, sizeof(int)));
+  }
+  h->comm_rank = rank;
+  h->comm_world = world;
+  cudaIpcMemHandle_t hd;
+  CUDA_TRY(h, cudaIpcGetMemHandle(&hd, h->comm_local));
+  memcpy(handle_out, &hd, sizeof hd);
+  return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_comm_connect(tampc_mppi* h, const void* handles) {
+  if (!h || !handles) return TAMPC_ERR_INVALID;
+  if (!h->comm_local) { h->err = "comm_connect before comm_init"; return TAMPC_ERR_STATE; }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const unsigned char* hb = reinterpret_cast<const unsigned char*>(handles);
+  for (int p = 0; p < h->comm_world; ++p) {
+    if (p == h->comm_rank) { h->comm_peer[p] = h->comm_local; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, hb + (size_t)p * TAMPC_IPC_HANDLE_BYTES, sizeof hd);
+    void* ptr = nullptr;
+    CUDA_TRY(h, cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->comm_peer[p] = reinterpret_cast<unsigned char*>(ptr);
+  }
+  h->comm_connected = true;
+  return TAMPC_OK;
 }
 
 TAMPC_API int tampc_mppi_set_state_resident(tampc_mppi* h, const double* state) {
@@ -973,6 +1072,11 @@ TAMPC_API int tampc_mppi_command_resident(tampc_mppi* h, int32_t noise_mode) {
   if (rc) return rc;
   if (noise_mode != kModePhilox && !h->d_noise) { h->err = "resident command with injected noise needs a previous upload"; return TAMPC_ERR_STATE; }
   bool done = false;
+  if (h->comm_connected) {
+    if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/2, h->d_rank_partial, &done))) return rc;
+    if (!done && (rc = run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/0, h->d_rank_partial))) return rc;
+    return run_exchange_combine(h);
+  }
   if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/1, nullptr, &done))) return rc;
   if (done) return TAMPC_OK;
   return run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/1);

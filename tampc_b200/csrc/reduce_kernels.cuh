@@ -124,7 +124,7 @@ struct CombineArgs {
 
 constexpr int kCombineThreads = 512;  // also the largest group
 
-__global__ void __launch_bounds__(kCombineThreads) combine_kernel(const CombineArgs a) {
+__device__ __forceinline__ void combine_body(const CombineArgs& a) {
   __shared__ double s_beta[kCombineThreads];
   __shared__ double s_scale[kCombineThreads];
   __shared__ double s_sum[kCombineThreads];
@@ -211,6 +211,79 @@ __global__ void __launch_bounds__(kCombineThreads) combine_kernel(const CombineA
       __threadfence_system();
     }
   }
+}
+
+__global__ void __launch_bounds__(kCombineThreads) combine_kernel(const CombineArgs a) { combine_body(a); }
+
+// ---- multi-GPU exchange over peer memory ---------------------------------------------------------------------
+// The only inter-GPU step of a K-sharded command is ~1 KB per rank.  Instead of an NCCL all-gather
+// (a separate launch plus host-side collective bookkeeping: ~45 us measured at 2 ranks) the merge kernel itself does
+// the exchange: every rank stores its merged partial straight into slot[rank] of every peer's exchange buffer (P2P
+// stores over NVLink to CUDA-IPC mapped memory), publishes a per-rank sequence flag at system scope, waits for the
+// world's flags in its own buffer, and then runs the same deterministic combine as the single-GPU path — so every
+// rank finishes with a bitwise-identical U.  Buffers are double-buffered on the sequence parity: a rank can run at
+// most one command ahead of a peer (it needs the peer's flag of command n to finish n), never two.
+constexpr int kMaxRanks = 8;
+struct ExchangeArgs {
+  CombineArgs c;                         // finalize = 1; partials / n_partials are filled in by the kernel
+  const tampc_partial* mine;             // this rank's merged partial (device-local)
+  tampc_partial* peer_slots[kMaxRanks];  // slot array (world entries) of this parity in every rank's buffer
+  unsigned long long* peer_flags[kMaxRanks];
+  int rank, world;
+  unsigned long long seq;
+  long long timeout_ns;
+  int* error_out;                        // device int: set to 1 if a peer never arrived
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(kCombineThreads) exchange_combine_kernel(const ExchangeArgs e) {
+  __shared__ int s_fail;
+  const int tid = threadIdx.x;
+  const int nw = e.c.T * e.c.nu;
+  if (tid == 0) s_fail = 0;
+  // 1. my partial -> slot[rank] on every rank (header = 4 x 8 bytes, then T*nu sums)
+  for (int p = 0; p < e.world; ++p) {
+    tampc_partial* dst = e.peer_slots[p] + e.rank;
+    for (int i = tid; i < nw; i += kCombineThreads) dst->wsum[i] = e.mine->wsum[i];
+    if (tid == 0) { dst->beta = e.mine->beta; dst->eta = e.mine->eta; dst->argmin = e.mine->argmin; dst->count = e.mine->count; }
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. publish, 3. wait for everyone (bounded)
+  if (tid < e.world) {
+    *reinterpret_cast<volatile unsigned long long*>(e.peer_flags[tid] + e.rank) = e.seq;
+    __threadfence_system();
+    volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(e.peer_flags[e.rank] + tid);
+    const unsigned long long t0 = globaltimer_ns();
+    while (*mine != e.seq) {
+      if ((long long)(globaltimer_ns() - t0) > e.timeout_ns) { s_fail = 1; break; }
+      __nanosleep(200);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) {
+      *e.error_out = 1;
+      if (e.c.host_out != nullptr) {  // wake the host: it reads the error flag after the sequence number
+        e.c.host_out[kMaxNu + 3] = -1.0;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(e.c.host_flag) = e.c.seq;
+      }
+    }
+    return;
+  }
+  // 4. the same merge as on one GPU, over the world's partials in rank order
+  CombineArgs c = e.c;
+  c.partials = e.peer_slots[e.rank];
+  c.n_partials = e.world;
+  c.group = e.world;
+  combine_body(c);
 }
 
 // ExperimentalMPPI.perturbed_action (K, T, nu), regenerated on request (tampc/env/pybullet_sim.py:127 reads it)

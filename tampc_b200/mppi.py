@@ -37,13 +37,17 @@ def shard_bounds(K, rank, world):
 
 class B200MPPI:
     def __init__(self, spec: S.RolloutSpec, precision='mixed', device=0, seed=1234, max_horizon=None,
-                 rank=0, world_size=1, process_group=None, controller=None, U_init=None, use_torch_stream=False):
+                 rank=0, world_size=1, process_group=None, controller=None, U_init=None, use_torch_stream=False,
+                 exchange='auto'):
         """
         :param spec: flattened problem (dynamics, cost, sampler constants)
         :param precision: 'f64' (reference arithmetic), 'mixed' (float32 networks, float64 state/cost), 'f32'
         :param rank, world_size, process_group: K-sharding over torch.distributed ranks (one process per GPU);
                every rank holds the full U and obtains bitwise-identical updates
         :param controller: live tampc controller to re-read the cost program from on every command()
+        :param exchange: multi-GPU exchange of the softmax partials: 'p2p' = stores into CUDA-IPC mapped peer memory
+               from inside the merge kernel (one node, NVLink); 'nccl' = all_gather_into_tensor; 'auto' = p2p, falling
+               back to nccl if the peers cannot be mapped
         """
         self._lib = L.load()
         self.spec = spec
@@ -102,6 +106,13 @@ class B200MPPI:
             U_init = self.noise_dist.sample((self.T,))
         self.U = U_init
         self._gather = None
+        self._p2p = False
+        if world_size > 1 and exchange in ('auto', 'p2p'):
+            try:
+                self._connect_peers()
+            except Exception:
+                if exchange == 'p2p':
+                    raise
         self._last_noise = None
         self._cost_cache = None
         self._probe_cache = {}
@@ -215,9 +226,25 @@ class B200MPPI:
             self._command_sharded(x, mode, nptr, action)
         return torch.from_numpy(action)
 
+    def _connect_peers(self):
+        """Exchange CUDA IPC handles of the ranks' exchange buffers (torch.distributed is only the plumbing)."""
+        import torch.distributed as dist
+        mine = (C.c_ubyte * L.IPC_HANDLE_BYTES)()
+        self._check(self._lib.tampc_mppi_comm_init(self._h, self.rank, self.world_size, C.cast(mine, C.c_void_p)))
+        handles = [None] * self.world_size
+        dist.all_gather_object(handles, bytes(mine), group=self.group)
+        blob = (C.c_ubyte * (L.IPC_HANDLE_BYTES * self.world_size)).from_buffer_copy(b''.join(handles))
+        self._check(self._lib.tampc_mppi_comm_connect(self._h, C.cast(blob, C.c_void_p)))
+        dist.barrier(group=self.group)
+        self._p2p = True
+
     def _command_sharded(self, x, mode, nptr, action):
         """K-sharded command: local rollout + partial, one all_gather of tampc_partial (NCCL over NVLink), identical
         combine on every rank."""
+        if self._p2p:
+            # the merge kernel does the exchange itself over peer memory: nothing to do on the host
+            self._check(self._lib.tampc_mppi_command(self._h, L.dptr(x), mode, nptr, L.dptr(action)))
+            return
         import torch.distributed as dist
         if self._gather is None:
             dev = torch.device('cuda', self.device_index)
