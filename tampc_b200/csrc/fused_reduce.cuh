@@ -143,16 +143,25 @@ __device__ __forceinline__ void last_warp_combine(const RolloutArgs& a, int n, i
       const int base = base0 + 32 * u;
       const double sc = (base + lane < n) ? exp(-li * (be[u] - b)) : 0.0;
       eta = __fma_rn(sc, et[u], eta);
-      unsigned live = __ballot_sync(full, sc != 0.0);
-      while (live) {  // partials in index order
-        const int jj = __ffs(live) - 1;
-        live &= live - 1;
-        const double sj = __shfl_sync(full, sc, jj);
-        const double* ws = a.pwsum + (size_t)(base + jj) * nw;
+      // partials in index order, eight at a time so that their loads are in flight together; a group whose scales
+      // all underflowed (the usual case with a peaked softmax) is skipped, a zero scale inside a live group adds 0
+      const unsigned live = __ballot_sync(full, sc != 0.0);
+#pragma unroll 1
+      for (int j0 = 0; j0 < 32; j0 += 8) {
+        if (((live >> j0) & 0xffu) == 0u) continue;
+        double sj[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sj[q] = __shfl_sync(full, sc, j0 + q);
 #pragma unroll
         for (int k = 0; k < SLOTS; ++k) {
           const int i = lane + 32 * k;
-          if (i < nw) acc[k] = __fma_rn(sj, __ldcg(&ws[i]), acc[k]);
+          if (i < nw) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = (base + j0 + q < n) ? __ldcg(a.pwsum + (size_t)(base + j0 + q) * nw + i) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[k] = __fma_rn(sj[q], v[q], acc[k]);
+          }
         }
       }
     }

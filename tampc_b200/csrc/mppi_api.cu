@@ -252,7 +252,8 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
   const int nx = d.nx, nu = d.nu;
   if (nx != h->cfg.nx || nu != h->cfg.nu) { h->err = "model nx/nu differ from the handle's"; return TAMPC_ERR_INVALID; }
   if (!(d.leaky_slope >= 0.0 && d.leaky_slope <= 1.0)) { h->err = "leaky_slope must be in [0,1]"; return TAMPC_ERR_UNSUPPORTED; }
-  const ModelVariant* all[] = {variant_rex_push(), variant_rex_peg(), variant_mlp_5_3_32(), variant_mlp_5_3_64(), variant_pendulum()};
+  const ModelVariant* all[] = {variant_rex_push(), variant_rex_peg(), variant_mlp_5_3_32(), variant_mlp_5_3_64(), variant_mlp_5_3_128(),
+                               variant_pendulum()};
   char buf[256];
   if (d.kind == TAMPC_DYN_PENDULUM) {
     if (nx != 2 || nu != 1) { h->err = "pendulum dynamics need nx=2, nu=1"; return TAMPC_ERR_INVALID; }
@@ -287,8 +288,10 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
       h->err = buf;
       return TAMPC_ERR_UNSUPPORTED;
     }
-    pack_mlp<float>(out.f32, net);
-    pack_mlp<double>(out.f64, net);
+    if (out.variant->f64_s1) {  // shapes with FMA-path kernels
+      pack_mlp<float>(out.f32, net);
+      pack_mlp<double>(out.f64, net);
+    }
     if (out.variant->bytes_mma_f64) {
       pack_mlp_mma(out.mma_f64, net, 1, true);
       pack_mlp_mma(out.mma_tf32, net, 1, false);
@@ -395,10 +398,14 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
 struct LaunchPlan {
   rollout_launch_fn fn = nullptr;
   int block = 128;
-  int fuse_warps = 0;  // > 0: the kernel can run the fused softmax update; number of partial slots (warps) it uses
+  // > 0: the kernel can run the fused softmax update (fused_reduce.cuh); number of partial slots (warps) it uses.
+  // Opt-in (TAMPC_FUSE=1): measured on B200 it saves ~3 us per command when the softmax is peaked (lambda = 0.01
+  // with pushing-scale costs) but its single merging warp is several times slower than the separate
+  // partials/combine kernels when most weights are non-zero (peg-scale costs), so the default is the robust path.
+  int fuse_warps = 0;
 };
 
-constexpr int kMaxFusedWarps = 2048;
+constexpr int kMaxFusedWarps = 148 * 4;  // fused update only while one warp per SM sub-partition (latency-bound sizes)
 
 LaunchPlan choose_launch(const tampc_mppi* h, int K) {
   const ModelVariant* v = h->variant;
@@ -411,9 +418,10 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     // CTAs, 3 two-warp CTAs or 2 four-warp CTAs.  While everything fits in one wave the kernel is latency-bound and
     // the smallest tile (most warps) wins; a second wave costs a full kernel time, so beyond one wave of the
     // smallest tile move to the next tile size (measured on B200, tools/perf_sweep.py).
-    const int cap32 = 148 * 4, cap64 = 148 * 3 * 2, cap128 = 148 * 2 * 4;
+    const bool big = h->img_bytes > 100 * 1024;  // wide networks: one CTA per SM, always four warps sharing the image
+    const int cap32 = big ? 0 : 148 * 4, cap64 = big ? 0 : 148 * 3 * 2, cap128 = big ? 148 * 4 : 148 * 2 * 4;
     int idx = 0;  // NM = 1 << idx
-    while (idx < max_idx && (K + (mt << idx) - 1) / (mt << idx) > cap128) ++idx;
+    while (idx < max_idx && (f64 ? v->f64_mma[idx + 1] : v->tf32_mma[idx + 1]) != nullptr && (K + (mt << idx) - 1) / (mt << idx) > cap128) ++idx;
     const int en = env_int("TAMPC_MMA_NM", 0);
     if (en == 1) idx = 0; else if (en == 2) idx = 1; else if (en == 4 && f64) idx = 2;
     const int warps = (K + (mt << idx) - 1) / (mt << idx);
@@ -422,17 +430,17 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     if (eb == 32 || eb == 64 || eb == 128 || eb == 256) p.block = eb;
     {
       const int wpb = p.block / 32, grid = (warps + wpb - 1) / wpb;
-      if (grid * wpb <= kMaxFusedWarps && env_int("TAMPC_FUSE", 1)) p.fuse_warps = grid * wpb;
+      if (grid * wpb <= kMaxFusedWarps && env_int("TAMPC_FUSE", 0)) p.fuse_warps = grid * wpb;
     }
     // latency-bound sizes: the two-warp pipelined kernel (dynamics warp + cost warp per 16-sample tile)
     // (measured on B200: wins while at most two 16-sample tiles share an SM, i.e. K <= 4736; above that the
     //  single-warp kernel's lower footprint wins.  TAMPC_PIPE=0/1 forces the choice.)
     const int tiles = (K + 15) / 16, pipe_env = env_int("TAMPC_PIPE", -1);
-    const bool pipe = pipe_env >= 0 ? pipe_env != 0 : tiles <= 2 * 148;
+    const bool pipe = !big && (pipe_env >= 0 ? pipe_env != 0 : tiles <= 2 * 148);
     if (!f64 && idx == 0 && v->tf32_pipe && pipe) {
       p.fn = v->tf32_pipe;
       p.block = 64;
-      p.fuse_warps = env_int("TAMPC_FUSE", 1) ? tiles : 0;
+      p.fuse_warps = env_int("TAMPC_FUSE", 0) ? tiles : 0;
       return p;
     }
   } else {
@@ -870,6 +878,10 @@ TAMPC_API int tampc_mppi_set_model(tampc_mppi* h, const tampc_model_desc* desc, 
     if (!use_mma && pm.variant->kind != TAMPC_DYN_PENDULUM) { h->err = std::string("no tensor-core kernel for ") + pm.variant->name; return TAMPC_ERR_UNSUPPORTED; }
   } else if (f64 && pm.variant->bytes_mma_f64 && !(f64_impl && !strcmp(f64_impl, "fma"))) {
     use_mma = true;
+  }
+  if (!use_mma && !pm.variant->f64_s1) {
+    h->err = std::string(pm.variant->name) + " has tensor-core kernels only: use precision f64 or tf32x3";
+    return TAMPC_ERR_UNSUPPORTED;
   }
   const void* src;
   size_t raw_bytes;

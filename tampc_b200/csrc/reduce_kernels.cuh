@@ -169,11 +169,23 @@ __device__ __forceinline__ void combine_body(const CombineArgs& a) {
   // ---- weighted sums, one thread per (t, i), partials in index order
   const int nw = a.T * a.nu;
   for (int i = tid; i < nw; i += kCombineThreads) {
+    // partials in index order; their records are 4 KB apart, so the loads of eight partials are issued together
+    // before any is consumed.  Groups whose scales all underflowed are skipped; a zero scale in a live group adds 0.
     double sum = 0.0;
-#pragma unroll 4
-    for (int p = 0; p < n; ++p) {
-      const double s = s_scale[p];
-      if (s != 0.0) sum = __fma_rn(s, part[p].wsum[i], sum);
+    for (int p0 = 0; p0 < n; p0 += 8) {
+      double sc[8];
+      bool any = false;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        sc[q] = p0 + q < n ? s_scale[p0 + q] : 0.0;
+        any |= sc[q] != 0.0;
+      }
+      if (!any) continue;
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = p0 + q < n ? part[p0 + q].wsum[i] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sum = __fma_rn(sc[q], v[q], sum);
     }
     if (a.finalize) {
       const int t = i / a.nu, d = i % a.nu, ts = t + 1;

@@ -1,0 +1,58 @@
+"""GPU: the synthetic sweep of BASELINE.json configs[3] (random-init MLP, hidden width 32 / 64 / 128, horizon 10-100)
+against the CPU oracle on injected noise.  Width 256 has no kernel yet and must be refused loudly."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mppi_oracle as O
+from tampc_b200.synthetic import make_synthetic_spec
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('precision', ['f64', 'tf32x3'])
+@pytest.mark.parametrize('H,K,T', [(32, 4096, 40), (32, 1000, 100), (64, 2048, 10), (64, 1024, 40), (128, 2048, 40),
+                                   (128, 1000, 10)])
+def test_synthetic_mlp_matches_oracle(cuda_lib, H, K, T, precision):
+    from tampc_b200.mppi import B200MPPI
+    spec, x0 = make_synthetic_spec(H=H, K=K, T=T, seed=H + T)
+    noise = O.sample_noise(spec, 5)
+    U0 = torch.zeros(T, 3, dtype=torch.double)
+    want = O.command(spec, torch.from_numpy(x0), U0, noise)
+    m = B200MPPI(spec, precision=precision, U_init=U0, max_horizon=T)
+    a = m.command(x0, noise=noise.numpy())
+    cost = m.cost_total
+    rel = float(((cost - want['cost_total']).abs() / want['cost_total'].abs()).max())
+    assert rel < (1e-9 if precision == 'f64' else 1e-5), rel
+    s = torch.sort(want['cost_total']).values
+    if float(s[1] - s[0]) > 1e-4 * float(s[0].abs()):
+        assert int(cost.argmin()) == want['argmin']
+        assert float((a - want['action']).abs().max()) < 1e-4
+    m.close()
+
+
+@pytest.mark.parametrize('precision', ['mixed', 'f32'])
+def test_fma_modes_cover_widths_32_and_64(cuda_lib, precision):
+    from tampc_b200.mppi import B200MPPI
+    for H in (32, 64):
+        spec, x0 = make_synthetic_spec(H=H, K=512, T=20, seed=3)
+        noise = O.sample_noise(spec, 6)
+        U0 = torch.zeros(20, 3, dtype=torch.double)
+        want = O.command(spec, torch.from_numpy(x0), U0, noise)
+        m = B200MPPI(spec, precision=precision, U_init=U0)
+        m.command(x0, noise=noise.numpy())
+        rel = float(((m.cost_total - want['cost_total']).abs() / want['cost_total'].abs()).max())
+        assert rel < 1e-5
+        m.close()
+
+
+def test_unsupported_widths_are_refused(cuda_lib):
+    from tampc_b200.mppi import B200MPPI, TampcError
+    spec, _ = make_synthetic_spec(H=256, K=256, T=10)
+    with pytest.raises(TampcError) as e:
+        B200MPPI(spec, precision='tf32x3')
+    assert e.value.code == -2
+    spec, _ = make_synthetic_spec(H=128, K=256, T=10)
+    with pytest.raises(TampcError) as e:
+        B200MPPI(spec, precision='mixed')   # width 128 has tensor-core kernels only
+    assert e.value.code == -2

@@ -39,22 +39,28 @@ def main():
     ap.add_argument('--spt', type=int, nargs='+', default=[0])
     ap.add_argument('--block', type=int, nargs='+', default=[0])
     ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--synthetic', type=int, default=0, help='hidden width of the synthetic MLP problem (config 4)')
     args = ap.parse_args()
     z = np.load(os.path.join(os.path.dirname(__file__), '..', 'tests', 'golden', args.case + '.npz'))
     for prec in args.precision:
         for K in args.K:
             for spt in args.spt:
                 for block in args.block:
-                    spec = S.spec_from_arrays(z)
-                    spec.sampler.K = K
-                    if args.T:
-                        spec.sampler.T = args.T
+                    if args.synthetic:
+                        from tampc_b200.synthetic import make_synthetic_spec
+                        spec, x0 = make_synthetic_spec(H=args.synthetic, K=K, T=args.T or 40)
+                        z = {'in.U': np.zeros((spec.sampler.T, 3)), 'in.state': x0}
+                    else:
+                        spec = S.spec_from_arrays(z)
+                        spec.sampler.K = K
+                        if args.T:
+                            spec.sampler.T = args.T
                     T = spec.sampler.T
                     if spt:
                         os.environ['TAMPC_SAMPLES_PER_THREAD'] = str(spt)
                     if block:
                         os.environ['TAMPC_BLOCK'] = str(block)
-                    m = B200MPPI(spec, precision=prec, use_torch_stream=True,
+                    m = B200MPPI(spec, precision=prec, use_torch_stream=True, max_horizon=max(T, 64),
                                  U_init=torch.from_numpy(np.resize(z['in.U'], (T, spec.sampler.nu))))
                     m.set_state_resident(z['in.state'])
                     iters = max(3, min(args.iters, int(2e9 / (K * T * 3600)) + 3))
@@ -68,7 +74,7 @@ def main():
                         m.command(state)
                     t_e2e = (time.perf_counter() - t0) / iters * 1e3
                     flops = 2.0 * spec.dynamics.macs_per_step * K * T
-                    print(json.dumps({'case': args.case, 'precision': prec, 'K': K, 'T': T, 'spt': spt, 'block': block,
+                    print(json.dumps({'case': ('synthetic_H%d' % args.synthetic) if args.synthetic else args.case, 'precision': prec, 'K': K, 'T': T, 'spt': spt, 'block': block,
                                       'rollout_ms': round(t_roll, 4), 'command_ms': round(t_cmd, 4), 'e2e_ms': round(t_e2e, 4),
                                       'rollout_tflops': round(flops / t_roll * 1e-9, 2),
                                       'Msteps_per_s_e2e': round(K * T / t_e2e * 1e-3, 1)}), flush=True)
