@@ -222,6 +222,10 @@ TAMPC_API int tampc_mppi_rollout_costs(tampc_mppi* h, const double* state, const
 /* MPPI.get_rollouts(state)[0]: the T states reached by the current nominal U (controller.py:434-435) */
 TAMPC_API int tampc_mppi_get_rollouts(tampc_mppi* h, const double* state, double* states_out /* (T,nx) */);
 
+/* ControllerWithModelPrediction.predict_next_state (controller.py:312-313, online_controller.py:47-58): one step of the
+ * nominal dynamics (guard, network, constrain_state) from `state` under `action`; next_state[nx]. */
+TAMPC_API int tampc_mppi_predict(tampc_mppi* h, const double* state, const double* action, double* next_state);
+
 TAMPC_API int tampc_mppi_query(tampc_mppi* h, int32_t what, double* out, size_t n_doubles);
 /* device pointer to the per-sample costs of the last rollout (double[num_local]); valid until the next call */
 TAMPC_API int tampc_mppi_device_costs(tampc_mppi* h, void** dev_ptr);

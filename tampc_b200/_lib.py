@@ -23,7 +23,7 @@ EXPORTS = [
     'tampc_mppi_set_model', 'tampc_mppi_set_cost', 'tampc_mppi_set_nominal', 'tampc_mppi_get_nominal',
     'tampc_mppi_command', 'tampc_mppi_command_begin', 'tampc_mppi_command_finish', 'tampc_mppi_rollout_costs',
     'tampc_mppi_get_rollouts', 'tampc_mppi_query', 'tampc_mppi_device_costs', 'tampc_mppi_synchronize',
-    'tampc_mppi_command_resident', 'tampc_mppi_set_state_resident', 'tampc_mppi_rollout_resident', 'tampc_mppi_comm_init', 'tampc_mppi_comm_connect',
+    'tampc_mppi_command_resident', 'tampc_mppi_set_state_resident', 'tampc_mppi_rollout_resident', 'tampc_mppi_comm_init', 'tampc_mppi_comm_connect', 'tampc_mppi_predict',
 ]
 
 
@@ -119,6 +119,7 @@ def load():
     lib.tampc_mppi_rollout_resident.argtypes = [vp, i32]
     lib.tampc_mppi_comm_init.argtypes = [vp, i32, i32, vp]
     lib.tampc_mppi_comm_connect.argtypes = [vp, vp]
+    lib.tampc_mppi_predict.argtypes = [vp, dp, dp, dp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ('tampc_mppi_last_error', 'tampc_mppi_destroy'):

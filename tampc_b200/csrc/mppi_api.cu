@@ -59,6 +59,7 @@ struct tampc_mppi {
   double* d_noise = nullptr;    // injected noise / given actions staging (K_local, Tmax, nu)
   double* d_states = nullptr;   // optional trajectories (K_local, Tmax, nx)
   double* d_scratch = nullptr;  // perturbed-action readback
+  double* d_predict = nullptr;  // action + cost scratch of tampc_mppi_predict
   tampc_partial* d_partials = nullptr;
   int n_partial_slots = 0;
   // peer-memory exchange (multi-GPU): [parity][slots world | flags world]
@@ -848,7 +849,7 @@ TAMPC_API void tampc_mppi_destroy(tampc_mppi* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_sampler); cudaFree(h->d_cost); cudaFree(h->d_U[0]); cudaFree(h->d_U[1]); cudaFree(h->d_state);
-  cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_partials2); cudaFree(h->d_ticket); cudaFree(h->d_phdr); cudaFree(h->d_pwsum);
+  cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_predict); cudaFree(h->d_partials); cudaFree(h->d_partials2); cudaFree(h->d_ticket); cudaFree(h->d_phdr); cudaFree(h->d_pwsum);
   cudaFree(h->d_rank_partial); cudaFree(h->d_action); cudaFree(h->d_stats); cudaFree(h->d_weights);
   for (int p = 0; p < h->comm_world; ++p)
     if (h->comm_connected && p != h->comm_rank && h->comm_peer[p]) cudaIpcCloseMemHandle(h->comm_peer[p]);
@@ -1147,9 +1148,47 @@ TAMPC_API int tampc_mppi_get_rollouts(tampc_mppi* h, const double* state, double
   a.bad_norm = h->model.bad_state_norm;
   const LaunchPlan plan = choose_launch(h, 1);
   if (!plan.fn) { h->err = "no kernel compiled for this precision"; return TAMPC_ERR_UNSUPPORTED; }
-  CUDA_TRY(h, plan.fn(a, 32, h->stream));
+  CUDA_TRY(h, plan.fn(a, plan.block, h->stream));
   h->launches++;
   CUDA_TRY(h, cudaMemcpyAsync(states_out, h->d_states, sizeof(double) * h->T * h->cfg.nx, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->states_valid = false;
+  return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_predict(tampc_mppi* h, const double* state, const double* action, double* next_state) {
+  if (!h || !state || !action || !next_state) return TAMPC_ERR_INVALID;
+  if (!h->has_model || !h->has_cost) { h->err = "set_model / set_cost first"; return TAMPC_ERR_STATE; }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  int rc;
+  if ((rc = upload_state(h, state))) return rc;
+  if ((rc = ensure_states(h))) return rc;
+  // a one-sample, one-step "nominal" rollout whose nominal sequence is the given action
+  double* d_act = h->d_stats + 3;  // scratch: d_stats has 4 doubles, [3] is free; nu <= 4 needs its own buffer
+  if (!h->d_predict) CUDA_TRY(h, cudaMalloc(&h->d_predict, sizeof(double) * (kMaxNu + 1)));
+  d_act = h->d_predict;
+  CUDA_TRY(h, cudaMemcpyAsync(d_act, action, sizeof(double) * h->cfg.nu, cudaMemcpyHostToDevice, h->stream));
+  RolloutArgs a{};
+  a.image = h->d_weights;
+  a.image_bytes = h->img_bytes;
+  a.slope = h->model.leaky_slope;
+  a.cost = h->d_cost;
+  a.sampler = h->d_sampler;
+  a.U = d_act;
+  a.shift = 0;
+  memcpy(a.state, h->state_host, sizeof a.state);
+  a.src = make_src(h, kModeNominal, 0, 1);
+  a.K_local = 1;
+  a.cost_out = h->d_predict + kMaxNu;
+  a.states_out = h->d_states;
+  a.wrap_mask = h->model.wrap_mask;
+  a.has_guard = h->model.has_bad_state_guard;
+  a.bad_norm = h->model.bad_state_norm;
+  const LaunchPlan plan = choose_launch(h, 1);
+  if (!plan.fn) { h->err = "no kernel compiled for this precision"; return TAMPC_ERR_UNSUPPORTED; }
+  CUDA_TRY(h, plan.fn(a, plan.block, h->stream));
+  h->launches++;
+  CUDA_TRY(h, cudaMemcpyAsync(next_state, h->d_states, sizeof(double) * h->cfg.nx, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->states_valid = false;
   return TAMPC_OK;

@@ -295,6 +295,15 @@ class B200MPPI:
         self._check(self._lib.tampc_mppi_get_rollouts(self._h, L.dptr(x), L.dptr(out)))
         return torch.from_numpy(out).unsqueeze(0).repeat(num_rollouts, 1, 1)
 
+    def predict_next_state(self, state, control):
+        """ControllerWithModelPrediction.predict_next_state (controller.py:312-313): one step of the nominal dynamics,
+        returned as a (1, nx) float64 ndarray like the reference."""
+        x = self._state_array(state)
+        u = np.ascontiguousarray(torch.as_tensor(control).detach().to('cpu', torch.double).numpy().reshape(-1))
+        out = np.empty(self.nx)
+        self._check(self._lib.tampc_mppi_predict(self._h, L.dptr(x), L.dptr(u), L.dptr(out)))
+        return out.reshape(1, -1)
+
     def _compute_rollout_costs(self, perturbed_actions, state=None):
         """ExperimentalMPPI._compute_rollout_costs (controller.py:340-381): (cost_total (K,), states (M,K,T,nx),
         actions (M,K,T,nu)) for caller-given actions.  M replicas of a deterministic model are identical, so M=1
@@ -326,11 +335,14 @@ class B200MPPI:
         self._check(self._lib.tampc_mppi_synchronize(self._h))
 
 
-def install(ctrl, **kwargs):
+def install(ctrl, predict_on_device=True, **kwargs):
     """Swap `ctrl.mpc` (an ExperimentalMPPI built at controller.py:418-421) for a B200MPPI bound to `ctrl`.
 
     The controller's own state machine (trap detection, recovery, MAB; online_controller.py:437-515) is untouched:
     it keeps assigning `ctrl.mpc.running_cost / terminal_state_cost`, calling `change_horizon` and `command`."""
     mpc = B200MPPI.from_controller(ctrl, **kwargs)
     ctrl.mpc = mpc
+    if predict_on_device and hasattr(ctrl, 'predict_next_state'):
+        # MPC.command calls this once per control step (controller.py:306): one 30 us launch instead of a host forward
+        ctrl.predict_next_state = mpc.predict_next_state
     return mpc

@@ -211,3 +211,22 @@ def test_unsupported_shapes_and_bad_arguments_raise(cuda_lib):
     with pytest.raises(ValueError):
         m.U = torch.zeros(500, 3)
     m.close()
+
+
+@pytest.mark.parametrize('precision', ['f64', 'tf32x3', 'mixed'])
+@pytest.mark.parametrize('case', ['push_nominal', 'peg_nominal', 'pendulum', 'push_badstate'])
+def test_predict_next_state_matches_oracle(cuda_lib, case, precision):
+    """controller.py:312-313 / online_controller.py:47-58: one nominal-dynamics step for the chosen action."""
+    from tampc_b200.mppi import B200MPPI
+    z, spec = _spec(case, 64)
+    m = B200MPPI(spec, precision=precision, U_init=_U(z, spec))
+    g = torch.Generator().manual_seed(2)
+    for _ in range(3):
+        u = torch.rand(spec.sampler.nu, dtype=torch.double, generator=g)
+        x = torch.from_numpy(z['in.state']) if case == 'push_badstate' else torch.from_numpy(z['in.state']) + 0.05 * torch.randn(
+            spec.dynamics.nx, dtype=torch.double, generator=g)
+        want, _ = O.apply_dynamics(spec.dynamics, x.view(1, -1), u.view(1, -1))
+        got = m.predict_next_state(x, u)
+        assert got.shape == (1, spec.dynamics.nx)
+        np.testing.assert_allclose(got, want.numpy(), rtol=0, atol=1e-10 if precision == 'f64' else 2e-4)
+    m.close()
