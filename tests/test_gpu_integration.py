@@ -1,0 +1,80 @@
+"""GPU: the integration path a reference user takes — install() on a live controller — exercised with a duck-typed
+controller rebuilt from the golden specs (tests/fake_tampc.py); outputs must match the reference's golden outputs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+import fake_tampc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('case', ['push_nominal', 'peg_nominal', 'push_recovery', 'push_mlp_notransform', 'push_null_action'])
+def test_install_on_live_controller_reproduces_reference(cuda_lib, case):
+    from tampc_b200 import extract, spec as S
+    from tampc_b200.mppi import install
+    z, spec = load_golden(case)
+    ctrl = fake_tampc.make_controller(spec, z['in.U'])
+    got = extract.spec_from_controller(ctrl)
+    a, b = S.spec_to_arrays(spec), S.spec_to_arrays(got)
+    for k in a:
+        if k.endswith('name') or 'bad_state_norm' in k:
+            continue
+        np.testing.assert_allclose(np.asarray(a[k], dtype=float), np.asarray(b[k], dtype=float), rtol=0, atol=1e-12, err_msg=k)
+    mpc = install(ctrl, precision='f64')
+    assert ctrl.mpc is mpc and ctrl.predict_next_state == mpc.predict_next_state
+    action = ctrl.mpc.command(torch.from_numpy(z['in.state']), noise=z['in.noise']).numpy()
+    np.testing.assert_allclose(action, z['ref.action'], rtol=0, atol=1e-8)
+    rel = np.max(np.abs(mpc.cost_total.numpy() - z['ref.cost_total']) / np.abs(z['ref.cost_total']))
+    assert rel < 1e-9 and mpc.stats['argmin'] == int(z['ref.argmin'])
+    mpc.close()
+
+
+def test_cost_program_is_reread_every_command(cuda_lib):
+    """The controller mutates trap set / weights / cost callbacks between commands (online_controller.py:353,
+    400-402,416-418,461-478); the drop-in must follow without being told."""
+    from tampc_b200.mppi import install
+    from oracle import mppi_oracle as O
+    from tampc_b200 import spec as S
+    z, spec = load_golden('push_nominal')
+    zr, spec_r = load_golden('push_recovery')
+    ctrl = fake_tampc.make_controller(spec, z['in.U'])
+    mpc = install(ctrl, precision='f64')
+    state = torch.from_numpy(z['in.state'])
+    # 1. anneal the trap weight and grow the trap set
+    ctrl.trap_set_weight = 0.37
+    ctrl.trap_set.append((torch.tensor([0.1, 0.2, 0.3, 0., 0.], dtype=torch.double), torch.tensor([0.5, 0.5, -0.5], dtype=torch.double)))
+    noise = O.sample_noise(spec, 3)
+    U0 = mpc.U.clone()
+    mpc.command(state, noise=noise.numpy())
+    spec.cost.trap_weight = 0.37
+    spec.cost.trap_x = np.vstack([spec.cost.trap_x, [0.1, 0.2, 0.3, 0., 0.]])
+    spec.cost.trap_u = np.vstack([spec.cost.trap_u, [0.5, 0.5, -0.5]])
+    want = O.command(spec, state, U0, noise)
+    assert float(((mpc.cost_total - want['cost_total']).abs() / want['cost_total'].abs()).max()) < 1e-9
+    # 2. enter recovery mode the way OnlineMPPI._start_recovery_mode does
+    rc = fake_tampc.make_controller(spec_r, zr['in.U'])
+    ctrl.recovery_cost = rc.recovery_cost
+    ctrl.mpc.running_cost = ctrl._recovery_running_cost
+    ctrl.mpc.terminal_state_cost = None
+    ctrl.mpc.change_horizon(5)
+    U1 = mpc.U.clone()
+    noise5 = O.sample_noise(spec_r, 4, K=spec.sampler.K, T=5)
+    mpc.command(state, noise=noise5.numpy())
+    spec_mix = S.RolloutSpec(spec.dynamics, spec_r.cost, S.SamplerSpec(K=spec.sampler.K, T=5, nu=3, lambda_=spec.sampler.lambda_,
+                             noise_mu=spec.sampler.noise_mu, noise_sigma=spec.sampler.noise_sigma, u_min=spec.sampler.u_min,
+                             u_max=spec.sampler.u_max, u_init=spec.sampler.u_init))
+    want = O.command(spec_mix, state, U1, noise5)
+    assert float(((mpc.cost_total - want['cost_total']).abs() / want['cost_total'].abs()).max()) < 1e-9
+    # 3. leave it again
+    ctrl.mpc.running_cost = ctrl._running_cost
+    ctrl.mpc.terminal_state_cost = ctrl._terminal_cost
+    ctrl.mpc.change_horizon(40)
+    mpc.command(state)
+    # 4. an unknown callback is an error, not a fallback
+    from tampc_b200.extract import UnsupportedSpec
+    ctrl.mpc.running_cost = lambda x, u: x.sum(dim=1)
+    with pytest.raises(UnsupportedSpec):
+        mpc.command(state)
+    mpc.close()
