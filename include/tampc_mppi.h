@@ -47,6 +47,9 @@ extern "C" {
 #define TAMPC_MAX_SET_GOALS 8
 #define TAMPC_MAX_LAYERS 4
 #define TAMPC_MAX_HORIZON 128
+#define TAMPC_GP_MAX_POINTS 64 /* OnlineGPMixing.max_data_points defaults to 50 (online_model.py:327) */
+#define TAMPC_GP_MAX_DIM 8
+#define TAMPC_MAX_ROLLOUT_SAMPLES 32
 
 typedef enum tampc_status {
   TAMPC_OK = 0,
@@ -114,6 +117,33 @@ typedef struct tampc_model_desc {
   double bad_state_norm;     /* online_controller.py:63 (1e5) */
   double pendulum[6];        /* g, m, l, dt, |u| clamp, |thdot| clamp */
 } tampc_model_desc;
+
+/* Online GP residual on top of the nominal network: OnlineGPMixing with independent outputs
+ * (tampc/dynamics/online_model.py:286-315,324-457), frozen at its current data and hyper-parameters.  Per output d:
+ * kernel s_d exp(-|a-b|^2 / (2 l_d^2)), Gaussian noise n_d, mean function = the nominal model.  The library prepares
+ * alpha_d = (K_d + n_d I)^-1 resid_d and the inverse Cholesky factor; the rollout kernel evaluates the posterior mean
+ * and variance per sample-step and draws Normal(mean, stddev) (online_model.py:435-449).  The hyper-parameter fit
+ * (online_model.py:412-430) stays with the caller. */
+typedef enum tampc_gp_space {
+  TAMPC_GP_AT_NETWORK = 0, /* inputs = the rows the network sees, outputs add to what it emits (GP built on the nominal
+                              datasource, hybrid_model.py:110-112) */
+  TAMPC_GP_ORIGINAL = 1    /* inputs = [x,u]*in_scale + in_offset, outputs are scaled dx: dx_i += delta_i / out_scale_i
+                              (temporary local model behind util.no_tsf_preprocessor(), hybrid_model.py:189-199) */
+} tampc_gp_space;
+
+typedef struct tampc_gp_desc {
+  int32_t n_points; /* 0 switches the residual off */
+  int32_t n_in, n_out;
+  int32_t space;    /* tampc_gp_space */
+  int32_t sample;   /* OnlineGPMixing.sample_dynamics: 1 = draw, 0 = posterior mean */
+  int32_t x_off, resid_off; /* (n_points, n_in) inputs and (n_points, n_out) targets minus the mean function there,
+                               row-major, in the float64 `params` array */
+  double lengthscale[TAMPC_GP_MAX_DIM], outputscale[TAMPC_GP_MAX_DIM], noise[TAMPC_GP_MAX_DIM];
+  double in_scale[TAMPC_GP_MAX_DIM], in_offset[TAMPC_GP_MAX_DIM], out_scale[TAMPC_GP_MAX_DIM]; /* TAMPC_GP_ORIGINAL */
+  /* a sampled model makes ExperimentalMPPI's M rollout replicas differ (controller.py:317,355-380) */
+  int32_t rollout_samples; /* M in [1, TAMPC_MAX_ROLLOUT_SAMPLES] */
+  double rollout_var_cost, rollout_var_discount;
+} tampc_gp_desc;
 
 typedef struct tampc_cost_desc {
   int32_t kind; /* tampc_cost_kind */
@@ -190,6 +220,12 @@ TAMPC_API void tampc_mppi_destroy(tampc_mppi* h);
  * (the reference mutates cost, horizon and trap set between calls: online_controller.py:400-402,416-418,353,462) */
 TAMPC_API int tampc_mppi_set_model(tampc_mppi* h, const tampc_model_desc* desc, const double* params, size_t n_params);
 TAMPC_API int tampc_mppi_set_cost(tampc_mppi* h, const tampc_cost_desc* desc);
+/* online GP residual (replaces OnlineDynamicsModel.predict, online_model.py:67-99, inside the rollout); call after
+ * every OnlineGPMixing update (online_model.py:386-410).  desc->n_points == 0 returns to the nominal network. */
+TAMPC_API int tampc_mppi_set_gp(tampc_mppi* h, const tampc_gp_desc* desc, const double* params, size_t n_params);
+/* standard normals behind the GP draws of the NEXT command / rollout, (num_local, M, T, n_out) float64, instead of the
+ * on-device Philox stream (the equivalent of patching Normal.sample in the reference; parity tests).  One-shot. */
+TAMPC_API int tampc_mppi_set_gp_draws(tampc_mppi* h, const double* eps, size_t n);
 TAMPC_API int tampc_mppi_set_nominal(tampc_mppi* h, const double* U, int32_t horizon); /* (horizon, nu): MPPI.U, sets T */
 TAMPC_API int tampc_mppi_get_nominal(tampc_mppi* h, double* U);
 

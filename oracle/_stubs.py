@@ -1,5 +1,5 @@
 """Import-only stand-ins for modules the reference imports but the MPPI path never executes
-(gpytorch, pybullet, tensorboardX, matplotlib, seaborn, gym, ROS, and the arm_pytorch_utilities
+(pybullet, tensorboardX, matplotlib, seaborn, gym, ROS, and the arm_pytorch_utilities
 submodules that are off the path).  TEST INFRASTRUCTURE ONLY.
 
 A stub module answers any attribute with a subclassable, callable placeholder class, so statements like
@@ -12,7 +12,7 @@ import sys
 import types
 
 STUB_ROOTS = (
-    'gpytorch', 'tensorboardX', 'pybullet', 'pybullet_data', 'matplotlib', 'seaborn', 'gym', 'rospy',
+    'tensorboardX', 'pybullet', 'pybullet_data', 'matplotlib', 'seaborn', 'gym', 'rospy',
     'std_msgs', 'geometry_msgs', 'visualization_msgs', 'window_recorder', 'arm_video_recorder', 'mujoco_py',
     'tampc_or', 'tampc_or_msgs',
 )

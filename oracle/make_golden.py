@@ -40,16 +40,19 @@ def t64(a):
     return torch.tensor(a, dtype=torch.double)
 
 
-def run_reference_command(ctrl, spec, state, U0, noise):
-    """mpc.command(state) of the reference with the noise draw injected."""
+def run_reference_command(ctrl, spec, state, U0, noise, gp_eps=None):
+    """mpc.command(state) of the reference with the noise draw injected (and, for a GP-sampled model, the standard
+    normals behind OnlineGPMixing.sample: gp_eps (T, M, K, ny), one (M*K, ny) block per horizon step)."""
     mpc = ctrl.mpc
     mpc.U = U0.clone()
     orig = mpc.noise_dist.sample
     KT = (spec.sampler.K, spec.sampler.T)
     mpc.noise_dist.sample = lambda shape=(): noise.clone() if tuple(shape) == KT else orig(shape)
+    draws = [] if gp_eps is None else [gp_eps[t].reshape(-1, gp_eps.shape[-1]) for t in range(gp_eps.shape[0])]
     try:
-        with torch.no_grad():
+        with torch.no_grad(), rh.inject_gp_draws(draws) as inj:
             action = mpc.command(state.clone())
+            assert not inj.draws, "the reference consumed {} of the injected GP draws".format(len(draws) - len(inj.draws))
     finally:
         mpc.noise_dist.sample = orig
     return action
@@ -65,8 +68,13 @@ def save_case(name, ctrl, state, seed, note):
         U0 = torch.max(torch.min(U0, t64(spec.sampler.u_max)), t64(spec.sampler.u_min))
     noise = O.sample_noise(spec, seed)
     state = t64(state)
-    action = run_reference_command(ctrl, spec, state, U0, noise)
-    with torch.no_grad():
+    gp_eps = None
+    if spec.dynamics.gp is not None:
+        ny = spec.dynamics.gp.resid.shape[1]
+        gp_eps = torch.randn(spec.sampler.T, mpc.M, spec.sampler.K, ny, dtype=torch.double,
+                             generator=torch.Generator().manual_seed(seed + 2))
+    action = run_reference_command(ctrl, spec, state, U0, noise, gp_eps)
+    with torch.no_grad(), rh.inject_gp_draws([]):  # a GP-sampled model rolls the nominal sequence out at its mean
         rollouts = mpc.get_rollouts(state.clone())[0]
     M = mpc.M
     states = mpc.states  # (M,K,T,nx)
@@ -77,8 +85,10 @@ def save_case(name, ctrl, state, seed, note):
         'ref.states_first8': states[0, :8].numpy(), 'ref.get_rollouts': rollouts.numpy(),
         'ref.M': np.array(M), 'note': np.array(note),
     }
+    if gp_eps is not None:
+        ref['in.gp_eps'] = gp_eps.numpy()
     # oracle must agree before the fixture is written
-    out = O.command(spec, state, U0, noise)
+    out = O.command(spec, state, U0, noise, gp_eps)
     rel = ((out['cost_total'] - mpc.cost_total).abs() / mpc.cost_total.abs().clamp_min(1e-300)).max().item()
     aerr = (out['action'] - action).abs().max().item()
     assert out['argmin'] == int(ref['ref.argmin']), (name, out['argmin'], int(ref['ref.argmin']))
@@ -103,9 +113,46 @@ def add_push_traps(ctrl, n=3):
         ctrl.trap_set.append((t2, tu.clone()))
 
 
+def gp_cases():
+    """the online GP residual (OnlineGPMixing over oracle/shim/gpytorch), both placements."""
+    # 9. --always_estimate_error (push_main.py:1788-1789): the nominal model IS a GP around the latent network,
+    #    built on the nominal datasource (first 50 training rows, hybrid_model.py:110-112), script M=10
+    ctrl, ds, env = rh.build_task('push', num_samples=32, rollout_samples=10, horizon=12,
+                                  nominal_adapt='GP_KERNEL_INDEP_OUT')
+    ctrl.set_goal(np.array(PUSH_GOAL))
+    add_push_traps(ctrl, n=1)
+    save_case('push_gp_latent', ctrl, PUSH_START, 41, 'GP residual in the latent space (nominal_adapt=GP_KERNEL_INDEP_OUT), M=10')
+
+    # 10. the TAMPC flow: entering non-nominal dynamics swaps in a temporary local GP with no data, behind the plain
+    #     scaler preprocessor, and feeds it the transitions seen since (online_controller.py:324-335; hybrid_model.py:
+    #     189-199).  Here: six "stuck against the wall" transitions.  rollout_var_cost at the class default 0.5
+    #     (controller.py:317) so that the across-replica variance term is exercised.
+    ctrl, ds, env = rh.build_task('push', num_samples=32, rollout_samples=10, horizon=12)
+    ctrl.set_goal(np.array(PUSH_GOAL))
+    add_push_traps(ctrl, n=1)
+    ctrl.mpc.rollout_var_cost = 0.5
+    g = torch.Generator().manual_seed(8)
+    x = t64(PUSH_TRAP[0])
+    with torch.enable_grad():
+        ctrl.dynamics.use_temp_local_nominal_model()
+        for i in range(6):
+            u = t64(spec_bounds_sample(ctrl, g))
+            nx_ = x + 0.003 * torch.randn(5, dtype=torch.double, generator=g) * t64([1, 1, 1, 50, 50])
+            ctrl.dynamics.update(x, u, nx_)
+            x = nx_
+    save_case('push_gp_local', ctrl, x.tolist(), 43, 'temporary local GP (6 points, original space), M=10, var cost 0.5')
+
+
+def spec_bounds_sample(ctrl, g):
+    lo, hi = ctrl.u_min.double(), ctrl.u_max.double()
+    return (lo + (hi - lo) * torch.rand(lo.shape[0], dtype=torch.double, generator=g)).tolist()
+
+
 def main():
     torch.manual_seed(0)
     np.random.seed(0)
+    if '--gp-only' in sys.argv:
+        return gp_cases()
 
     # 1. pushing, nominal cost (QR + 3 traps + terminal x50), M=2
     ctrl, ds, env = rh.build_task('push', num_samples=256, rollout_samples=2)
@@ -204,6 +251,8 @@ def main():
                                              'noise_sigma': torch.eye(1, dtype=torch.double)})
     ctrl.set_goal(np.array([0., 0.]))
     save_case('pendulum', ctrl, [math.pi, 1.0], 6, 'analytic pendulum, K=100 T=15 M=20 lambda=1, no trap cost')
+
+    gp_cases()
 
 
 if __name__ == '__main__':

@@ -76,9 +76,68 @@ def u_similarity(c: S.CostSpec, U, goal_u):
 # ------------------------------------------------------------------------------------------------
 # dynamics
 
-def predict(d: S.DynamicsSpec, x, u):
+def gp_posterior(d: S.DynamicsSpec, z):
+    """Exact-GP posterior of OnlineGPMixing with independent outputs at the transformed inputs z (B, n_in)
+    (online_model.py:286-315 MixingBatchGP, :435-438 _make_prediction = likelihood(gp(xu)) in eval mode).
+    gpytorch 1.1.1 is not under /root/reference: restated from Rasmussen & Williams eqs. 2.25-2.26 (PARITY
+    UNPINNED upstream; pinned against the reference's OnlineGPMixing run over oracle/shim/gpytorch).
+    Returns (mean - m(z), predictive variance incl. likelihood noise), both (B, n_out); the mean function m is
+    the nominal network (online_model.py:295-302)."""
+    g = d.gp
+    X, resid = _t(g.X), _t(g.resid)  # resid = y - m(X), the targets minus the mean function at the training inputs
+    mean = torch.zeros(z.shape[0], resid.shape[1], dtype=DT)
+    var = torch.zeros_like(mean)
+    d2_xx = torch.cdist(X, X).square()
+    d2_zx = (z.unsqueeze(1) - X.unsqueeze(0)).square().sum(-1)
+    for k in range(resid.shape[1]):
+        l2, s, n = float(g.lengthscale[k]) ** 2, float(g.outputscale[k]), float(g.noise[k])
+        Kxx = s * torch.exp(-0.5 * d2_xx / l2) + n * torch.eye(X.shape[0], dtype=DT)
+        Kzx = s * torch.exp(-0.5 * d2_zx / l2)
+        L = torch.linalg.cholesky(Kxx)
+        alpha = torch.cholesky_solve(resid[:, k:k + 1], L)
+        mean[:, k] = (Kzx @ alpha).squeeze(1)
+        w = torch.linalg.solve_triangular(L, Kzx.T, upper=False)
+        var[:, k] = s - w.square().sum(0) + n
+    return mean, var
+
+
+def _net_with_gp(d: S.DynamicsSpec, z, gp_eps):
+    """DeterministicUser.sample (model.py:72-74), or OnlineGPMixing._dynamics_in_transformed_space
+    (online_model.py:440-449): Normal(mean, stddev).sample() with the standard-normal draw `gp_eps` injected."""
+    y = mlp_forward(d.net, z)
+    if d.gp is None or d.gp.space != S.GP_AT_NETWORK:
+        return y
+    mean, var = gp_posterior(d, z)
+    y = y + mean
+    if d.gp.sample:
+        y = y + var.sqrt() * gp_eps
+    return y
+
+
+def predict_dx(d: S.DynamicsSpec, x, u, gp_eps=None):
+    """State difference predicted by the nominal network chain (model.py:147-165 with get_next_state=False), plus
+    the GP residual when it lives in the network's space."""
+    xu = torch.cat((x, u), dim=1)
+    if d.kind == S.DYN_MLP:
+        # PytorchTransformer(RobustMinMaxScaler) on both sides (util.py:422-423)
+        z = xu * _t(d.aff_in.scale) + _t(d.aff_in.offset)
+        y = _net_with_gp(d, z, gp_eps)
+        return (y - _t(d.aff_out.offset)) / _t(d.aff_out.scale)
+    # DYN_REX: Compose[ y-scaler, InvariantTransformer(RexExtract), z/v scaler ]
+    z = mlp_forward(d.encoder, xu)  # xu_to_z, invariant.py:792-795
+    z = z * _t(d.aff_in.scale) + _t(d.aff_in.offset)  # stage 3 transform_x
+    v = _net_with_gp(d, z, gp_eps)  # latent dynamics, model.py:300-301 (+ GP residual)
+    v = (v - _t(d.aff_out.offset)) / _t(d.aff_out.scale)  # stage 3 invert_transform
+    e = torch.nn.functional.linear(x, _t(d.ext_w), _t(d.ext_b))  # x_extractor, invariant.py:885
+    C = mlp_forward(d.decoder, e).view(-1, d.nx, d.nv)  # get_dx, invariant.py:926-931
+    dxs = (C @ v.unsqueeze(2)).squeeze(2)  # linalg.batch_batch_product
+    return (dxs - _t(d.aff_y.offset)) / _t(d.aff_y.scale)  # stage 1 invert_transform
+
+
+def predict(d: S.DynamicsSpec, x, u, gp_eps=None):
     """NetworkModelWrapper.predict on cat(x,u) -> next state (model.py:147-170,131-133,300-301), with the
-    preprocessor chain of util.py:408-411 and RexExtract (invariant.py:628-640,792-795,926-931)."""
+    preprocessor chain of util.py:408-411 and RexExtract (invariant.py:628-640,792-795,926-931).  With d.gp:
+    OnlineDynamicsModel.predict (online_model.py:67-99); gp_eps (B, n_out) are the injected standard normals."""
     if d.kind == S.DYN_PENDULUM:
         # scripts/pendulum.py:223-241 true_dynamics
         g, m, l, dt, umax, thdmax = d.pendulum
@@ -88,26 +147,22 @@ def predict(d: S.DynamicsSpec, x, u):
         newth = th + newthdot * dt
         newthdot = torch.clamp(newthdot, -thdmax, thdmax)
         return torch.cat((newth, newthdot), dim=1)
-    xu = torch.cat((x, u), dim=1)
-    if d.kind == S.DYN_MLP:
-        # PytorchTransformer(RobustMinMaxScaler) on both sides (util.py:422-423)
-        z = xu * _t(d.aff_in.scale) + _t(d.aff_in.offset)
-        y = mlp_forward(d.net, z)
-        dx = (y - _t(d.aff_out.offset)) / _t(d.aff_out.scale)
-        return x + dx
-    # DYN_REX: Compose[ y-scaler, InvariantTransformer(RexExtract), z/v scaler ]
-    z = mlp_forward(d.encoder, xu)  # xu_to_z, invariant.py:792-795
-    z = z * _t(d.aff_in.scale) + _t(d.aff_in.offset)  # stage 3 transform_x
-    v = mlp_forward(d.net, z)  # latent dynamics, model.py:300-301
-    v = (v - _t(d.aff_out.offset)) / _t(d.aff_out.scale)  # stage 3 invert_transform
-    e = torch.nn.functional.linear(x, _t(d.ext_w), _t(d.ext_b))  # x_extractor, invariant.py:885
-    C = mlp_forward(d.decoder, e).view(-1, d.nx, d.nv)  # get_dx, invariant.py:926-931
-    dxs = (C @ v.unsqueeze(2)).squeeze(2)  # linalg.batch_batch_product
-    dx = (dxs - _t(d.aff_y.offset)) / _t(d.aff_y.scale)  # stage 1 invert_transform
-    return x + dx  # advance_pred_all_diff, model.py:131-133
+    if d.gp is not None and d.gp.space == S.GP_ORIGINAL:
+        # temporary local model (hybrid_model.py:189-199): the GP sits behind its own per-dim scalers and its mean
+        # function is transform_y(nominal dx in the original space) (online_model.py:304-311)
+        g = d.gp
+        dx_nom = predict_dx(d, x, u)
+        zin = torch.cat((x, u), dim=1) * _t(g.aff_in.scale) + _t(g.aff_in.offset)
+        y = dx_nom * _t(g.aff_out.scale) + _t(g.aff_out.offset)
+        mean, var = gp_posterior(d, zin)
+        y = y + mean
+        if g.sample:
+            y = y + var.sqrt() * gp_eps
+        return x + (y - _t(g.aff_out.offset)) / _t(g.aff_out.scale)
+    return x + predict_dx(d, x, u, gp_eps)  # advance_pred_all_diff, model.py:131-133
 
 
-def apply_dynamics(d: S.DynamicsSpec, state, u):
+def apply_dynamics(d: S.DynamicsSpec, state, u, gp_eps=None):
     """OnlineMPC._apply_dynamics (online_controller.py:60-79) with AlwaysSelectNominal gating.
 
     Returns (next_state, u_seen_by_cost): rows whose ||state|| > 1e5 have state AND action zeroed in place in the
@@ -120,7 +175,7 @@ def apply_dynamics(d: S.DynamicsSpec, state, u):
         u[bad] = 0
     else:
         bad = None
-    nxt = predict(d, state, u)
+    nxt = predict(d, state, u, gp_eps)
     for k in d.wrap_dims:  # constrain_state (push_main.py:190-193)
         nxt[:, k] = angle_normalize(nxt[:, k])
     if bad is not None:
@@ -198,9 +253,39 @@ def terminal_cost(c: S.CostSpec, X_last):
 # ------------------------------------------------------------------------------------------------
 # MPPI
 
-def rollout_costs(spec: S.RolloutSpec, state, perturbed_actions, return_states=False):
+def rollout_costs_replicated(spec: S.RolloutSpec, state, perturbed_actions, gp_eps, return_states=False):
+    """ExperimentalMPPI._compute_rollout_costs (controller.py:340-381) with a stochastic (GP-sampled) model: M
+    replicas per sample, cost = mean over replicas + rollout_var_cost * sum_t var_M(c_t) * discount^t.
+    gp_eps: (T, M, K, n_out) standard-normal draws (row m*K+k of the reference's flattened (M*K, .) batch)."""
+    s = spec.sampler
+    K, T, nu = perturbed_actions.shape
+    M = s.rollout_samples
+    x = _t(state).view(1, -1).repeat(M * K, 1)
+    cost_samples = torch.zeros(M, K, dtype=DT)
+    cost_var = torch.zeros(K, dtype=DT)
+    states = []
+    for t in range(T):
+        u = perturbed_actions[:, t].repeat(M, 1)
+        eps = None if gp_eps is None else _t(gp_eps[t]).reshape(M * K, -1)
+        x, u_seen = apply_dynamics(spec.dynamics, x, u, eps)
+        c = running_cost(spec.cost, x, u_seen).view(M, K)
+        cost_samples = cost_samples + c
+        if M > 1:
+            cost_var = cost_var + c.var(dim=0) * (s.rollout_var_discount ** t)
+        if return_states:
+            states.append(x.view(M, K, -1))
+    cost_samples = cost_samples + terminal_cost(spec.cost, x).view(M, K)
+    total = cost_samples.mean(dim=0) + cost_var * s.rollout_var_cost
+    if return_states:
+        return total, torch.stack(states, dim=2)
+    return total
+
+
+def rollout_costs(spec: S.RolloutSpec, state, perturbed_actions, return_states=False, gp_eps=None):
     """ExperimentalMPPI._compute_rollout_costs (controller.py:340-381) for a deterministic model: all M replicas
     are identical, so mean over M = one rollout and the variance term is 0 (SURVEY.md §7 #2)."""
+    if spec.dynamics.gp is not None:
+        return rollout_costs_replicated(spec, state, perturbed_actions, gp_eps, return_states)
     K, T, nu = perturbed_actions.shape
     x = _t(state).view(1, -1).repeat(K, 1)
     total = torch.zeros(K, dtype=DT)
@@ -229,10 +314,10 @@ def perturb(spec: S.RolloutSpec, U, noise):
     return perturbed, noise_post, action_cost
 
 
-def total_cost(spec: S.RolloutSpec, state, U, noise):
+def total_cost(spec: S.RolloutSpec, state, U, noise, gp_eps=None):
     """ExperimentalMPPI._compute_total_cost_batch (controller.py:383-402) with the noise injected."""
     perturbed, noise_post, action_cost = perturb(spec, U, noise)
-    cost = rollout_costs(spec, state, perturbed)
+    cost = rollout_costs(spec, state, perturbed, gp_eps=gp_eps)
     cost = cost + torch.sum(perturbed * action_cost, dim=(1, 2))  # NB perturbed_action, not U (controller.py:400)
     return cost, perturbed, noise_post
 
@@ -244,12 +329,12 @@ def shift_nominal(spec: S.RolloutSpec, U):
     return U
 
 
-def command(spec: S.RolloutSpec, state, U, noise):
+def command(spec: S.RolloutSpec, state, U, noise, gp_eps=None):
     """One MPPI.command(state): shift, total cost, beta/eta/omega, U update; returns a dict.
     `U` is the nominal sequence BEFORE the shift; `noise` is the (K,T,nu) draw N(mu, Sigma)."""
     U = shift_nominal(spec, _t(U).clone())
     noise = _t(noise)
-    cost, perturbed, noise_post = total_cost(spec, state, U, noise)
+    cost, perturbed, noise_post = total_cost(spec, state, U, noise, gp_eps)
     beta = torch.min(cost)
     w = torch.exp(-(1.0 / spec.sampler.lambda_) * (cost - beta))
     eta = torch.sum(w)

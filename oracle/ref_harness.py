@@ -125,10 +125,11 @@ def _fake_env(cls):
     return object.__new__(cls)
 
 
-def build_task(task, num_samples=None, rollout_samples=None, horizon=None):
+def build_task(task, num_samples=None, rollout_samples=None, horizon=None, nominal_adapt='NONE'):
     """Build the reference's real OnlineMPPI controller for 'push' or 'peg' exactly as
     run_controller does (push_main.py:796-892 / peg_main.py:221-367), REX_EXTRACT transform,
-    online_adapt NONE, AlwaysSelectNominal gating."""
+    AlwaysSelectNominal gating.  nominal_adapt: name of a hybrid_model.OnlineAdapt member ('NONE' is the scripts'
+    default; 'GP_KERNEL_INDEP_OUT' is --always_estimate_error, push_main.py:1788-1789)."""
     ref = load_reference()
     UseTsf = ref.util.UseTsf
     if task == 'push':
@@ -161,9 +162,11 @@ def build_task(task, num_samples=None, rollout_samples=None, horizon=None):
                 return prefix
 
         pm = _Getter.loaded_prior(ref.prior.NNPrior, ds, tsf_name, False)
-        hybrid = ref.hybrid_model.HybridDynamicsModel(
-            [ds], pm, env.state_difference, [tsf_name], device='cpu', preprocessor=ref.util.no_tsf_preprocessor(),
-            nominal_model_kwargs={'online_adapt': ref.hybrid_model.OnlineAdapt.NONE}, local_model_kwargs={})
+        with torch.enable_grad():  # OnlineGPMixing fits its hyper-parameters by Adam in its constructor
+            hybrid = ref.hybrid_model.HybridDynamicsModel(
+                [ds], pm, env.state_difference, [tsf_name], device='cpu', preprocessor=ref.util.no_tsf_preprocessor(),
+                nominal_model_kwargs={'online_adapt': getattr(ref.hybrid_model.OnlineAdapt, nominal_adapt)},
+                local_model_kwargs={})
         if num_samples is not None:
             mpc['num_samples'] = num_samples
         if rollout_samples is not None:
@@ -175,3 +178,30 @@ def build_task(task, num_samples=None, rollout_samples=None, horizon=None):
                                                 autonomous_recovery=ref.online_controller.AutonomousRecovery.MAB,
                                                 constrain_state=constrain, mpc_opts=mpc, **common)
     return ctrl, ds, env
+
+
+class inject_gp_draws:
+    """Context manager: every `torch.distributions.Normal.sample()` made by OnlineGPMixing.sample
+    (online_model.py:446-449) returns loc + scale * eps with eps popped from `draws` (a list of (rows, ny) tensors, one
+    per horizon step); with the list exhausted it returns loc (a zero draw)."""
+
+    def __init__(self, draws):
+        self.draws = list(draws)
+
+    def __enter__(self):
+        import torch.distributions as D
+        self._orig = D.Normal.sample
+        outer = self
+
+        def sample(self_, sample_shape=torch.Size()):
+            if outer.draws and tuple(outer.draws[0].shape) == tuple(self_.loc.shape):
+                return self_.loc + self_.scale * outer.draws.pop(0)
+            return self_.loc.clone()
+
+        D.Normal.sample = sample
+        return self
+
+    def __exit__(self, *exc):
+        import torch.distributions as D
+        D.Normal.sample = self._orig
+        return False

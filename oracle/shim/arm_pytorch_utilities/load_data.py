@@ -47,7 +47,9 @@ class DataLoader:
     `_process_file_raw_data(d) -> (xu, y, info)`."""
 
     def __init__(self, file_cfg=None, dir_load_callback=None, config=None):
-        self.file_cfg = file_cfg
+        # the reference passes its `tampc.cfg` MODULE (env/env.py:13-16); keep only the path so that a datasource
+        # holding this loader stays deep-copyable (hybrid_model.py:131 deep-copies it for every local model)
+        self.data_dir = getattr(file_cfg, 'DATA_DIR', None)
         self.config = config if config is not None else DataConfig()
         self.dir_load_callback = dir_load_callback
 
@@ -59,7 +61,7 @@ class DataLoader:
         return self._process_file_raw_data(raw)
 
     def load(self, dir_or_file):
-        full = os.path.join(self.file_cfg.DATA_DIR, dir_or_file)
+        full = os.path.join(self.data_dir, dir_or_file)
         if os.path.isfile(full):
             return self.load_file(full)
         parts = []

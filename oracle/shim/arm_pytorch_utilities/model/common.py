@@ -25,6 +25,10 @@ class LearnableParameterizedModel(abc.ABC):
             ps += list(m.parameters())
         return ps
 
+    def device(self):
+        # used at hybrid_model.py:197 (use_temp_local_nominal_model) and controller.py:162
+        return next(iter(self.parameters())).device
+
     def eval(self):
         for m in self.modules().values():
             m.eval()

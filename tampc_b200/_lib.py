@@ -10,6 +10,7 @@ import numpy as np
 from . import spec as S
 
 MAX_NX, MAX_NU, MAX_TRAPS, MAX_GOAL_SETS, MAX_SET_GOALS, MAX_LAYERS, MAX_HORIZON = 8, 4, 16, 2, 8, 4, 128
+GP_MAX_POINTS, GP_MAX_DIM, MAX_ROLLOUT_SAMPLES = 64, 8, 32
 ABI_VERSION = 1
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
@@ -24,6 +25,7 @@ EXPORTS = [
     'tampc_mppi_command', 'tampc_mppi_command_begin', 'tampc_mppi_command_finish', 'tampc_mppi_rollout_costs',
     'tampc_mppi_get_rollouts', 'tampc_mppi_query', 'tampc_mppi_device_costs', 'tampc_mppi_synchronize',
     'tampc_mppi_command_resident', 'tampc_mppi_set_state_resident', 'tampc_mppi_rollout_resident', 'tampc_mppi_comm_init', 'tampc_mppi_comm_connect', 'tampc_mppi_predict',
+    'tampc_mppi_set_gp', 'tampc_mppi_set_gp_draws',
 ]
 
 
@@ -43,6 +45,15 @@ class ModelDesc(C.Structure):
                 ('aff_in', AffineDesc), ('aff_out', AffineDesc), ('aff_y', AffineDesc),
                 ('wrap_mask', C.c_uint32), ('has_bad_state_guard', C.c_int32), ('bad_state_norm', C.c_double),
                 ('pendulum', C.c_double * 6)]
+
+
+class GpDesc(C.Structure):
+    _fields_ = [('n_points', C.c_int32), ('n_in', C.c_int32), ('n_out', C.c_int32), ('space', C.c_int32),
+                ('sample', C.c_int32), ('x_off', C.c_int32), ('resid_off', C.c_int32),
+                ('lengthscale', C.c_double * GP_MAX_DIM), ('outputscale', C.c_double * GP_MAX_DIM),
+                ('noise', C.c_double * GP_MAX_DIM), ('in_scale', C.c_double * GP_MAX_DIM),
+                ('in_offset', C.c_double * GP_MAX_DIM), ('out_scale', C.c_double * GP_MAX_DIM),
+                ('rollout_samples', C.c_int32), ('rollout_var_cost', C.c_double), ('rollout_var_discount', C.c_double)]
 
 
 class CostDesc(C.Structure):
@@ -120,6 +131,8 @@ def load():
     lib.tampc_mppi_comm_init.argtypes = [vp, i32, i32, vp]
     lib.tampc_mppi_comm_connect.argtypes = [vp, vp]
     lib.tampc_mppi_predict.argtypes = [vp, dp, dp, dp]
+    lib.tampc_mppi_set_gp.argtypes = [vp, C.POINTER(GpDesc), dp, C.c_size_t]
+    lib.tampc_mppi_set_gp_draws.argtypes = [vp, dp, C.c_size_t]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ('tampc_mppi_last_error', 'tampc_mppi_destroy'):
@@ -207,6 +220,31 @@ def model_desc(dyn: S.DynamicsSpec):
     d.bad_state_norm = dyn.bad_state_norm if dyn.bad_state_norm is not None else 0.0
     for i, v in enumerate(dyn.pendulum):
         d.pendulum[i] = v
+    return d, pb.array()
+
+
+def gp_desc(gp, sampler: S.SamplerSpec):
+    """GPSpec (or None = residual off) -> (tampc_gp_desc, float64 params array)."""
+    d = GpDesc()
+    if gp is None:
+        return d, np.zeros(0)
+    pb = _ParamBuilder()
+    d.n_points, d.n_in, d.n_out = gp.X.shape[0], gp.X.shape[1], gp.resid.shape[1]
+    if d.n_in > GP_MAX_DIM or d.n_out > GP_MAX_DIM:
+        raise ValueError("GP wider than {} inputs / outputs".format(GP_MAX_DIM))
+    d.space, d.sample = gp.space, int(gp.sample)
+    d.x_off, d.resid_off = pb.add(gp.X), pb.add(gp.resid)
+    for i in range(d.n_out):
+        d.lengthscale[i], d.outputscale[i], d.noise[i] = gp.lengthscale[i], gp.outputscale[i], gp.noise[i]
+    if gp.space == S.GP_ORIGINAL:
+        for i in range(d.n_in):
+            d.in_scale[i], d.in_offset[i] = gp.aff_in.scale[i], gp.aff_in.offset[i]
+        for i in range(d.n_out):
+            d.out_scale[i] = gp.aff_out.scale[i]
+            if gp.aff_out.offset[i] != gp.aff_out.offset[i]:
+                raise ValueError("GP output scaler offset is NaN")
+    d.rollout_samples = sampler.rollout_samples
+    d.rollout_var_cost, d.rollout_var_discount = sampler.rollout_var_cost, sampler.rollout_var_discount
     return d, pb.array()
 
 

@@ -98,6 +98,20 @@ struct tampc_mppi {
   bool last_valid = false;
   bool states_valid = false;
   double last_stats[3] = {0, 0, 0};
+
+  // online GP residual (tampc_mppi_set_gp)
+  std::vector<double> model_params;  // kept so that the network image can be re-laid-out when the GP toggles
+  double net_in_scale[kMaxNx + kMaxNu] = {0}, net_in_off[kMaxNx + kMaxNu] = {0}, net_out_scale[kMaxNx] = {0};  // scalers around `net`
+  bool gp_on = false;
+  tampc_gp_desc gp{};
+  void* d_gp = nullptr;
+  size_t gp_capacity = 0;
+  int gp_bytes = 0;
+  double* d_gp_eps = nullptr;
+  size_t gp_eps_capacity = 0;
+  bool gp_eps_armed = false;
+  int gp_eps_T = 0;
+  uint64_t gp_aux_calls = 0;
 };
 
 namespace {
@@ -275,7 +289,9 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
     std::vector<double> s, o;
     if ((rc = read_affine(h, d.aff_in, p, n, nx + nu, s, o))) return rc;
     fold_input_affine(net[0], s, o);
+    for (int i = 0; i < nx + nu; ++i) { h->net_in_scale[i] = s[i]; h->net_in_off[i] = o[i]; }
     if ((rc = read_affine(h, d.aff_out, p, n, nx, s, o))) return rc;
+    for (int i = 0; i < nx; ++i) h->net_out_scale[i] = s[i];
     {  // dx = (y - o)/s
       std::vector<double> si(nx), oi(nx);
       for (int i = 0; i < nx; ++i) { si[i] = 1.0 / s[i]; oi[i] = -o[i] / s[i]; }
@@ -316,6 +332,8 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
   fold_output_affine(enc[2], s, o);
   // v = (v' - o)/s after the latent dynamics
   if ((rc = read_affine(h, d.aff_out, p, n, nv, s, o))) return rc;
+  if (nv > kMaxNx) { h->err = "latent output wider than TAMPC_MAX_NX"; return TAMPC_ERR_UNSUPPORTED; }
+  for (int i = 0; i < nv; ++i) h->net_out_scale[i] = s[i];
   {
     std::vector<double> si(nv), oi(nv);
     for (int i = 0; i < nv; ++i) { si[i] = 1.0 / s[i]; oi[i] = -o[i] / s[i]; }
@@ -412,6 +430,16 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
   const ModelVariant* v = h->variant;
   LaunchPlan p;
   const int eb = env_int("TAMPC_BLOCK", 0);
+  if (h->gp_on) {
+    // one thread per (sample, replica), FMA-layout networks; float32 networks for every precision but F64
+    switch (h->cfg.precision) {
+      case TAMPC_PREC_F64: p.fn = v->gp.f64; break;
+      case TAMPC_PREC_F32: p.fn = v->gp.f32; break;
+      default: p.fn = v->gp.mixed; break;
+    }
+    p.block = 128;
+    return p;
+  }
   if (h->use_mma) {
     const bool f64 = h->cfg.precision == TAMPC_PREC_F64;
     const int mt = f64 ? 8 : 16, max_idx = f64 ? 2 : 1;
@@ -498,6 +526,25 @@ int check_ready(tampc_mppi* h) {
   return TAMPC_OK;
 }
 
+// online GP residual: kernel arguments of the (sample, replica) kernels; consumes injected draws if armed (one-shot)
+int apply_gp_args(tampc_mppi* h, RolloutArgs& a, int T) {
+  if (!h->gp_on) return TAMPC_OK;
+  a.gp = h->d_gp;
+  a.gp_bytes = h->gp_bytes;
+  a.M = h->gp.rollout_samples;
+  a.var_cost = h->gp.rollout_var_cost;
+  a.var_discount = h->gp.rollout_var_discount;
+  // get_rollouts / predict are sampled too in the reference (they go through the same dynamics): a Philox stream
+  // of their own, advanced per call
+  if (a.src.mode == kModeNominal) a.src.call = (1ull << 62) + h->gp_aux_calls++;
+  if (h->gp_eps_armed) {
+    if (T != h->gp_eps_T) { h->err = "the injected GP draws were sized for another horizon"; return TAMPC_ERR_INVALID; }
+    a.gp_eps = h->d_gp_eps;
+    h->gp_eps_armed = false;
+  }
+  return TAMPC_OK;
+}
+
 // fuse: 0 = rollout only; 1 / 2 = ask for the fused softmax update (finalise / rank partial).  Returns in *fused
 // whether the selected kernel did it (small-K tensor-core kernels) or the separate reduction kernels must follow.
 int launch_rollout_for(tampc_mppi* h, int mode, int shift, const double* d_U, int T, uint64_t call, bool keep_states, int fuse = 0,
@@ -518,6 +565,10 @@ int launch_rollout_for(tampc_mppi* h, int mode, int shift, const double* d_U, in
   a.wrap_mask = h->model.wrap_mask;
   a.has_guard = h->model.has_bad_state_guard;
   a.bad_norm = h->model.bad_state_norm;
+  {
+    int rc = apply_gp_args(h, a, T);
+    if (rc) return rc;
+  }
   const LaunchPlan plan = choose_launch(h, a.K_local);
   if (!plan.fn) { h->err = "no kernel compiled for this precision"; return TAMPC_ERR_UNSUPPORTED; }
   if (fused) *fused = false;
@@ -857,12 +908,16 @@ TAMPC_API void tampc_mppi_destroy(tampc_mppi* h) {
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->h_map) cudaFreeHost(h->h_map);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  cudaFree(h->d_gp);
+  cudaFree(h->d_gp_eps);
   delete h;
 }
 
-TAMPC_API int tampc_mppi_set_model(tampc_mppi* h, const tampc_model_desc* desc, const double* params, size_t n_params) {
-  if (!h || !desc) return TAMPC_ERR_INVALID;
-  if (n_params && !params) { h->err = "params is null"; return TAMPC_ERR_INVALID; }
+}  // extern "C"
+
+// Lay the model out for the kernels the handle will run.  With the GP residual on, the networks are always in the
+// FMA layout (gp_rollout.cuh); otherwise the precision picks the layout.
+static int install_model(tampc_mppi* h, const tampc_model_desc* desc, const double* params, size_t n_params) {
   PackedModel pm;
   int rc = pack_model(h, *desc, params, n_params, pm);
   if (rc) return rc;
@@ -872,7 +927,9 @@ TAMPC_API int tampc_mppi_set_model(tampc_mppi* h, const tampc_model_desc* desc, 
   const bool f64 = prec == TAMPC_PREC_F64;
   const char* f64_impl = getenv("TAMPC_F64_IMPL");
   bool use_mma = false;
-  if (prec == TAMPC_PREC_TF32X3) {
+  if (h->gp_on) {
+    if (!pm.variant->gp.f64) { h->err = std::string("no GP-residual kernel compiled for ") + pm.variant->name; return TAMPC_ERR_UNSUPPORTED; }
+  } else if (prec == TAMPC_PREC_TF32X3) {
     // shapes without network layers (analytic pendulum) have nothing to put on the tensor cores: the float64
     // state/cost arithmetic of TF32X3 is exactly the MIXED kernel there
     use_mma = pm.variant->bytes_mma_tf32 != 0;
@@ -934,6 +991,197 @@ TAMPC_API int tampc_mppi_set_model(tampc_mppi* h, const tampc_model_desc* desc, 
   h->model = *desc;
   h->has_model = true;
   return prep_image(h);
+}
+
+extern "C" {
+
+TAMPC_API int tampc_mppi_set_model(tampc_mppi* h, const tampc_model_desc* desc, const double* params, size_t n_params) {
+  if (!h || !desc) return TAMPC_ERR_INVALID;
+  if (n_params && !params) { h->err = "params is null"; return TAMPC_ERR_INVALID; }
+  if (h->gp_on) {  // a new model invalidates the residual fitted around the old one
+    h->gp_on = false;
+    h->gp = tampc_gp_desc{};
+  }
+  int rc = install_model(h, desc, params, n_params);
+  if (rc) return rc;
+  h->model_params.assign(params, params + n_params);
+  return TAMPC_OK;
+}
+
+}  // extern "C"
+
+// Cholesky factor (lower, in place in A, row-major n x n); false if A is not positive definite
+static bool cholesky_lower(std::vector<double>& A, int n) {
+  for (int j = 0; j < n; ++j) {
+    double d = A[(size_t)j * n + j];
+    for (int k = 0; k < j; ++k) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+    if (!(d > 0.0)) return false;
+    d = std::sqrt(d);
+    A[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double v = A[(size_t)i * n + j];
+      for (int k = 0; k < j; ++k) v -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+      A[(size_t)i * n + j] = v / d;
+    }
+  }
+  return true;
+}
+
+template <typename T>
+static void pack_gp(std::vector<unsigned char>& blob, const tampc_gp_desc& g, const double* in_scale, const double* in_off, const double* out_mul,
+                    const double* X, const std::vector<std::vector<double>>& alpha, const std::vector<std::vector<double>>& Linv) {
+  const int n = g.n_points, npad = (n + 3) & ~3, stride = gp_tri_stride(n);
+  blob.assign(gp_block_bytes<T>(n, g.n_out), 0);
+  GpHeader<T>& H = *reinterpret_cast<GpHeader<T>*>(blob.data());
+  H.n = n; H.npad = npad; H.n_in = g.n_in; H.n_out = g.n_out; H.sample = g.sample; H.space = g.space; H.tri_stride = stride;
+  for (int i = 0; i < kGpMaxDim; ++i) {
+    H.in_scale[i] = i < g.n_in ? (T)in_scale[i] : (T)0;
+    H.in_off[i] = i < g.n_in ? (T)in_off[i] : (T)0;
+    const bool o = i < g.n_out;
+    H.out_mul[i] = o ? (T)out_mul[i] : (T)0;
+    H.neg_half_inv_l2[i] = o ? (T)(-0.5 / (g.lengthscale[i] * g.lengthscale[i])) : (T)0;
+    H.oscale[i] = o ? (T)g.outputscale[i] : (T)0;
+    H.prior_var[i] = o ? (T)(g.outputscale[i] + g.noise[i]) : (T)0;
+  }
+  T* Xs = reinterpret_cast<T*>(blob.data() + sizeof(GpHeader<T>));
+  T* al = Xs + (size_t)npad * kGpMaxDim;
+  T* tri = al + (size_t)g.n_out * npad;
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < g.n_in; ++i) Xs[(size_t)j * kGpMaxDim + i] = (T)X[(size_t)j * g.n_in + i];
+  for (int d = 0; d < g.n_out; ++d) {
+    for (int j = 0; j < n; ++j) al[(size_t)d * npad + j] = (T)alpha[d][j];
+    T* row = tri + (size_t)d * stride;
+    for (int i = 0; i < n; ++i) {
+      for (int j = 0; j <= i; ++j) row[j] = (T)Linv[d][(size_t)i * n + j];
+      row += (i + 4) & ~3;
+    }
+  }
+}
+
+extern "C" {
+
+TAMPC_API int tampc_mppi_set_gp(tampc_mppi* h, const tampc_gp_desc* g, const double* params, size_t n_params) {
+  if (!h || !g) return TAMPC_ERR_INVALID;
+  if (!h->has_model) { h->err = "set_model has not been called"; return TAMPC_ERR_STATE; }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const bool on = g->n_points > 0;
+  if (!on) {
+    if (h->gp_on) {
+      h->gp_on = false;
+      h->gp = tampc_gp_desc{};
+      return install_model(h, &h->model, h->model_params.data(), h->model_params.size());
+    }
+    return TAMPC_OK;
+  }
+  const int n = g->n_points, nx = h->cfg.nx, nu = h->cfg.nu;
+  const int kind = h->model.kind;
+  if (kind != TAMPC_DYN_MLP && kind != TAMPC_DYN_REX) { h->err = "a GP residual needs a network dynamics model"; return TAMPC_ERR_UNSUPPORTED; }
+  if (n > TAMPC_GP_MAX_POINTS) { h->err = "GP data points exceed TAMPC_GP_MAX_POINTS"; return TAMPC_ERR_UNSUPPORTED; }
+  if (g->rollout_samples < 1 || g->rollout_samples > TAMPC_MAX_ROLLOUT_SAMPLES) { h->err = "rollout_samples outside [1, TAMPC_MAX_ROLLOUT_SAMPLES]"; return TAMPC_ERR_UNSUPPORTED; }
+  if (g->space != TAMPC_GP_AT_NETWORK && g->space != TAMPC_GP_ORIGINAL) { h->err = "unknown GP space"; return TAMPC_ERR_INVALID; }
+  // where the GP sits decides its widths
+  const bool latent = kind == TAMPC_DYN_REX && g->space == TAMPC_GP_AT_NETWORK;
+  const int want_in = latent ? h->model.net.dims[0] : nx + nu, want_out = latent ? h->model.nv : nx;
+  if (g->n_in != want_in || g->n_out != want_out || g->n_in > kGpMaxDim || g->n_out > kGpMaxDim) {
+    h->err = "GP input/output widths do not match the model (" + std::to_string(g->n_in) + "->" + std::to_string(g->n_out) + ", expected " +
+             std::to_string(want_in) + "->" + std::to_string(want_out) + ")";
+    return TAMPC_ERR_INVALID;
+  }
+  if (!params || g->x_off < 0 || g->resid_off < 0 || (size_t)g->x_off + (size_t)n * g->n_in > n_params || (size_t)g->resid_off + (size_t)n * g->n_out > n_params) {
+    h->err = "GP data offsets outside the params array";
+    return TAMPC_ERR_INVALID;
+  }
+  for (int d = 0; d < g->n_out; ++d)
+    if (!(g->lengthscale[d] > 0.0 && g->outputscale[d] > 0.0 && g->noise[d] > 0.0)) { h->err = "GP hyper-parameters must be positive"; return TAMPC_ERR_INVALID; }
+  // scalers between the model's arrays and the GP's space
+  double in_scale[kGpMaxDim], in_off[kGpMaxDim], out_mul[kGpMaxDim];
+  for (int i = 0; i < kGpMaxDim; ++i) { in_scale[i] = 1.0; in_off[i] = 0.0; out_mul[i] = 1.0; }
+  if (g->space == TAMPC_GP_ORIGINAL) {
+    for (int i = 0; i < g->n_in; ++i) { in_scale[i] = g->in_scale[i]; in_off[i] = g->in_offset[i]; }
+    for (int i = 0; i < g->n_out; ++i) {
+      if (g->out_scale[i] == 0.0) { h->err = "GP out_scale must be non-zero"; return TAMPC_ERR_INVALID; }
+      out_mul[i] = 1.0 / g->out_scale[i];
+    }
+  } else if (kind == TAMPC_DYN_MLP) {  // the network's own in / out scalers (folded into its layers for the nominal part)
+    for (int i = 0; i < g->n_in; ++i) { in_scale[i] = h->net_in_scale[i]; in_off[i] = h->net_in_off[i]; }
+    for (int i = 0; i < g->n_out; ++i) out_mul[i] = 1.0 / h->net_out_scale[i];
+  } else {  // REX latent: the encoder already emits scaled z; v is un-scaled by the latent net's folded last layer
+    for (int i = 0; i < g->n_out; ++i) out_mul[i] = 1.0 / h->net_out_scale[i];
+  }
+  // exact-GP factors in float64: K_d + n_d I = L L^T, alpha_d = (K_d + n_d I)^-1 resid_d, L^-1
+  const double* X = params + g->x_off;
+  const double* R = params + g->resid_off;
+  std::vector<double> d2((size_t)n * n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double s = 0.0;
+      for (int c = 0; c < g->n_in; ++c) { const double d = X[(size_t)i * g->n_in + c] - X[(size_t)j * g->n_in + c]; s += d * d; }
+      d2[(size_t)i * n + j] = s;
+    }
+  std::vector<std::vector<double>> alpha(g->n_out), Linv(g->n_out);
+  for (int d = 0; d < g->n_out; ++d) {
+    std::vector<double> Lm((size_t)n * n);
+    const double l2 = g->lengthscale[d] * g->lengthscale[d];
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) Lm[(size_t)i * n + j] = g->outputscale[d] * std::exp(-0.5 * d2[(size_t)i * n + j] / l2) + (i == j ? g->noise[d] : 0.0);
+    if (!cholesky_lower(Lm, n)) { h->err = "GP kernel matrix of output " + std::to_string(d) + " is not positive definite"; return TAMPC_ERR_INVALID; }
+    std::vector<double>& Li = Linv[d];
+    Li.assign((size_t)n * n, 0.0);
+    for (int c = 0; c < n; ++c) {  // column c of L^-1 by forward substitution on e_c
+      for (int i = c; i < n; ++i) {
+        double v = i == c ? 1.0 : 0.0;
+        for (int k = c; k < i; ++k) v -= Lm[(size_t)i * n + k] * Li[(size_t)k * n + c];
+        Li[(size_t)i * n + c] = v / Lm[(size_t)i * n + i];
+      }
+    }
+    std::vector<double> w(n, 0.0);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j <= i; ++j) w[i] += Li[(size_t)i * n + j] * R[(size_t)j * g->n_out + d];
+    alpha[d].assign(n, 0.0);
+    for (int j = 0; j < n; ++j)
+      for (int i = j; i < n; ++i) alpha[d][j] += Li[(size_t)i * n + j] * w[i];
+  }
+  std::vector<unsigned char> blob;
+  if (h->cfg.precision == TAMPC_PREC_F64) pack_gp<double>(blob, *g, in_scale, in_off, out_mul, X, alpha, Linv);
+  else pack_gp<float>(blob, *g, in_scale, in_off, out_mul, X, alpha, Linv);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (blob.size() > h->gp_capacity) {
+    cudaFree(h->d_gp);
+    h->d_gp = nullptr;
+    const size_t cap = gp_block_bytes<double>(TAMPC_GP_MAX_POINTS, kGpMaxDim);
+    CUDA_TRY(h, cudaMalloc(&h->d_gp, cap));
+    h->gp_capacity = cap;
+  }
+  CUDA_TRY(h, cudaMemcpy(h->d_gp, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  h->gp_bytes = (int)blob.size();
+  h->gp = *g;
+  if (!h->gp_on) {
+    h->gp_on = true;
+    int rc = install_model(h, &h->model, h->model_params.data(), h->model_params.size());
+    if (rc) { h->gp_on = false; return rc; }
+  }
+  return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_set_gp_draws(tampc_mppi* h, const double* eps, size_t n) {
+  if (!h) return TAMPC_ERR_INVALID;
+  if (!eps) { h->gp_eps_armed = false; return TAMPC_OK; }
+  if (!h->gp_on) { h->err = "set_gp has not been called"; return TAMPC_ERR_STATE; }
+  const size_t per_step = (size_t)h->cfg.num_local * h->gp.rollout_samples * h->gp.n_out;
+  if (n == 0 || n % per_step != 0 || n / per_step > (size_t)h->cfg.max_horizon) { h->err = "GP draws must be (num_local, M, T, n_out)"; return TAMPC_ERR_INVALID; }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (n > h->gp_eps_capacity) {
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_gp_eps);
+    h->d_gp_eps = nullptr;
+    CUDA_TRY(h, cudaMalloc(&h->d_gp_eps, sizeof(double) * n));
+    h->gp_eps_capacity = n;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_gp_eps, eps, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->gp_eps_armed = true;
+  h->gp_eps_T = (int)(n / per_step);
+  return TAMPC_OK;
 }
 
 TAMPC_API int tampc_mppi_set_cost(tampc_mppi* h, const tampc_cost_desc* d) {
@@ -1146,6 +1394,7 @@ TAMPC_API int tampc_mppi_get_rollouts(tampc_mppi* h, const double* state, double
   a.wrap_mask = h->model.wrap_mask;
   a.has_guard = h->model.has_bad_state_guard;
   a.bad_norm = h->model.bad_state_norm;
+  if ((rc = apply_gp_args(h, a, h->T))) return rc;
   const LaunchPlan plan = choose_launch(h, 1);
   if (!plan.fn) { h->err = "no kernel compiled for this precision"; return TAMPC_ERR_UNSUPPORTED; }
   CUDA_TRY(h, plan.fn(a, plan.block, h->stream));
@@ -1184,6 +1433,7 @@ TAMPC_API int tampc_mppi_predict(tampc_mppi* h, const double* state, const doubl
   a.wrap_mask = h->model.wrap_mask;
   a.has_guard = h->model.has_bad_state_guard;
   a.bad_norm = h->model.bad_state_norm;
+  if ((rc = apply_gp_args(h, a, 1))) return rc;
   const LaunchPlan plan = choose_launch(h, 1);
   if (!plan.fn) { h->err = "no kernel compiled for this precision"; return TAMPC_ERR_UNSUPPORTED; }
   CUDA_TRY(h, plan.fn(a, plan.block, h->stream));

@@ -38,6 +38,13 @@ struct RolloutArgs {
   unsigned long long* host_flag;
   unsigned long long seq;
   tampc_partial* partial_out;
+  // online GP residual (gp_rollout.cuh): shared-memory block, M rollout replicas per sample, variance penalty,
+  // optional injected standard normals (K_local, M, T, n_out)
+  const void* gp;
+  int gp_bytes;
+  int M;
+  double var_cost, var_discount;
+  const double* gp_eps;
 };
 
 template <typename T> __host__ __device__ constexpr size_t align16(size_t n) { return (n + 15) & ~size_t(15); }

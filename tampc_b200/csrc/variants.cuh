@@ -2,6 +2,7 @@
 #pragma once
 #include <initializer_list>
 #include "mma_rollout.cuh"
+#include "gp_rollout.cuh"
 
 namespace tampc {
 
@@ -16,6 +17,7 @@ struct ModelVariant {
   rollout_launch_fn f64_s1, mixed_s1, mixed_s2, f32_s1, f32_s2;  // one-thread-per-sample FMA kernels
   rollout_launch_fn f64_mma[3];   // DMMA kernels, NM = 1, 2, 4 m-tiles (8, 16, 32 samples) per warp
   rollout_launch_fn tf32_mma[2];
+  GpLaunchers gp;                 // one-thread-per-(sample, replica) FMA kernels with the online GP residual
   rollout_launch_fn tf32_pipe;    // two-warp pipelined 3xTF32 kernel for small K (16 samples per CTA)  // 3xTF32 kernels, NM = 1, 2 (16, 32 samples per warp); float32 state and cost terms, float64 cost sum
 };
 
@@ -52,6 +54,11 @@ void add_mma(ModelVariant& v) {
   v.tf32_mma[1] = &launch_rollout_mma<MM32, float, float, 2, false>;
   v.tf32_pipe = &launch_rollout_mma_pipe<MM32>;
 }
+
+// GP-residual kernels live in their own translation unit (variant_gp.cu)
+GpLaunchers gp_launchers_rex_push();
+GpLaunchers gp_launchers_rex_peg();
+GpLaunchers gp_launchers_mlp_5_3_32();
 
 const ModelVariant* variant_rex_push();   // nx5 nu3, enc 8-16-32-5, dyn 5-32-32-5, dec 5(2)-16-32-25
 const ModelVariant* variant_rex_peg();    // nx5 nu2, enc 7-16-32-5, ...

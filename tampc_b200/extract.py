@@ -210,11 +210,76 @@ def probe_usim_dims(u_similarity, nu):
     return tuple(dims)
 
 
+def gp_from_online_model(om) -> S.GPSpec:
+    """Freeze an OnlineGPMixing-like object (tampc/dynamics/online_model.py:324-457) at its current data and
+    hyper-parameters.  Duck-typed on gpytorch's names: gp.covar_module = ScaleKernel(RBFKernel) batched over the
+    outputs (online_model.py:299-302), likelihood = MultitaskGaussianLikelihood (task noises + global noise)."""
+    if not getattr(om, 'use_independent_outputs', False):
+        raise UnsupportedSpec("only the independent-output GP (OnlineAdapt.GP_KERNEL_INDEP_OUT) is fused")
+    gp, lik = getattr(om, 'gp', None), getattr(om, 'likelihood', None)
+    if gp is None or lik is None or getattr(om, 'xu', None) is None or len(om.xu) == 0:
+        raise UnsupportedSpec("the online GP holds no data yet (the reference cannot predict in that state either)")
+    if getattr(gp, 'training', False):
+        raise UnsupportedSpec("the online GP is in training mode; the reference predicts only after _fit_params")
+    cm = getattr(gp, 'covar_module', None)
+    base = getattr(cm, 'base_kernel', None)
+    if cm is None or base is None or not hasattr(cm, 'outputscale') or not hasattr(base, 'lengthscale'):
+        raise UnsupportedSpec("GP kernel {} is not ScaleKernel(RBFKernel)".format(type(cm).__name__))
+    if 'rbf' not in type(base).__name__.lower():
+        raise UnsupportedSpec("GP base kernel {} is not an RBF kernel".format(type(base).__name__))
+    ny = int(om.y.shape[1])
+    ls = _np(base.lengthscale).reshape(-1)
+    osc = _np(cm.outputscale).reshape(-1)
+    if ls.shape != (ny,) or osc.shape != (ny,):
+        raise UnsupportedSpec("GP hyper-parameters are not one (lengthscale, outputscale) per output "
+                              "(ARD lengthscales are not fused)")
+    noise = np.zeros(ny)
+    for attr in ('task_noises', 'noise'):
+        if hasattr(lik, attr):
+            noise = noise + _np(getattr(lik, attr)).reshape(-1)
+    if not np.all(noise > 0):
+        raise UnsupportedSpec("GP likelihood {} exposes no positive noise".format(type(lik).__name__))
+    # mean function at the training inputs, from the live model's own forward (online_model.py:304-315): the
+    # residual targets belong to the host-side GP maintenance (fit / update), not to the per-sample path
+    with torch.no_grad():
+        mean_X = _np(gp.forward(om.xu).mean).reshape(len(om.xu), ny)
+    return S.GPSpec(_np(om.xu), _np(om.y) - mean_X, ls, osc, noise, sample=bool(getattr(om, 'sample_dynamics', True)))
+
+
+def gp_spec_from_model(online_model, nx, nu) -> S.GPSpec:
+    """GPSpec of an OnlineGPMixing nominal model, including where it sits relative to its mean network."""
+    inner = online_model.prior.dyn_net
+    pre_gp = getattr(getattr(online_model, 'ds', None), 'preprocessor', None)
+    pre_nn = getattr(getattr(inner, 'ds', None), 'preprocessor', None)
+    gp = gp_from_online_model(online_model)
+    if pre_gp is not pre_nn:
+        # the temporary local model (hybrid_model.py:189-199): GP behind its own per-dim scalers on (x,u) / dx,
+        # mean function = the whole nominal model evaluated in the original space (online_model.py:304-311)
+        tsf = getattr(pre_gp, 'tsf', pre_gp)
+        if tsf is None or not _is_pytorch_transformer(tsf):
+            raise UnsupportedSpec("the GP's preprocessor {} is neither the nominal model's nor a per-dim "
+                                  "scaler pair".format(type(tsf).__name__))
+        gp.space = S.GP_ORIGINAL
+        gp.aff_in = _affine_from_single(tsf.method_x, nx + nu)
+        gp.aff_out = _affine_from_single(tsf.method_y, nx)
+        gp.__post_init__()
+    return gp
+
+
 def dynamics_from_model(nominal_model, nx, nu, constrain_state=None, bad_state_norm=1e5) -> S.DynamicsSpec:
-    """DynamicsSpec of a NetworkModelWrapper-like object (tampc/dynamics/model.py:210-301)."""
+    """DynamicsSpec of a NetworkModelWrapper-like object (tampc/dynamics/model.py:210-301), or of an
+    OnlineGPMixing wrapped around one (online_model.py:324-457; its mean function is prior.dyn_net)."""
     if hasattr(nominal_model, 'prior') and not hasattr(nominal_model, 'model'):
-        raise UnsupportedSpec("online-adapted residual models (OnlineDynamicsModel) are not fused yet "
-                              "(SURVEY.md §8 a10); use online_adapt=NONE")
+        if not hasattr(nominal_model, 'gp'):
+            raise UnsupportedSpec("online model {} is not a GP residual (OnlineLinearizeMixing and the other "
+                                  "variants are not fused)".format(type(nominal_model).__name__))
+        inner = getattr(nominal_model.prior, 'dyn_net', None)
+        if inner is None or not hasattr(inner, 'model'):
+            raise UnsupportedSpec("the GP's prior exposes no .dyn_net network")
+        spec = dynamics_from_model(inner, nx, nu, constrain_state, bad_state_norm)
+        spec.gp = gp_spec_from_model(nominal_model, nx, nu)
+        spec.__post_init__()
+        return spec
     if not hasattr(nominal_model, 'model'):
         raise UnsupportedSpec("dynamics {} exposes no .model network".format(type(nominal_model).__name__))
     net = mlp_from_module(nominal_model.model)

@@ -150,6 +150,18 @@ class B200MPPI:
                                                    params.size))
         self._dyn_spec = dyn
         self.spec.dynamics = dyn
+        self.set_gp(dyn.gp)
+
+    def set_gp(self, gp: Optional[S.GPSpec]):
+        """Online GP residual around the nominal network (OnlineGPMixing, online_model.py:324-457), frozen at its
+        current data / hyper-parameters; None switches it off.  Cheap (<= 64 points): call after every GP update."""
+        s = self.spec.sampler
+        if gp is not None and not 1 <= self.M <= L.MAX_ROLLOUT_SAMPLES:
+            raise extract.UnsupportedSpec("rollout_samples={} outside [1,{}]".format(self.M, L.MAX_ROLLOUT_SAMPLES))
+        s.rollout_samples, s.rollout_var_cost, s.rollout_var_discount = self.M, self.rollout_var_cost, self.rollout_var_discount
+        desc, params = L.gp_desc(gp, s)
+        self._check(self._lib.tampc_mppi_set_gp(self._h, C.byref(desc), L.dptr(params) if params.size else None, params.size))
+        self._dyn_spec.gp = gp
 
     def set_cost(self, cost: S.CostSpec):
         desc = L.cost_desc(cost)
@@ -164,6 +176,29 @@ class B200MPPI:
             return
         cost = extract.cost_from_controller(self._ctrl, self.running_cost, self.terminal_state_cost)
         self.set_cost(cost)
+        self._refresh_dynamics_from_controller()
+
+    def _refresh_dynamics_from_controller(self):
+        """The nominal model object can be swapped between commands (use_temp_local_nominal_model /
+        use_normal_nominal_model, hybrid_model.py:189-202; online_controller.py:324-335) and an online GP changes with
+        every dynamics.update (online_controller.py:85): re-read the residual whenever one is, or was, present."""
+        dyn = getattr(self._ctrl, 'dynamics', None)
+        model = getattr(dyn, 'nominal_model', None)
+        if model is None:
+            return
+        online = hasattr(model, 'prior') and not hasattr(model, 'model')
+        if not online:
+            if self._dyn_spec.gp is not None:
+                self.set_gp(None)
+            return
+        inner = model.prior.dyn_net
+        if getattr(self, '_gp_inner', None) is not inner:
+            # first time this network is seen behind a GP: it must be the one the kernels already hold
+            new = extract.dynamics_from_controller(self._ctrl)
+            self._gp_inner = inner
+            self.set_dynamics(new)
+            return
+        self.set_gp(extract.gp_spec_from_model(model, self.nx, self.nu))
 
     # ------------------------------------------------------------------ nominal sequence
     @property
@@ -205,12 +240,28 @@ class B200MPPI:
             raise ValueError("state must have {} entries (per-sample start states are not supported)".format(self.nx))
         return a
 
-    def command(self, state, noise=None):
+    def _arm_gp_draws(self, gp_eps):
+        """gp_eps: (T, M, K, ny) standard normals in the reference's layout (row m*K+k of its flattened (M*K, .) batch
+        at step t) -> the library's (K_local, M, T, ny)."""
+        if gp_eps is None:
+            return
+        if self._dyn_spec.gp is None:
+            raise ValueError("gp_eps given but the dynamics have no GP residual")
+        e = torch.as_tensor(gp_eps).detach().to('cpu', torch.double).numpy()
+        ny = self._dyn_spec.gp.resid.shape[1]
+        if e.shape != (self.T, self.M, self.K, ny):
+            raise ValueError("gp_eps must be (T,M,K,ny) = {}".format((self.T, self.M, self.K, ny)))
+        local = np.ascontiguousarray(e[:, :, self.sample_offset:self.sample_offset + self.K_local].transpose(2, 1, 0, 3))
+        self._check(self._lib.tampc_mppi_set_gp_draws(self._h, L.dptr(local), local.size))
+
+    def command(self, state, noise=None, gp_eps=None):
         """MPPI.command(state) -> action (nu,) float64 tensor.
 
         noise: optional (K,T,nu) draw N(mu, Sigma) to use instead of the on-device Philox stream — the equivalent of
-        patching `noise_dist.sample((K,T))` in the reference, used by the parity tests."""
+        patching `noise_dist.sample((K,T))` in the reference, used by the parity tests.
+        gp_eps: optional (T,M,K,ny) standard normals behind the GP residual's draws (parity tests)."""
         self._refresh_from_controller()
+        self._arm_gp_draws(gp_eps)
         x = self._state_array(state)
         mode, nptr, local = L.NOISE_PHILOX, None, None
         if noise is not None:

@@ -78,6 +78,52 @@ class AffineSpec:
         return AffineSpec(np.ones(n), np.zeros(n))
 
 
+GP_MAX_POINTS = 64  # TAMPC_GP_MAX_POINTS (OnlineGPMixing.max_data_points defaults to 50, online_model.py:327)
+
+
+GP_AT_NETWORK = 0  # GP shares the nominal network's transformed space (nominal_adapt=GP_KERNEL_INDEP_OUT)
+GP_ORIGINAL = 1  # GP behind its own per-dim scalers on (x,u) and dx (use_temp_local_nominal_model, hybrid_model.py:189-199)
+
+
+@dataclass
+class GPSpec:
+    """OnlineGPMixing with independent outputs (tampc/dynamics/online_model.py:286-315,324-457), frozen at its
+    current data and hyper-parameters: per output d an exact GP with kernel s_d * exp(-|a-b|^2 / (2 l_d^2)), Gaussian
+    noise n_d, and the nominal model as the mean function.
+
+    space GP_AT_NETWORK: inputs are the rows the nominal network sees (z' for RexExtract), outputs add to what it
+    emits (v') — the GP was built on the nominal model's own datasource (hybrid_model.py:110-112).
+    space GP_ORIGINAL: inputs are aff_in([x,u]), the mean function is aff_out(dx_nominal(x,u)), outputs are scaled
+    dx — the temporary local model of hybrid_model.py:189-199, whose preprocessor is util.no_tsf_preprocessor()."""
+    X: np.ndarray  # (N, n_in) training inputs  (OnlineGPMixing.xu)
+    resid: np.ndarray  # (N, n_out) training targets minus the mean function at X  (OnlineGPMixing.y - m(xu))
+    lengthscale: np.ndarray  # (n_out,)
+    outputscale: np.ndarray  # (n_out,)
+    noise: np.ndarray  # (n_out,) likelihood noise per output (task noise + global noise)
+    sample: bool = True  # OnlineGPMixing.sample_dynamics: draw from N(mean, stddev) instead of returning the mean
+    space: int = GP_AT_NETWORK
+    aff_in: Optional['AffineSpec'] = None  # GP_ORIGINAL: scaler on [x,u]
+    aff_out: Optional['AffineSpec'] = None  # GP_ORIGINAL: scaler on dx
+
+    def __post_init__(self):
+        self.X = _f64(self.X)
+        self.resid = _f64(self.resid)
+        assert self.X.ndim == 2 and self.resid.ndim == 2 and len(self.X) == len(self.resid)
+        if not 1 <= len(self.X) <= GP_MAX_POINTS:
+            raise ValueError("GP with {} data points (supported: 1..{})".format(len(self.X), GP_MAX_POINTS))
+        ny = self.resid.shape[1]
+        self.lengthscale = _f64(self.lengthscale).reshape(-1)
+        self.outputscale = _f64(self.outputscale).reshape(-1)
+        self.noise = _f64(self.noise).reshape(-1)
+        assert self.lengthscale.shape == self.outputscale.shape == self.noise.shape == (ny,)
+        self.sample = bool(self.sample)
+        self.space = int(self.space)
+        if self.space == GP_ORIGINAL:
+            self.aff_in = self.aff_in or AffineSpec.identity(self.X.shape[1])
+            self.aff_out = self.aff_out or AffineSpec.identity(ny)
+            assert self.aff_in.scale.shape == (self.X.shape[1],) and self.aff_out.scale.shape == (ny,)
+
+
 DYN_MLP = 0  # x' = x + inv_y( net( aff_in([x,u]) ) )           (UseTsf.NO_TRANSFORM / synthetic sweep)
 DYN_REX = 1  # RexExtract latent dynamics (UseTsf.REX_EXTRACT)    (push / peg checkpoints)
 DYN_PENDULUM = 2  # scripts/pendulum.py:223-241 analytic dynamics
@@ -106,6 +152,8 @@ class DynamicsSpec:
     bad_state_norm: Optional[float] = 1e5
     # DYN_PENDULUM constants (pendulum.py:227-238): g, m, l, dt, |u| clamp, |thdot| clamp
     pendulum: Sequence[float] = (10.0, 1.0, 1.0, 0.05, 2.0, 8.0)
+    # online-adapted residual on top of `net`; None = nominal network only
+    gp: Optional[GPSpec] = None
 
     def __post_init__(self):
         assert 1 <= self.nx <= MAX_NX and 1 <= self.nu <= MAX_NU
@@ -130,6 +178,12 @@ class DynamicsSpec:
             assert self.nx == 2 and self.nu == 1
         else:
             raise ValueError("unknown dynamics kind {}".format(self.kind))
+        if self.gp is not None:
+            assert self.kind in (DYN_MLP, DYN_REX), "a GP residual needs a network as its mean function"
+            if self.gp.space == GP_AT_NETWORK:
+                assert self.gp.X.shape[1] == self.net.dims[0] and self.gp.resid.shape[1] == self.net.dims[-1]
+            else:
+                assert self.gp.X.shape[1] == self.nx + self.nu and self.gp.resid.shape[1] == self.nx
 
     @property
     def macs_per_step(self):
@@ -308,6 +362,13 @@ def spec_to_arrays(spec: RolloutSpec, prefix='spec.'):
     if dy.ext_w is not None:
         d['dyn.ext_w'] = dy.ext_w
         d['dyn.ext_b'] = dy.ext_b
+    if dy.gp is not None:
+        g = dy.gp
+        d['dyn.gp.X'], d['dyn.gp.resid'] = g.X, g.resid
+        d['dyn.gp.lengthscale'], d['dyn.gp.outputscale'], d['dyn.gp.noise'] = g.lengthscale, g.outputscale, g.noise
+        d['dyn.gp.sample'], d['dyn.gp.space'] = np.array(int(g.sample)), np.array(g.space)
+        _put_aff(d, 'dyn.gp.aff_in', g.aff_in)
+        _put_aff(d, 'dyn.gp.aff_out', g.aff_out)
     d['cost.kind'] = np.array(c.kind)
     d['cost.ang_dims'] = np.array(c.ang_dims, dtype=np.int64)
     d['cost.dist_scale'] = c.dist_scale
@@ -341,7 +402,12 @@ def spec_from_arrays(arrays, prefix='spec.'):
     d = {k[len(prefix):]: arrays[k] for k in arrays.keys() if k.startswith(prefix)}
     nx, nu = int(d['dyn.nx']), int(d['dyn.nu'])
     bsn = float(d['dyn.bad_state_norm'])
-    dyn = DynamicsSpec(kind=int(d['dyn.kind']), nx=nx, nu=nu, net=_get_mlp(d, 'dyn.net'),
+    gp = None
+    if 'dyn.gp.X' in d:
+        gp = GPSpec(d['dyn.gp.X'], d['dyn.gp.resid'], d['dyn.gp.lengthscale'], d['dyn.gp.outputscale'],
+                    d['dyn.gp.noise'], bool(int(d['dyn.gp.sample'])), int(d['dyn.gp.space']),
+                    _get_aff(d, 'dyn.gp.aff_in'), _get_aff(d, 'dyn.gp.aff_out'))
+    dyn = DynamicsSpec(kind=int(d['dyn.kind']), nx=nx, nu=nu, net=_get_mlp(d, 'dyn.net'), gp=gp,
                        aff_in=_get_aff(d, 'dyn.aff_in'), aff_out=_get_aff(d, 'dyn.aff_out'),
                        encoder=_get_mlp(d, 'dyn.encoder'), decoder=_get_mlp(d, 'dyn.decoder'),
                        ext_w=d.get('dyn.ext_w'), ext_b=d.get('dyn.ext_b'), aff_y=_get_aff(d, 'dyn.aff_y'),

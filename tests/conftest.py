@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 GOLDEN_CASES = ['push_nominal', 'push_M10', 'push_recovery', 'push_badstate', 'push_null_action', 'peg_nominal',
                 'push_mlp_notransform', 'pendulum']
+# online GP residual: M genuinely different replicas, injected GP draws
+GP_CASES = ['push_gp_latent', 'push_gp_local']
 
 
 def pytest_configure(config):
