@@ -167,3 +167,29 @@ def make_controller(spec: S.RolloutSpec, U):
     ctrl.mpc = mpc
     ctrl.predict_next_state = lambda state, control: None
     return ctrl
+
+
+class RBFKernel:
+    def __init__(self, lengthscale):
+        self.lengthscale = _t(lengthscale).view(-1, 1, 1)
+
+
+def make_online_gp(spec: S.RolloutSpec, nominal):
+    """Duck-typed OnlineGPMixing (online_model.py:324-457) around `nominal`, frozen at spec.dynamics.gp: what
+    hybrid_model.use_temp_local_nominal_model (GP_ORIGINAL) or nominal_adapt=GP_KERNEL_INDEP_OUT (GP_AT_NETWORK)
+    leave in `ctrl.dynamics.nominal_model`."""
+    g = spec.dynamics.gp
+    n, ny = g.resid.shape
+    if g.space == S.GP_ORIGINAL:
+        pre = types.SimpleNamespace(tsf=preprocess.PytorchTransformer(_scaler(g.aff_in), _scaler(g.aff_out)))
+    else:
+        pre = nominal.ds.preprocessor
+    gp = types.SimpleNamespace(
+        training=False,
+        covar_module=types.SimpleNamespace(outputscale=_t(g.outputscale), base_kernel=RBFKernel(g.lengthscale)),
+        # mean function at the training inputs; this stand-in keeps y - m(X) in `y` and answers m(X) = 0
+        forward=lambda xu: types.SimpleNamespace(mean=torch.zeros(len(xu), ny, dtype=torch.double)))
+    lik = types.SimpleNamespace(task_noises=_t(g.noise) * 0.75, noise=_t(g.noise[:1]) * 0 + _t(g.noise) * 0.25)
+    return types.SimpleNamespace(prior=types.SimpleNamespace(dyn_net=nominal), ds=types.SimpleNamespace(preprocessor=pre),
+                                 gp=gp, likelihood=lik, xu=_t(g.X), y=_t(g.resid), use_independent_outputs=True,
+                                 sample_dynamics=g.sample)

@@ -78,3 +78,40 @@ def test_cost_program_is_reread_every_command(cuda_lib):
     with pytest.raises(UnsupportedSpec):
         mpc.command(state)
     mpc.close()
+
+
+@pytest.mark.parametrize('case', ['push_gp_local', 'push_gp_latent'])
+def test_online_gp_is_followed_when_the_nominal_model_is_swapped(cuda_lib, case):
+    """online_controller.py:324-335 swaps `dynamics.nominal_model` for an OnlineGPMixing when non-nominal dynamics
+    start and back when they end (hybrid_model.py:189-202); every dynamics.update refits it.  The drop-in re-reads the
+    residual on each command."""
+    from tampc_b200.mppi import install
+    z, spec = load_golden(case)
+    gp_spec = spec.dynamics.gp
+    spec.dynamics.gp = None
+    ctrl = fake_tampc.make_controller(spec, z['in.U'])
+    mpc = install(ctrl, precision='f64')
+    nominal = ctrl.dynamics.nominal_model
+    mpc.command(torch.from_numpy(z['in.state']), noise=z['in.noise'])
+    cost_nominal = mpc.cost_total.numpy().copy()
+    # entering non-nominal dynamics
+    spec.dynamics.gp = gp_spec
+    ctrl.dynamics.nominal_model = fake_tampc.make_online_gp(spec, nominal)
+    mpc.U = torch.from_numpy(z['in.U'])
+    action = mpc.command(torch.from_numpy(z['in.state']), noise=z['in.noise'], gp_eps=z['in.gp_eps']).numpy()
+    rel = np.max(np.abs(mpc.cost_total.numpy() - z['ref.cost_total']) / np.abs(z['ref.cost_total']))
+    assert rel < 1e-9 and mpc.stats['argmin'] == int(z['ref.argmin'])
+    np.testing.assert_allclose(action, z['ref.action'], rtol=0, atol=1e-8)
+    # a GP update between commands (new data point): the next command must see it
+    g2 = fake_tampc.make_online_gp(spec, nominal)
+    g2.xu, g2.y = g2.xu[:-1], g2.y[:-1]
+    ctrl.dynamics.nominal_model.xu, ctrl.dynamics.nominal_model.y = g2.xu, g2.y
+    mpc.U = torch.from_numpy(z['in.U'])
+    mpc.command(torch.from_numpy(z['in.state']), noise=z['in.noise'], gp_eps=z['in.gp_eps'])
+    assert np.max(np.abs(mpc.cost_total.numpy() - z['ref.cost_total'])) > 0
+    # leaving: back to the nominal network (and to the tensor-core layout)
+    ctrl.dynamics.nominal_model = nominal
+    mpc.U = torch.from_numpy(z['in.U'])
+    mpc.command(torch.from_numpy(z['in.state']), noise=z['in.noise'])
+    np.testing.assert_array_equal(mpc.cost_total.numpy(), cost_nominal)
+    mpc.close()

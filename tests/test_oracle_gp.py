@@ -64,3 +64,27 @@ def test_gp_spec_roundtrip():
         assert a.keys() == b.keys()
         for k in a:
             np.testing.assert_array_equal(a[k], b[k])
+
+
+def test_extraction_of_a_duck_typed_online_gp():
+    """extract.py reads an OnlineGPMixing-like object by attribute names only (runs on the GPU box too)."""
+    import fake_tampc
+    from tampc_b200 import extract
+    for case in GP_CASES:
+        z, spec = load_golden(case)
+        ctrl = fake_tampc.make_controller(spec, z['in.U'])
+        nominal = ctrl.dynamics.nominal_model
+        ctrl.dynamics.nominal_model = fake_tampc.make_online_gp(spec, nominal)
+        got = extract.spec_from_controller(ctrl)
+        a, b = S.spec_to_arrays(spec), S.spec_to_arrays(got)
+        for k in a:
+            if k.endswith('name') or 'bad_state_norm' in k:
+                continue
+            np.testing.assert_allclose(np.asarray(a[k], dtype=float), np.asarray(b[k], dtype=float), rtol=0, atol=1e-12, err_msg=k)
+        ctrl.dynamics.nominal_model.gp.training = True
+        with pytest.raises(extract.UnsupportedSpec):
+            extract.spec_from_controller(ctrl)
+        ctrl.dynamics.nominal_model.gp.training = False
+        ctrl.dynamics.nominal_model.use_independent_outputs = False
+        with pytest.raises(extract.UnsupportedSpec):
+            extract.spec_from_controller(ctrl)

@@ -88,3 +88,37 @@ def test_peg_env_functions_probe_correctly():
     assert spec.cost.ang_dims == () and spec.cost.usim_dims == (0, 1) and spec.dynamics.wrap_dims == ()
     np.testing.assert_array_equal(spec.cost.dist_scale, [1, 1, 0, 0, 0])
     assert spec.dynamics.macs_per_step == 3507
+
+
+def test_oracle_follows_the_live_online_gp_through_updates():
+    """The TAMPC flow (online_controller.py:324-335, 85): the nominal model becomes a temporary local GP fed one
+    transition per control step.  After each update the re-extracted spec + oracle must reproduce the reference's
+    command with the action noise and the GP draws injected."""
+    torch.manual_seed(1)
+    ctrl, ds, env = rh.build_task('push', num_samples=24, rollout_samples=4, horizon=8)
+    ctrl.set_goal(np.array([0.55, -0.65, 0., 0., 0.]))
+    g = torch.Generator().manual_seed(11)
+    x = torch.tensor([0.6, 0.14, -1.2, 5., 12.], dtype=torch.double)
+    with torch.enable_grad():
+        ctrl.dynamics.use_temp_local_nominal_model()
+    for step in range(3):
+        u = torch.rand(3, dtype=torch.double, generator=g) * 2 - 1
+        nx_ = x + 0.004 * torch.randn(5, dtype=torch.double, generator=g) * torch.tensor([1, 1, 1, 40, 40.])
+        with torch.enable_grad():
+            ctrl.dynamics.update(x, u, nx_)
+        x = nx_
+        spec = extract.spec_from_controller(ctrl)
+        assert spec.dynamics.gp.space == S.GP_ORIGINAL and len(spec.dynamics.gp.X) == step + 1
+        U0 = torch.rand(spec.sampler.T, 3, dtype=torch.double, generator=g) * 0.5
+        noise = O.sample_noise(spec, 20 + step)
+        eps = torch.randn(spec.sampler.T, 4, spec.sampler.K, 5, dtype=torch.double, generator=g)
+        with rh.inject_gp_draws([eps[t].reshape(-1, 5) for t in range(spec.sampler.T)]) as inj:
+            a_ref = _run_ref(ctrl, spec, x, U0, noise)
+            assert not inj.draws
+        out = O.command(spec, x, U0, noise, eps)
+        rel = ((out['cost_total'] - ctrl.mpc.cost_total).abs() / ctrl.mpc.cost_total.abs()).max().item()
+        assert rel < 1e-10 and out['argmin'] == int(ctrl.mpc.cost_total.argmin())
+        assert (out['action'] - a_ref).abs().max().item() < 1e-11
+    # leaving non-nominal dynamics restores the plain network (hybrid_model.py:201-202)
+    ctrl.dynamics.use_normal_nominal_model()
+    assert extract.spec_from_controller(ctrl).dynamics.gp is None
