@@ -517,6 +517,81 @@ __device__ __forceinline__ CT running_cost(const CostS<ST, CT>& c, const ST (&x)
   return cost;
 }
 
+// The loop-invariant operands of the goal / trap cost held in registers.  A rollout loop that stores to shared
+// memory between steps cannot keep them there by itself (the compiler must assume the stores alias the cost block),
+// so every step would re-load ~45 scalars; latency-bound kernels load them once before the horizon loop instead.
+template <typename ST, typename CT, int NX, int NU>
+struct CostHot {
+  ST goal[NX];
+  CT Q[NX * NX], R[NU * NU], dist_scale[NX];
+  __device__ __forceinline__ void load(const CostS<ST, CT>& c) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      goal[i] = c.goal[i];
+      dist_scale[i] = c.dist_scale[i];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) Q[i * NX + j] = c.Q[i * kMaxNx + j];
+    }
+#pragma unroll
+    for (int i = 0; i < NU; ++i)
+#pragma unroll
+      for (int j = 0; j < NU; ++j) R[i * NU + j] = c.R[i * kMaxNu + j];
+  }
+};
+
+// running_cost with the goal-cost operands taken from registers; same operations in the same order
+template <typename ST, typename CT, int NX, int NU>
+__device__ __forceinline__ CT running_cost_hot(const CostS<ST, CT>& c, const CostHot<ST, CT, NX, NU>& h, const ST (&x)[NX], const ST (&us)[NU],
+                                               int part, int nparts) {
+  if (c.kind == TAMPC_COST_RECOVERY) return running_cost<ST, CT, NX, NU>(c, x, us, part, nparts);
+  CT d[NX];
+  CT u[NU];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) u[i] = (CT)us[i];
+  CT cost = (CT)0;
+  if (part == 0) {
+    state_diff<ST, CT, NX>(c.ang_mask, x, h.goal, d);
+    CT total = (CT)0;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      CT col = (CT)0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) col = t_fma(d[i], h.Q[i * NX + j], col);
+      total = t_fma(col, d[j], total);
+    }
+    cost = total;
+    CT ru = (CT)0;
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+      CT col = (CT)0;
+#pragma unroll
+      for (int i = 0; i < NU; ++i) col = t_fma(u[i], h.R[i * NU + j], col);
+      ru = t_fma(col, u[j], ru);
+    }
+    cost += ru;
+  }
+  if (c.use_trap && c.n_traps > 0) {
+    CT un = (CT)0;
+#pragma unroll
+    for (int i = 0; i < NU; ++i)
+      if ((c.usim_mask >> i) & 1u) un = t_fma(u[i], u[i], un);
+    un = t_max(t_sqrt_fast(un), (CT)kCosSimEps);
+    CT tsum = (CT)0;
+    for (int p = part; p < c.n_traps; p += nparts) {
+      state_diff<ST, CT, NX>(c.ang_mask, x, c.trap_x[p], d);
+      CT cx = t_max(t_min(t_div((CT)1, dist_sq<CT, NX>(h.dist_scale, d)), (CT)kTrapMaxCost), (CT)0);
+      CT dot = (CT)0;
+#pragma unroll
+      for (int i = 0; i < NU; ++i)
+        if ((c.usim_mask >> i) & 1u) dot = t_fma(u[i], c.trap_u[p][i], dot);
+      CT cu = t_max(t_min(t_div(dot, un * c.trap_u_norm[p]), (CT)1), (CT)0);
+      tsum = t_fma(cx, cu, tsum);
+    }
+    cost = t_fma(tsum, c.trap_weight, cost);
+  }
+  return cost;
+}
+
 // terminal_cost_multiplier * cost(x_T, terminal=True): QR on the state only; the trap term is multiplied by
 // c_u = 0 when terminal (cost.py:177)      [controller.py:251-259]
 template <typename ST, typename CT, int NX>

@@ -233,6 +233,7 @@ struct ModelRexMma {
   using Enc = Mlp3Mma<P, 1, E1 / 8, E2 / 8, 1>;
   using Dyn = Mlp3Mma<P, 1, D1 / 8, D2 / 8, 1>;
   static constexpr int CO8 = (NX_ * NV + 7) / 8;
+  static constexpr int kNV = NV;
   using Dec = Mlp3Mma<P, 1, C1 / 8, C2 / 8, CO8>;
   static constexpr int NX = NX_, NU = NU_;
   static constexpr int kOffDyn = Enc::kBytes;
@@ -578,6 +579,239 @@ __global__ void __launch_bounds__(64) rollout_mma_pipe_kernel(const RolloutArgs 
                          gridDim.x);
     }
   }
+}
+
+// ---- role-split variant for latency-bound K (RexExtract shapes) --------------------------------------------
+// At K <= ~19k there is at most one 16-sample tile per SM sub-partition and the single-warp kernel is bound by the
+// length of its own dependent instruction chain (ncu: issue slots 28 % busy, stall `wait` 50 %; measured
+// tools/peaks/mma_latency: HMMA.1688.TF32 issues every 8 cycles, dependent latency 20).  Here a tile is shared by two
+// warps, and only what the recurrence x_{t+1} = f(x_t, u_t) really needs stays on the critical path:
+//   warp A ("chain")    [x_t, u_t] -> encoder -> latent dynamics -> v_t;  x_{t+1} = x_t + C_t v_t + d0, wrap, guard
+//   warp B ("decoder")  x_t -> decoder -> C_t  (ready before A's chain ends);  running / perturbation / terminal cost
+// A publishes the rows of step t+1 and goes straight on; B trails: it turns the published x into C_{t+1} first and
+// evaluates the cost of the finished step while A is busy.  Hand-offs: 512-byte shared-memory rows and two named
+// barriers (bar.arrive / bar.sync, 64 threads).  The arithmetic per sample (layer order, accumulation order, cost
+// terms) is exactly the single-warp kernel's, so both produce bitwise-identical costs.  Two tiles per 128-thread CTA;
+// CTAs that land on the same SM alternate the order of the roles so that every sub-partition gets one chain warp and
+// one decoder warp (warps are bound to sub-partitions by their index in the CTA).
+template <class Model>
+struct SplitSmem {
+  using T = typename Model::T;
+  static constexpr int SW = PolicyTF32x3::MT, TILES = 2;
+  static constexpr int kCStride = 8 * Model::CO8 + 2;  // floats per row of the decoder output tile (+2: bank spread)
+  static constexpr size_t kCost = align16<int>(Model::kBytes);
+  static constexpr size_t kSampler = kCost + align16<int>(sizeof(CostS<float, float>));
+  static constexpr size_t kSamplerD = kSampler + align16<int>(sizeof(SamplerS<float>));
+  static constexpr size_t kU = kSamplerD + align16<int>(sizeof(SamplerS<double>));
+  static __host__ __device__ constexpr size_t tiles_off(int T_) { return kU + align16<int>(sizeof(float) * (size_t)T_ * kMaxNu); }
+  // per tile: xs[SW][8] network input rows | xc[SW][8] true state + bad flag | vs[SW][8] | Cs[SW][kCStride] |
+  //           upre[T][SW][NU] actions | pcs[T][SW] perturbation-cost terms
+  static constexpr size_t kXs = 0, kXc = sizeof(float) * SW * 8, kVs = 2 * sizeof(float) * SW * 8, kCs = 3 * sizeof(float) * SW * 8;
+  static constexpr size_t kUpre = kCs + align16<int>(sizeof(float) * SW * kCStride);
+  static __host__ __device__ constexpr size_t pcs_off(int T_) { return kUpre + align16<int>(sizeof(float) * (size_t)T_ * SW * Model::NU); }
+  static __host__ __device__ constexpr size_t tile_bytes(int T_) { return pcs_off(T_) + align16<int>(sizeof(float) * (size_t)T_ * SW); }
+  static __host__ __device__ constexpr size_t bytes(int T_) { return tiles_off(T_) + TILES * tile_bytes(T_); }
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+static __device__ unsigned int g_sm_turn[1024];  // per-SM CTA counter (never reset: only its parity is used)
+
+template <class Model>
+__global__ void __launch_bounds__(128) rollout_mma_split_kernel(const RolloutArgs a) {
+  static_assert(sizeof(typename Model::T) == 4, "role-split variant is for the TF32x3 policy");
+  static_assert(Model::NX < 8, "xc rows keep the bad flag in column NX");
+  using P = PolicyTF32x3;
+  constexpr int NX = Model::NX, NU = Model::NU, NV = Model::kNV, SW = P::MT, CO8 = Model::CO8;
+  using L = SplitSmem<Model>;
+  constexpr int CS = L::kCStride;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned int s_flip;
+  unsigned char* w = smem_raw;
+  CostS<float, float>& cs = *reinterpret_cast<CostS<float, float>*>(smem_raw + L::kCost);
+  SamplerS<float>& sp = *reinterpret_cast<SamplerS<float>*>(smem_raw + L::kSampler);
+  float* Ush = reinterpret_cast<float*>(smem_raw + L::kU);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = warp >> 1;
+  const int T = a.src.T;
+  unsigned char* tbase = smem_raw + L::tiles_off(T) + (size_t)tile * L::tile_bytes(T);
+  float* xs = reinterpret_cast<float*>(tbase + L::kXs);      // [SW][8] the step's network input rows (x_t | u_t | 0), zero if guarded
+  float* xc = reinterpret_cast<float*>(tbase + L::kXc);      // [SW][8] the state the cost sees + the guard flag of the step
+  float* vs = reinterpret_cast<float*>(tbase + L::kVs);      // [SW][8] latent output v_t (private to warp A)
+  float* Cs = reinterpret_cast<float*>(tbase + L::kCs);      // [SW][CS] decoder output C_t
+  float* upre = reinterpret_cast<float*>(tbase + L::kUpre);  // [T][SW][NU] actions the dynamics sees
+  float* pcs = reinterpret_cast<float*>(tbase + L::pcs_off(T));  // [T][SW] perturbation cost of (t, sample) (controller.py:395,400)
+  {
+    copy_image_async(smem_raw, a.image, (int)L::kU, tid, 128);
+    if (tid == 0) {
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      s_flip = atomicAdd(&g_sm_turn[smid & 1023u], 1u) & 1u;
+    }
+    for (int i = tid; i < T * NU; i += 128) {
+      int t = i / NU, d = i % NU, ts = t + a.shift;
+      Ush[t * kMaxNu + d] = (float)(ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d]);
+    }
+    copy_image_wait();
+  }
+  __syncthreads();
+  const int kbase = (blockIdx.x * L::TILES + tile) * SW;
+  const int row = lane % SW, part = lane / SW;
+  const bool live = kbase + row < a.K_local;
+  const int k = live ? kbase + row : a.K_local - 1;
+  if (kbase < a.K_local) {
+    // every perturbed action of the horizon, drawn by the tile's 64 threads (independent items)
+#pragma unroll 2
+    for (int item = tid & 63; item < T * SW; item += 64) {
+      const int t = item / SW, r = item % SW;
+      float u[NU], npost[NU];
+      pcs[item] = sample_action<float, NU>(a.src, sp, Ush + t * kMaxNu, min(kbase + r, a.K_local - 1), t, u, npost);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) upre[item * NU + i] = u[i];
+    }
+  }
+  __syncthreads();
+  if (kbase >= a.K_local) return;  // (no block-wide barrier below)
+  const int bar_x = 1 + 2 * tile, bar_c = 2 + 2 * tile;
+  const float slope = (float)a.slope;
+
+  if (((warp ^ s_flip) & 1u) == 0) {
+    // ================= warp A: encoder + latent dynamics + state update (the recurrence)
+    const float bad2 = (float)(a.bad_norm * a.bad_norm);
+    const float* d0 = reinterpret_cast<const float*>(w + Model::kOffD0);
+    float x[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = (float)a.state[i];
+    bool bad = false;
+    // rows of step t: guard (online_controller.py:62-66); xs = what the networks see, xc = what the cost sees
+    auto publish = [&](int t) {
+      bad = false;
+      if (a.has_guard) {
+        float n2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) n2 = __fmaf_rn(x[i], x[i], n2);
+        bad = n2 > bad2;
+      }
+      if (part == 0) {
+        float* r = xs + row * 8;
+        float* c = xc + row * 8;
+        if (t < T) {
+          float u[NU];
+#pragma unroll
+          for (int i = 0; i < NU; ++i) u[i] = upre[(t * SW + row) * NU + i];
+          float rv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rv[i] = bad ? 0.f : (i < NX ? x[i] : (i < NX + NU ? u[i - NX] : 0.f));
+          reinterpret_cast<float4*>(r)[0] = make_float4(rv[0], rv[1], rv[2], rv[3]);
+          reinterpret_cast<float4*>(r)[1] = make_float4(rv[4], rv[5], rv[6], rv[7]);
+        }
+        float cv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cv[i] = i < NX ? x[i] : (i == NX && bad ? 1.f : 0.f);
+        reinterpret_cast<float4*>(c)[0] = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        reinterpret_cast<float4*>(c)[1] = make_float4(cv[4], cv[5], cv[6], cv[7]);
+      }
+      __syncwarp();
+      named_bar_arrive(bar_x, 64);
+    };
+    publish(0);
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+      PROF_T0();
+      float in[1][1][P::R];
+      load_blocks<P, 1, 1, 8>(xs, in, lane);
+      PROF(1);
+      float z[1][1][P::R], v[1][1][P::R];
+      Model::Enc::template eval<1>(w, in, z, slope, lane);
+      PROF(2);
+      Model::Dyn::template eval<1>(w + Model::kOffDyn, z, v, slope, lane);
+      PROF(3);
+      store_blocks<P, 1, 1, 8>(vs, v, 0, lane);
+      __syncwarp();
+      named_bar_sync(bar_c, 64);  // Cs holds C_t
+      PROF(0);
+      const float* cr = Cs + row * CS;
+      const float* vr = vs + row * 8;
+      const bool was_bad = bad;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        float dx = d0[i];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) dx = __fmaf_rn(cr[i * NV + j], vr[j], dx);
+        float xn = (was_bad ? 0.f : x[i]) + dx;
+        if ((a.wrap_mask >> i) & 1u) xn = angle_normalize<float>(xn);
+        x[i] = was_bad ? 0.f : xn;
+      }
+      __syncwarp();  // every lane is done with Cs / vs / xs of step t
+      publish(t + 1);
+      PROF(4);
+    }
+  } else {
+    // ================= warp B: decoder, then the cost of the step that just finished (two lanes per sample share
+    // the trap-set terms)
+    double cost = 0.0;
+    float pert = 0.f;
+    float x[NX], useen[NU];
+    CostHot<float, float, NX, NU> hot;
+    hot.load(cs);
+#pragma unroll 1
+    for (int t = 0; t <= T; ++t) {
+      PROF_T0();
+      named_bar_sync(bar_x, 64);  // xs / xc hold step t
+      PROF(7);
+      const float* c = xc + row * 8;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = c[i];
+      const bool bad = c[NX] != 0.f;
+      if (t < T) {
+        float in[1][1][P::R], C[1][CO8][P::R];
+        load_blocks<P, 1, 1, 8>(xs, in, lane);
+        Model::Dec::template eval<1>(w + Model::kOffDec, in, C, slope, lane);
+        store_blocks<P, 1, CO8, CS>(Cs, C, 0, lane);
+        __syncwarp();
+        named_bar_arrive(bar_c, 64);
+      }
+      PROF(6);
+      if (t > 0) {
+        // x = x_t is the state reached by step t-1 (zero if that step was guarded, online_controller.py:77)
+        cost += (double)running_cost_hot<float, float, NX, NU>(cs, hot, x, useen, part, 2);
+        if (a.states_out != nullptr && live && part == 0) {
+          double* so = a.states_out + ((size_t)k * T + (t - 1)) * NX;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) so[i] = (double)x[i];
+        }
+      }
+      PROF(9);
+      if (t < T) {
+        pert += pcs[t * SW + row];  // drawn with the action, summed in step order
+#pragma unroll
+        for (int i = 0; i < NU; ++i) useen[i] = bad ? 0.f : upre[(t * SW + row) * NU + i];
+      }
+      PROF(5);
+    }
+    const double mine = cost;
+    cost += __shfl_sync(0xffffffffu, mine, (row + SW) & 31);
+    double total = cost + (double)terminal_cost<float, float, NX>(cs, x);
+    total += (double)pert;
+    if (live && part == 0) a.cost_out[k] = total;
+  }
+}
+
+template <class Model>
+cudaError_t launch_rollout_mma_split(const RolloutArgs& a, int /*block*/, cudaStream_t stream) {
+  auto kern = rollout_mma_split_kernel<Model>;
+  using L = SplitSmem<Model>;
+  const size_t smem = L::bytes(a.src.T);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const int per_block = L::TILES * L::SW;
+  const int grid = (a.K_local + per_block - 1) / per_block;
+  kern<<<grid, 128, smem, stream>>>(a);
+  return cudaGetLastError();
 }
 
 template <class Model>

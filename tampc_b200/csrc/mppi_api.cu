@@ -464,6 +464,20 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     // latency-bound sizes: the two-warp pipelined kernel (dynamics warp + cost warp per 16-sample tile)
     // (measured on B200: wins while at most two 16-sample tiles share an SM, i.e. K <= 4736; above that the
     //  single-warp kernel's lower footprint wins.  TAMPC_PIPE=0/1 forces the choice.)
+    // latency-bound sizes of the RexExtract shapes: two warps per 16-sample tile split by role (mma_rollout.cuh).
+    // Measured on B200 (push, T=40; rollout kernel, split vs one warp per tile): K=512 64 vs 74 us, 4096 67 vs 78,
+    // 8192 86 vs 112, 12288 117 vs 141; at 16384 (more than five tiles per SM) 161 vs 145, so the single-warp
+    // kernel takes over.  TAMPC_SPLIT=0/1 forces the choice.
+    {
+      const int split_env = env_int("TAMPC_SPLIT", -1);
+      const bool split = !big && (split_env >= 0 ? split_env != 0 : (K + 15) / 16 <= 5 * 148 + 28);
+      if (!f64 && idx == 0 && v->tf32_split && split && en == 0) {
+        p.fn = v->tf32_split;
+        p.block = 128;
+        p.fuse_warps = 0;
+        return p;
+      }
+    }
     const int tiles = (K + 15) / 16, pipe_env = env_int("TAMPC_PIPE", -1);
     const bool pipe = !big && (pipe_env >= 0 ? pipe_env != 0 : tiles <= 2 * 148);
     if (!f64 && idx == 0 && v->tf32_pipe && pipe) {

@@ -18,6 +18,7 @@ struct ModelVariant {
   rollout_launch_fn f64_mma[3];   // DMMA kernels, NM = 1, 2, 4 m-tiles (8, 16, 32 samples) per warp
   rollout_launch_fn tf32_mma[2];
   GpLaunchers gp;                 // one-thread-per-(sample, replica) FMA kernels with the online GP residual
+  rollout_launch_fn tf32_split;   // two warps per 16-sample tile, split by role (RexExtract shapes, latency-bound K)
   rollout_launch_fn tf32_pipe;    // two-warp pipelined 3xTF32 kernel for small K (16 samples per CTA)  // 3xTF32 kernels, NM = 1, 2 (16, 32 samples per warp); float32 state and cost terms, float64 cost sum
 };
 

@@ -10,7 +10,7 @@ int main(int argc, char** argv) {
   const int T = 40;
   std::vector<unsigned char> w(Model::kBytes);
   for (size_t i = 0; i < w.size() / 4; ++i) ((float*)w.data())[i] = 0.01f * ((int)(i * 2654435761u % 200) - 100) / 100.f;
-  void* dw; cudaMalloc(&dw, w.size()); cudaMemcpy(dw, w.data(), w.size(), cudaMemcpyHostToDevice);
+  void* dw; cudaMalloc(&dw, w.size() + 16384); cudaMemset(dw, 0, w.size() + 16384); cudaMemcpy(dw, w.data(), w.size(), cudaMemcpyHostToDevice);
   tampc_cost_desc c{}; c.kind = 0; c.nx = 5; c.nu = 3; c.ang_mask = 4; c.usim_mask = 5; c.use_trap_cost = 1; c.n_traps = 3; c.trap_weight = 1; c.has_terminal = 1; c.terminal_multiplier = 50;
   for (int i = 0; i < 5; ++i) { c.dist_scale[i] = i < 2 ? 1 : 0.1; c.Q[i * 8 + i] = 10; c.goal[i] = 0.5; for (int p = 0; p < 3; ++p) c.trap_x[p][i] = 0.3 * p; }
   for (int i = 0; i < 3; ++i) { c.R[i * 4 + i] = 0.01; for (int p = 0; p < 3; ++p) c.trap_u[p][i] = 0.5; }
@@ -25,10 +25,13 @@ int main(int argc, char** argv) {
   for (int rep = 0; rep < 2; ++rep) {
     unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_prof, z, sizeof z);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0);
-    cudaError_t e = (argc > 4 && argv[4][0] == 'p') ? launch_rollout_mma_pipe<Model>(a, 64, 0) : (argc > 4 ? (NM == 1 ? launch_rollout_mma<Model, float, float, 1, true>(a, block, 0) : launch_rollout_mma<Model, float, float, 2, false>(a, block, 0)) : (NM == 1 ? launch_rollout_mma<Model, double, float, 1, true>(a, block, 0) : launch_rollout_mma<Model, double, float, 2, false>(a, block, 0)));
+    const bool split = argc > 4 && argv[4][0] == 's';
+    cudaError_t e = split ? launch_rollout_mma_split<Model>(a, 128, 0) : (argc > 4 && argv[4][0] == 'p') ? launch_rollout_mma_pipe<Model>(a, 64, 0) : (argc > 4 ? (NM == 1 ? launch_rollout_mma<Model, float, float, 1, true>(a, block, 0) : launch_rollout_mma<Model, float, float, 2, false>(a, block, 0)) : (NM == 1 ? launch_rollout_mma<Model, double, float, 1, true>(a, block, 0) : launch_rollout_mma<Model, double, float, 2, false>(a, block, 0)));
     cudaEventRecord(e1); cudaDeviceSynchronize(); float ms; cudaEventElapsedTime(&ms, e0, e1);
     unsigned long long g[16]; cudaMemcpyFromSymbol(g, g_prof, sizeof g);
-    const char* names[] = {"sample_action", "guard", "stage_in", "enc", "dyn", "dec", "stage_out+dx", "wrap", "cost", "publish"};
+    const char* names_1[] = {"sample_action", "guard", "stage_in", "enc", "dyn", "dec", "stage_out+dx", "wrap", "cost", "publish"};
+    const char* names_s[] = {"A wait_c", "A load", "A enc", "A dyn", "A dx+publish", "B pert", "B dec", "B wait_x", "-", "B cost"};
+    const char** names = split ? names_s : names_1;
     int SW = NM * 16; double warps = (double)((K + SW - 1) / SW);
     if (rep) { printf("K=%d NM=%d block=%d  %.1f us  err=%d\n", K, NM, block, ms * 1e3, (int)e); double tot = 0;
       for (int i = 0; i < 10; ++i) { double c = g[i] / warps / T; tot += c; printf("  %-14s %8.0f cycles/step/warp\n", names[i], c); } printf("  %-14s %8.0f\n", "sum", tot); }
