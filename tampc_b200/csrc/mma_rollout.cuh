@@ -313,8 +313,10 @@ struct MmaSmem {
 
 // PRE: draw the whole horizon's standard normals into shared memory before the loop (all 32 lanes, independent
 // Philox blocks -> instruction-level parallelism), instead of one dependent Philox + Box-Muller chain per step.
-template <class Model, typename ST, typename CT, int NM, bool PRE>
-__global__ void __launch_bounds__(128) rollout_mma_kernel(const RolloutArgs a) {
+// BLK: largest block the instantiation is launched with.  256 asks for two resident CTAs (<= 128 registers): eight
+// warps share one copy of the image, 16 warps per SM instead of the 12 that three 4-warp CTAs give.
+template <class Model, typename ST, typename CT, int NM, bool PRE, int BLK = 128>
+__global__ void __launch_bounds__(BLK, BLK == 256 ? 2 : 1) rollout_mma_kernel(const RolloutArgs a) {
   using P_T = typename Model::T;
   constexpr int NX = Model::NX, NU = Model::NU;
   constexpr int SW = NM * (sizeof(P_T) == 8 ? PolicyF64::MT : PolicyTF32x3::MT);  // samples per warp
@@ -829,9 +831,10 @@ cudaError_t launch_rollout_mma_pipe(const RolloutArgs& a, int /*block*/, cudaStr
   return cudaGetLastError();
 }
 
-template <class Model, typename ST, typename CT, int NM, bool PRE>
+template <class Model, typename ST, typename CT, int NM, bool PRE, int BLK = 128>
 cudaError_t launch_rollout_mma(const RolloutArgs& a, int block, cudaStream_t stream) {
-  auto kern = rollout_mma_kernel<Model, ST, CT, NM, PRE>;
+  auto kern = rollout_mma_kernel<Model, ST, CT, NM, PRE, BLK>;
+  if (block > BLK) block = BLK;
   constexpr int SW = NM * (sizeof(typename Model::T) == 8 ? PolicyF64::MT : PolicyTF32x3::MT);
   const int warps = block / 32;
   const size_t smem = MmaSmem<Model, ST, CT>::bytes(a.src.T, warps, SW, PRE);

@@ -456,7 +456,19 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     const int warps = (K + (mt << idx) - 1) / (mt << idx);
     p.block = warps <= cap32 ? 32 : (warps <= cap64 ? 64 : 128);
     p.fn = f64 ? v->f64_mma[idx] : v->tf32_mma[idx];
-    if (eb == 32 || eb == 64 || eb == 128 || eb == 256) p.block = eb;
+    if (eb == 32 || eb == 64 || eb == 128) p.block = eb;
+    // throughput-bound 3xTF32: eight warps per CTA and two CTAs per SM give 16 resident warps instead of 12.
+    // Measured on B200 (push, T=40): a full wave takes 1.18x as long but holds 1.33x the samples (1M: 5.98 -> 5.68 ms),
+    // so it is used when it does not add a wave (K=131072: 0.83 vs 0.78 ms).  TAMPC_WIDE=0/1 forces the choice.
+    if (!f64 && idx == 1 && !big && v->tf32_mma_wide && eb == 0) {
+      const int wide_env = env_int("TAMPC_WIDE", -1);
+      const int ctas_d = (warps + 3) / 4, ctas_w = (warps + 7) / 8;
+      const bool wide = wide_env >= 0 ? wide_env != 0 : (ctas_d > 148 * 3 && ctas_w <= 148 * 2) || ctas_w >= 148 * 2 * 4;
+      if (wide) {
+        p.fn = v->tf32_mma_wide;
+        p.block = 256;
+      }
+    }
     {
       const int wpb = p.block / 32, grid = (warps + wpb - 1) / wpb;
       if (grid * wpb <= kMaxFusedWarps && env_int("TAMPC_FUSE", 0)) p.fuse_warps = grid * wpb;

@@ -18,6 +18,7 @@ struct ModelVariant {
   rollout_launch_fn f64_mma[3];   // DMMA kernels, NM = 1, 2, 4 m-tiles (8, 16, 32 samples) per warp
   rollout_launch_fn tf32_mma[2];
   GpLaunchers gp;                 // one-thread-per-(sample, replica) FMA kernels with the online GP residual
+  rollout_launch_fn tf32_mma_wide; // NM = 2, 256-thread CTAs, two per SM (throughput-bound K)
   rollout_launch_fn tf32_split;   // two warps per 16-sample tile, split by role (RexExtract shapes, latency-bound K)
   rollout_launch_fn tf32_pipe;    // two-warp pipelined 3xTF32 kernel for small K (16 samples per CTA)  // 3xTF32 kernels, NM = 1, 2 (16, 32 samples per warp); float32 state and cost terms, float64 cost sum
 };
@@ -53,6 +54,7 @@ void add_mma(ModelVariant& v) {
   v.f64_mma[2] = &launch_rollout_mma<MM64, double, double, 4, false>;
   v.tf32_mma[0] = &launch_rollout_mma<MM32, float, float, 1, true>;
   v.tf32_mma[1] = &launch_rollout_mma<MM32, float, float, 2, false>;
+  v.tf32_mma_wide = &launch_rollout_mma<MM32, float, float, 2, false, 256>;
   v.tf32_pipe = &launch_rollout_mma_pipe<MM32>;
 }
 
