@@ -33,7 +33,7 @@ FP64_TENSOR_PEAK_TFLOPS = 37.1  # tools/peaks/mma_peaks dmma (profiles/mma_peaks
 TF32_MMA_PEAK_TFLOPS = 278.0  # tools/peaks/mma_peaks mma.sync m16n8k8 tf32
 # DRAM traffic of one rollout launch at K=8192 from the committed ncu capture (the kernel reads its ~45 KB image and
 # the nominal sequence, writes 8*K bytes of costs that stay in L2): compute-bound by four orders of magnitude
-NCU_DRAM_BYTES_PER_LAUNCH = {'tf32x3': 104448}
+NCU_DRAM_BYTES_PER_LAUNCH = {'tf32x3': 82688}
 
 
 def load_push_spec(K):
@@ -267,8 +267,9 @@ def main():
             roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.precision),
                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, one "
-                                          "ncu --set full capture (profiles/r1_rollout_*_ncu_summary.txt)",
-                        "kernel": "rollout (fused K x T)",
+                                          "ncu --set full capture (profiles/r1c_rollout_split_tf32x3_k8192_ncu_summary.txt)",
+                        "kernel": "rollout (fused K x T): rollout_mma_split_kernel at this K (two warps per 16-sample "
+                                  "tile), rollout_mma_kernel above K=12288",
                         "kernel_ms": roll_ms, "algorithmic_flop_per_launch": K * T * flop_per_step,
                         "peak_source": src}
         # CPU baseline: bounded sample of the same workload on the host cores (oracle port, float64)

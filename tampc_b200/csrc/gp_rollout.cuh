@@ -55,9 +55,20 @@ __device__ __forceinline__ void load4(const double* p, double (&v)[4]) {
   v[0] = q0.x; v[1] = q0.y; v[2] = q1.x; v[3] = q1.y;
 }
 
-// delta[d] = (k_d alpha_d + sqrt(var_d) eps_d) * out_mul_d  for the input row `in` (NIN entries)
+// Four-element vectors of the GP's arithmetic type (shared-memory staging of the kernel vector k(g, X)).
+template <typename T> struct GpVec4;
+template <> struct GpVec4<float> { using type = float4; };
+template <> struct GpVec4<double> { using type = double4; };
+template <typename T> __host__ __device__ constexpr size_t gp_scratch_bytes(int threads) { return sizeof(T) * kGpMaxPoints * (size_t)threads; }
+
+// delta[d] = (k_d alpha_d + sqrt(var_d) eps_d) * out_mul_d  for the input row `in` (NIN entries).
+// `ks`: this thread's slot of the per-CTA scratch, 4-element vectors `kstride` apart (layout [j/4][thread]): the
+// kernel vector of one output lives there between its evaluation and the triangular product.  (A per-thread local
+// array would live in L1, most of which the shared-memory carve-out takes: measured 144 cycles per 4 FMAs.)
 template <typename T, int NIN, int NOUT>
-__device__ __forceinline__ void gp_delta(const unsigned char* __restrict__ gp, const T (&in)[NIN], const T (&eps)[NOUT], T (&delta)[NOUT]) {
+__device__ __forceinline__ void gp_delta(const unsigned char* __restrict__ gp, typename GpVec4<T>::type* __restrict__ ks, int kstride,
+                                         const T (&in)[NIN], const T (&eps)[NOUT], T (&delta)[NOUT]) {
+  using V4 = typename GpVec4<T>::type;
   const GpHeader<T>& H = *reinterpret_cast<const GpHeader<T>*>(gp);
   const T* __restrict__ X = reinterpret_cast<const T*>(gp + sizeof(GpHeader<T>));
   const int n = H.n, npad = H.npad;
@@ -66,42 +77,47 @@ __device__ __forceinline__ void gp_delta(const unsigned char* __restrict__ gp, c
   T g[NIN];
 #pragma unroll
   for (int i = 0; i < NIN; ++i) g[i] = t_fma(in[i], H.in_scale[i], H.in_off[i]);
-  __align__(16) T d2[kGpMaxPoints];
-  for (int j = 0; j < npad; ++j) {
-    T s = (T)0;
-#pragma unroll
-    for (int i = 0; i < NIN; ++i) {
-      const T d = g[i] - X[j * kGpMaxDim + i];
-      s = t_fma(d, d, s);
-    }
-    d2[j] = s;
-  }
 #pragma unroll 1
   for (int d = 0; d < NOUT; ++d) {
-    __align__(16) T kst[kGpMaxPoints];
     T mean = (T)0;
     const T nh = H.neg_half_inv_l2[d], os = H.oscale[d];
-    for (int j = 0; j < npad; ++j) {
-      const T k = j < n ? os * t_exp(nh * d2[j]) : (T)0;
-      kst[j] = k;
-      mean = t_fma(alpha[d * npad + j], k, mean);
+#pragma unroll 2
+    for (int j4 = 0; j4 < npad; j4 += 4) {
+      T kq[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j4 + e;
+        T s = (T)0;
+#pragma unroll
+        for (int i = 0; i < NIN; ++i) {
+          const T dd = g[i] - X[j * kGpMaxDim + i];
+          s = t_fma(dd, dd, s);
+        }
+        kq[e] = j < n ? os * t_exp(nh * s) : (T)0;
+        mean = t_fma(alpha[d * npad + j], kq[e], mean);
+      }
+      V4 v;
+      v.x = kq[0]; v.y = kq[1]; v.z = kq[2]; v.w = kq[3];
+      ks[(j4 >> 2) * kstride] = v;
     }
-    // q = | L^-1 k |^2, row by row over the packed lower triangle (4 entries per broadcast load)
+    // q = | L^-1 k |^2, row by row over the packed lower triangle: one broadcast load of four matrix entries and
+    // one load of four kernel values per four FMAs, unrolled so that several loads are in flight
     T q = (T)0;
     const T* __restrict__ row = tri + (size_t)d * H.tri_stride;
     for (int i = 0; i < n; ++i) {
       const int len = (i + 4) & ~3;
-      T acc0 = (T)0, acc1 = (T)0;
+      T acc[4] = {(T)0, (T)0, (T)0, (T)0};
+#pragma unroll 4
       for (int j = 0; j < len; j += 4) {
-        T r[4], kk[4];
+        T r[4];
         load4(row + j, r);
-        load4(kst + j, kk);
-        acc0 = t_fma(r[0], kk[0], acc0);
-        acc1 = t_fma(r[1], kk[1], acc1);
-        acc0 = t_fma(r[2], kk[2], acc0);
-        acc1 = t_fma(r[3], kk[3], acc1);
+        const V4 kk = ks[(j >> 2) * kstride];
+        acc[0] = t_fma(r[0], kk.x, acc[0]);
+        acc[1] = t_fma(r[1], kk.y, acc[1]);
+        acc[2] = t_fma(r[2], kk.z, acc[2]);
+        acc[3] = t_fma(r[3], kk.w, acc[3]);
       }
-      const T w = acc0 + acc1;
+      const T w = (acc[0] + acc[1]) + (acc[2] + acc[3]);
       q = t_fma(w, w, q);
       row += len;
     }
@@ -123,7 +139,8 @@ struct GpModel<ModelMlp<NT, NX_, NU_, H1, H2>> {
   using Base = ModelMlp<NT, NX_, NU_, H1, H2>;
   static constexpr int NOUT = NX_;
   template <typename ST>
-  static __device__ __forceinline__ void predict(const NT* __restrict__ w, NT slope, const unsigned char* __restrict__ gp, const NT (&eps)[NOUT],
+  static __device__ __forceinline__ void predict(const NT* __restrict__ w, NT slope, const unsigned char* __restrict__ gp,
+                                                 typename GpVec4<NT>::type* __restrict__ ks, int kstride, const NT (&eps)[NOUT],
                                                  ST (&x)[NX_], const ST (&u)[NU_]) {
     NT in[1][NX_ + NU_];
 #pragma unroll
@@ -133,7 +150,7 @@ struct GpModel<ModelMlp<NT, NX_, NU_, H1, H2>> {
     NT dx[1][NX_];
     Base::Net::template eval<1>(w, in, dx, slope);
     NT delta[NX_];
-    gp_delta<NT, NX_ + NU_, NX_>(gp, in[0], eps, delta);
+    gp_delta<NT, NX_ + NU_, NX_>(gp, ks, kstride, in[0], eps, delta);
 #pragma unroll
     for (int i = 0; i < NX_; ++i) x[i] += (ST)(dx[0][i] + delta[i]);
   }
@@ -144,7 +161,8 @@ struct GpModel<ModelRex<NT, NX_, NU_, E1, E2, NZ, D1, D2, NV, C1, C2>> {
   using Base = ModelRex<NT, NX_, NU_, E1, E2, NZ, D1, D2, NV, C1, C2>;
   static constexpr int NOUT = NX_ > NV ? NX_ : NV;
   template <typename ST>
-  static __device__ __forceinline__ void predict(const NT* __restrict__ w, NT slope, const unsigned char* __restrict__ gp, const NT (&eps)[NOUT],
+  static __device__ __forceinline__ void predict(const NT* __restrict__ w, NT slope, const unsigned char* __restrict__ gp,
+                                                 typename GpVec4<NT>::type* __restrict__ ks, int kstride, const NT (&eps)[NOUT],
                                                  ST (&x)[NX_], const ST (&u)[NU_]) {
     const int space = reinterpret_cast<const GpHeader<NT>*>(gp)->space;
     NT in[1][NX_ + NU_];
@@ -161,7 +179,7 @@ struct GpModel<ModelRex<NT, NX_, NU_, E1, E2, NZ, D1, D2, NV, C1, C2>> {
         NT e[NV], delta[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) e[j] = eps[j];
-        gp_delta<NT, NZ, NV>(gp, z[0], e, delta);
+        gp_delta<NT, NZ, NV>(gp, ks, kstride, z[0], e, delta);
 #pragma unroll
         for (int j = 0; j < NV; ++j) v[0][j] += delta[j];
       }
@@ -183,7 +201,7 @@ struct GpModel<ModelRex<NT, NX_, NU_, E1, E2, NZ, D1, D2, NV, C1, C2>> {
       NT e[NX_], delta[NX_];
 #pragma unroll
       for (int i = 0; i < NX_; ++i) e[i] = eps[i];
-      gp_delta<NT, NX_ + NU_, NX_>(gp, in[0], e, delta);
+      gp_delta<NT, NX_ + NU_, NX_>(gp, ks, kstride, in[0], e, delta);
 #pragma unroll
       for (int i = 0; i < NX_; ++i) dx[i] += delta[i];
     }
@@ -194,7 +212,7 @@ struct GpModel<ModelRex<NT, NX_, NU_, E1, E2, NZ, D1, D2, NV, C1, C2>> {
 
 // ---- kernel ---------------------------------------------------------------------------------------------
 // One thread per (sample, replica).  A warp holds G = 32 / M samples; lanes G*M..31 mirror the last group and never
-// write.  Shared memory: the FMA-path image | shifted nominal sequence | GP block.
+// write.  Shared memory: the FMA-path image | shifted nominal sequence | GP block | per-thread kernel-vector scratch.
 template <class Model, typename NT, typename ST, typename CT>
 __global__ void __launch_bounds__(128) rollout_gp_kernel(const RolloutArgs a) {
   using GM = GpModel<Model>;
@@ -208,6 +226,7 @@ __global__ void __launch_bounds__(128) rollout_gp_kernel(const RolloutArgs a) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
   const int T = a.src.T;
   unsigned char* gp = smem_raw + L::bytes(T);
+  typename GpVec4<NT>::type* ks = reinterpret_cast<typename GpVec4<NT>::type*>(gp + a.gp_bytes) + tid;  // [j/4][thread] scratch
   {
     copy_image_async(smem_raw, a.image, (int)L::kU, tid, nthr);
     copy_image_async(gp, a.gp, a.gp_bytes, tid, nthr);
@@ -265,7 +284,7 @@ __global__ void __launch_bounds__(128) rollout_gp_kernel(const RolloutArgs a) {
 #pragma unroll
       for (int i = 0; i < NOUT; ++i) eps[i] = (NT)z[i];
     }
-    GM::template predict<ST>(w, slope, gp, eps, x, u);
+    GM::template predict<ST>(w, slope, gp, ks, nthr, eps, x, u);
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       if ((a.wrap_mask >> i) & 1u) x[i] = angle_normalize<ST>(x[i]);
@@ -303,7 +322,10 @@ __global__ void __launch_bounds__(128) rollout_gp_kernel(const RolloutArgs a) {
 template <class Model, typename NT, typename ST, typename CT>
 cudaError_t launch_rollout_gp(const RolloutArgs& a, int block, cudaStream_t stream) {
   auto kern = rollout_gp_kernel<Model, NT, ST, CT>;
-  const size_t smem = RolloutSmem<Model, NT, ST, CT>::bytes(a.src.T) + (size_t)a.gp_bytes;
+  const size_t fixed = RolloutSmem<Model, NT, ST, CT>::bytes(a.src.T) + (size_t)a.gp_bytes;
+  while (block > 32 && fixed + gp_scratch_bytes<NT>(block) > 227 * 1024) block >>= 1;  // float64 with many points: smaller CTAs
+  const size_t smem = fixed + gp_scratch_bytes<NT>(block);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -26,11 +26,45 @@ struct ReduceArgs {
 
 constexpr int kReduceThreads = 256;
 
+// Block-wide (min, lowest index) and sum with warp shuffles and one shared-memory hop: two barriers instead of one per
+// tree level.  The combination order is a function of the block shape only, so results are deterministic.
+__device__ __forceinline__ void warp_min_arg(double& b, long long& bi) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double o = __shfl_xor_sync(0xffffffffu, b, off);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, off);
+    if (o < b || (o == b && oi < bi)) { b = o; bi = oi; }
+  }
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+// s_b / s_i: one slot per warp (<= 32 warps).  Every thread returns the block's (min, argmin).
+__device__ __forceinline__ void block_min_arg(double& b, long long& bi, double* s_b, long long* s_i, int tid, int nthreads) {
+  warp_min_arg(b, bi);
+  if ((tid & 31) == 0) { s_b[tid >> 5] = b; s_i[tid >> 5] = bi; }
+  __syncthreads();
+  const int nw = nthreads >> 5;
+  b = (tid & 31) < nw ? s_b[tid & 31] : __longlong_as_double(0x7ff0000000000000ll);
+  bi = (tid & 31) < nw ? s_i[tid & 31] : 0x7fffffffffffffffll;
+  warp_min_arg(b, bi);
+  __syncthreads();  // the slots may be reused
+}
+__device__ __forceinline__ double block_sum(double v, double* s_b, int tid, int nthreads) {
+  v = warp_sum(v);
+  if ((tid & 31) == 0) s_b[tid >> 5] = v;
+  __syncthreads();
+  const int nw = nthreads >> 5;
+  v = warp_sum((tid & 31) < nw ? s_b[tid & 31] : 0.0);
+  __syncthreads();
+  return v;
+}
+
 template <int NU>
 __global__ void __launch_bounds__(kReduceThreads) partials_kernel(const ReduceArgs a) {
-  __shared__ double s_w[kReduceThreads];      // costs, then weights, of the chunk (chunk <= kReduceThreads)
-  __shared__ double s_red[kReduceThreads];
-  __shared__ int s_idx[kReduceThreads];
+  __shared__ double s_w[kReduceThreads];      // weights of the chunk (chunk <= kReduceThreads)
   __shared__ SamplerS<double> sp;
   __shared__ double Ush[TAMPC_MAX_HORIZON * kMaxNu];
   __shared__ double s_acc[kReduceThreads * NU];
@@ -45,32 +79,17 @@ __global__ void __launch_bounds__(kReduceThreads) partials_kernel(const ReduceAr
     Ush[t * kMaxNu + d] = ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d];
   }
   // ---- block min / argmin (lowest index wins ties, like torch.min / argmin over a 1-D tensor)
-  double c = tid < n ? a.cost[k0 + tid] : __longlong_as_double(0x7ff0000000000000ll);
-  s_w[tid] = c;
-  s_red[tid] = c;
-  s_idx[tid] = tid;
-  __syncthreads();
-  for (int off = kReduceThreads / 2; off > 0; off >>= 1) {
-    if (tid < off) {
-      double o = s_red[tid + off];
-      int oi = s_idx[tid + off];
-      if (o < s_red[tid] || (o == s_red[tid] && oi < s_idx[tid])) { s_red[tid] = o; s_idx[tid] = oi; }
-    }
-    __syncthreads();
-  }
-  const double beta = s_red[0];
-  const int amin = s_idx[0];
-  __syncthreads();
-  // ---- weights and their sum (fixed-order tree)
+  __shared__ double s_wb[32];
+  __shared__ long long s_wi[32];
+  const double c = tid < n ? a.cost[k0 + tid] : __longlong_as_double(0x7ff0000000000000ll);
+  double beta = c;
+  long long amin_ll = tid;
+  block_min_arg(beta, amin_ll, s_wb, s_wi, tid, kReduceThreads);
+  const int amin = (int)amin_ll;
+  // ---- weights and their sum
   const double w = tid < n ? exp(-a.sampler->lambda_inv * (c - beta)) : 0.0;
   s_w[tid] = w;
-  s_red[tid] = w;
-  __syncthreads();
-  for (int off = kReduceThreads / 2; off > 0; off >>= 1) {
-    if (tid < off) s_red[tid] += s_red[tid + off];
-    __syncthreads();
-  }
-  const double eta = s_red[0];
+  const double eta = block_sum(w, s_wb, tid, kReduceThreads);  // (its barriers also publish s_w, sp and Ush)
   // ---- weighted post-clamp noise: thread (t, g) sums samples g, g+G, ... of the chunk for step t  (T <= 128)
   const int G = kReduceThreads / T;
   if (tid < G * T) {
@@ -122,71 +141,63 @@ struct CombineArgs {
   unsigned long long seq;
 };
 
-constexpr int kCombineThreads = 512;  // also the largest group
+constexpr int kCombineThreads = 512;  // also the largest group; combine_body deals partials over 4 x 128 threads
+static_assert(kCombineThreads == 512 && TAMPC_MAX_HORIZON * TAMPC_MAX_NU <= 512, "combine_body's thread mapping");
 
 __device__ __forceinline__ void combine_body(const CombineArgs& a) {
-  __shared__ double s_beta[kCombineThreads];
   __shared__ double s_scale[kCombineThreads];
-  __shared__ double s_sum[kCombineThreads];
-  __shared__ long long s_arg[kCombineThreads];
-  __shared__ long long s_cnt[kCombineThreads];
+  __shared__ double s_wb[32];
+  __shared__ long long s_wi[32];
+  __shared__ double s_part[4][TAMPC_MAX_HORIZON * kMaxNu];
   const int tid = threadIdx.x;
   const int p0 = blockIdx.x * a.group;
   const int n = min(a.group, a.n_partials - p0);
   const tampc_partial* part = a.partials + p0;
   const double li = a.sampler->lambda_inv;
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
-  // ---- min / argmin over the group (lowest global sample index wins ties), fixed-shape tree
+  // ---- min / argmin over the group (lowest global sample index wins ties)
   const double my_beta = tid < n ? part[tid].beta : inf;
   const double my_eta = tid < n ? part[tid].eta : 0.0;
-  s_beta[tid] = my_beta;
-  s_arg[tid] = tid < n ? part[tid].argmin : 0x7fffffffffffffffll;
-  s_cnt[tid] = tid < n ? part[tid].count : 0;
-  __syncthreads();
-  for (int off = kCombineThreads / 2; off > 0; off >>= 1) {
-    if (tid < off) {
-      const double o = s_beta[tid + off];
-      const long long oi = s_arg[tid + off];
-      if (o < s_beta[tid] || (o == s_beta[tid] && oi < s_arg[tid])) { s_beta[tid] = o; s_arg[tid] = oi; }
-      s_cnt[tid] += s_cnt[tid + off];
-    }
-    __syncthreads();
-  }
-  const double beta = s_beta[0];
-  const long long arg = s_arg[0];
-  const long long cnt = s_cnt[0];
-  __syncthreads();
-  // ---- log-sum-exp rescale of every partial to the common minimum, normaliser by a fixed-shape tree
+  double beta = my_beta;
+  long long arg = tid < n ? part[tid].argmin : 0x7fffffffffffffffll;
+  block_min_arg(beta, arg, s_wb, s_wi, tid, kCombineThreads);
+  const long long cnt = (long long)block_sum(tid < n ? (double)part[tid].count : 0.0, s_wb, tid, kCombineThreads);
+  // ---- log-sum-exp rescale of every partial to the common minimum, and the normaliser
   const double sc = tid < n ? exp(-li * (my_beta - beta)) : 0.0;
   s_scale[tid] = sc;
-  s_sum[tid] = sc * my_eta;
-  __syncthreads();
-  for (int off = kCombineThreads / 2; off > 0; off >>= 1) {
-    if (tid < off) s_sum[tid] += s_sum[tid + off];
-    __syncthreads();
-  }
-  const double eta = s_sum[0];
-  // ---- weighted sums, one thread per (t, i), partials in index order
+  const double eta = block_sum(sc * my_eta, s_wb, tid, kCombineThreads);  // (its barriers also publish s_scale)
+  // ---- weighted sums.  Partial records are 4 KB apart, so each load is a separate L2 round trip: the partials are
+  // dealt over four thread groups (group q takes p = q, q+4, ...), eight loads in flight per thread, and the four
+  // group sums are added in group order.  Groups whose scales all underflowed are skipped.
   const int nw = a.T * a.nu;
-  for (int i = tid; i < nw; i += kCombineThreads) {
-    // partials in index order; their records are 4 KB apart, so the loads of eight partials are issued together
-    // before any is consumed.  Groups whose scales all underflowed are skipped; a zero scale in a live group adds 0.
-    double sum = 0.0;
-    for (int p0 = 0; p0 < n; p0 += 8) {
-      double sc[8];
-      bool any = false;
+  {
+    const int q = tid >> 7, i = tid & 127;  // kCombineThreads = 4 x 128
+    for (int i0 = i; i0 < nw; i0 += 128) {
+      double sum = 0.0;
+      for (int b0 = q; b0 < n; b0 += 32) {
+        double scq[8], v[8];
+        bool any = false;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        sc[q] = p0 + q < n ? s_scale[p0 + q] : 0.0;
-        any |= sc[q] != 0.0;
+        for (int e = 0; e < 8; ++e) {
+          const int p = b0 + 4 * e;
+          scq[e] = p < n ? s_scale[p] : 0.0;
+          any |= scq[e] != 0.0;
+        }
+        if (!any) continue;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int p = b0 + 4 * e;
+          v[e] = (p < n && scq[e] != 0.0) ? part[p].wsum[i0] : 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum = __fma_rn(scq[e], v[e], sum);
       }
-      if (!any) continue;
-      double v[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = p0 + q < n ? part[p0 + q].wsum[i] : 0.0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) sum = __fma_rn(sc[q], v[q], sum);
+      s_part[q][i0] = sum;
     }
+  }
+  __syncthreads();
+  for (int i = tid; i < nw; i += kCombineThreads) {
+    const double sum = ((s_part[0][i] + s_part[1][i]) + s_part[2][i]) + s_part[3][i];
     if (a.finalize) {
       const int t = i / a.nu, d = i % a.nu, ts = t + 1;
       const double base = ts < a.T ? a.U[ts * a.nu + d] : a.sampler->u_init[d];
