@@ -560,9 +560,9 @@ int apply_gp_args(tampc_mppi* h, RolloutArgs& a, int T) {
   a.M = h->gp.rollout_samples;
   a.var_cost = h->gp.rollout_var_cost;
   a.var_discount = h->gp.rollout_var_discount;
-  // get_rollouts / predict are sampled too in the reference (they go through the same dynamics): a Philox stream
+  // get_rollouts / predict / rollout_costs of given actions are sampled too in the reference (they go through the same dynamics): a Philox stream
   // of their own, advanced per call
-  if (a.src.mode == kModeNominal) a.src.call = (1ull << 62) + h->gp_aux_calls++;
+  if (a.src.mode == kModeNominal || a.src.mode == kModeActions) a.src.call = (1ull << 62) + h->gp_aux_calls++;
   if (h->gp_eps_armed) {
     if (T != h->gp_eps_T) { h->err = "the injected GP draws were sized for another horizon"; return TAMPC_ERR_INVALID; }
     a.gp_eps = h->d_gp_eps;

@@ -128,6 +128,27 @@ class B200MPPI:
         obj.terminal_state_cost = old.terminal_state_cost
         return obj
 
+    @classmethod
+    def from_package(cls, path, **kwargs):
+        """Build from a packaged spec written by `tampc_b200.spec.save_spec`: no datasets, no scaler
+        fitting and none of the reference's un-vendored libraries are needed at start-up."""
+        return cls(S.load_spec(path), **kwargs)
+
+    @classmethod
+    def for_one_step(cls, ctrl, samples, **kwargs):
+        """A handle for the one-step action samplers of the APF baselines (APFVO / APFSP, online_controller.py:554-664)
+        and anything else that pushes `samples` candidate actions through `ctrl._apply_dynamics` from one state: the
+        dynamics of `ctrl`, K = samples, horizon 1.  Use `apply_dynamics`."""
+        dyn = extract.dynamics_from_controller(ctrl)
+        nx, nu = dyn.nx, dyn.nu
+        cost = S.CostSpec(kind=S.COST_GOAL_TRAP, nx=nx, nu=nu, Q=np.zeros((nx, nx)), R=np.zeros((nu, nu)), goal=np.zeros(nx),
+                          use_trap_cost=False)
+        u_min = None if getattr(ctrl, 'u_min', None) is None else extract._np(ctrl.u_min)
+        u_max = None if getattr(ctrl, 'u_max', None) is None else extract._np(ctrl.u_max)
+        sampler = S.SamplerSpec(K=int(samples), T=1, nu=nu, lambda_=1.0, noise_mu=np.zeros(nu), noise_sigma=np.eye(nu),
+                                u_min=u_min, u_max=u_max)
+        return cls(S.RolloutSpec(dyn, cost, sampler, name='one_step'), U_init=torch.zeros(1, nu, dtype=torch.double), **kwargs)
+
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc):
         if rc != L.OK:
@@ -354,6 +375,24 @@ class B200MPPI:
         out = np.empty(self.nx)
         self._check(self._lib.tampc_mppi_predict(self._h, L.dptr(x), L.dptr(u), L.dptr(out)))
         return out.reshape(1, -1)
+
+    def apply_dynamics(self, state, actions):
+        """OnlineMPC._apply_dynamics(state.repeat(N, 1), actions) (online_controller.py:60-79) for N candidate actions
+        from ONE state, in one fused launch per K_local actions: bad-state guard, network (+ GP residual), constrain_state.
+        This is the heavy step of the APF baselines' samplers (online_controller.py:583-590, 657-664).  Returns (N, nx)."""
+        a = torch.as_tensor(actions).detach().to('cpu', torch.double).numpy().reshape(-1, self.nu)
+        x = self._state_array(state)
+        N = a.shape[0]
+        out = np.empty((N, self.nx))
+        cost = np.empty(self.K_local)
+        states = np.empty((self.K_local, 1, self.nx))
+        for lo in range(0, N, self.K_local):
+            chunk = a[lo:lo + self.K_local]
+            buf = np.zeros((self.K_local, 1, self.nu))
+            buf[:len(chunk), 0] = chunk
+            self._check(self._lib.tampc_mppi_rollout_costs(self._h, L.dptr(x), L.dptr(buf), 1, L.dptr(cost), L.dptr(states)))
+            out[lo:lo + len(chunk)] = states[:len(chunk), 0]
+        return torch.from_numpy(out)
 
     def _compute_rollout_costs(self, perturbed_actions, state=None):
         """ExperimentalMPPI._compute_rollout_costs (controller.py:340-381): (cost_total (K,), states (M,K,T,nx),

@@ -435,3 +435,27 @@ def spec_from_arrays(arrays, prefix='spec.'):
                           rollout_var_cost=float(d['mppi.rollout_var_cost']),
                           rollout_var_discount=float(d['mppi.rollout_var_discount']))
     return RolloutSpec(dyn, cost, sampler, name=str(d['name']))
+
+
+# ------------------------------------------------------------------------------------------------
+# packaged specs: the extracted problem — network weights, FITTED scaler vectors, env tags, cost
+# program, sampler constants — in one .npz beside the reference's checkpoint, so that a controller can start without
+# re-fitting the RobustMinMaxScalers from the .mat datasets (tampc/util.py:408-415) and without the un-vendored
+# preprocess library on the runtime path.  The reference's own checkpoint format is untouched.
+
+PACKAGE_FORMAT = 1
+
+
+def save_spec(path, spec: RolloutSpec):
+    arrays = spec_to_arrays(spec)
+    arrays['package.format'] = np.array(PACKAGE_FORMAT)
+    np.savez_compressed(path, **arrays)
+
+
+def load_spec(path) -> RolloutSpec:
+    with np.load(path) as z:
+        if 'package.format' not in z.files:
+            raise ValueError("{} is not a packaged RolloutSpec".format(path))
+        if int(z['package.format']) != PACKAGE_FORMAT:
+            raise ValueError("packaged spec format {} != {}".format(int(z['package.format']), PACKAGE_FORMAT))
+        return spec_from_arrays({k: z[k] for k in z.files})

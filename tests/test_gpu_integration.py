@@ -115,3 +115,53 @@ def test_online_gp_is_followed_when_the_nominal_model_is_swapped(cuda_lib, case)
     mpc.command(torch.from_numpy(z['in.state']), noise=z['in.noise'])
     np.testing.assert_array_equal(mpc.cost_total.numpy(), cost_nominal)
     mpc.close()
+
+
+def test_packaged_spec_starts_a_controller_without_the_datasets(cuda_lib, tmp_path):
+    """B200MPPI.from_package reproduces the reference outputs from the .npz alone."""
+    from tampc_b200 import spec as S
+    from tampc_b200.mppi import B200MPPI
+    z, spec = load_golden('peg_nominal')
+    path = str(tmp_path / 'peg.spec.npz')
+    S.save_spec(path, spec)
+    m = B200MPPI.from_package(path, precision='f64', U_init=torch.from_numpy(z['in.U']))
+    action = m.command(z['in.state'], noise=z['in.noise']).numpy()
+    np.testing.assert_allclose(action, z['ref.action'], rtol=0, atol=1e-8)
+    assert m.stats['argmin'] == int(z['ref.argmin'])
+    m.close()
+
+
+@pytest.mark.parametrize('case,precision', [('push_nominal', 'f64'), ('peg_nominal', 'tf32x3'), ('push_gp_local', 'f64')])
+def test_one_step_sampler_of_the_apf_baselines(cuda_lib, case, precision):
+    """APFVO / APFSP push 5000 uniformly sampled actions through _apply_dynamics from the current state and take the
+    argmin of a potential (online_controller.py:583-590, 657-664): the dynamics step runs in the fused kernel."""
+    from oracle import mppi_oracle as O
+    from tampc_b200.mppi import B200MPPI
+    z, spec = load_golden(case)
+    if spec.dynamics.gp is not None:
+        spec.dynamics.gp.sample = False  # the posterior mean: comparable without injecting draws
+        spec.sampler.rollout_samples = 1
+    ctrl = fake_tampc.make_controller(spec, z['in.U'])
+    if spec.dynamics.gp is not None:
+        ctrl.dynamics.nominal_model = fake_tampc.make_online_gp(spec, ctrl.dynamics.nominal_model)
+    ctrl.u_min, ctrl.u_max = torch.from_numpy(spec.sampler.u_min), torch.from_numpy(spec.sampler.u_max)
+    m = B200MPPI.for_one_step(ctrl, samples=5000, precision=precision)
+    g = torch.Generator().manual_seed(0)
+    u = torch.rand(5000, spec.dynamics.nu, dtype=torch.double, generator=g) * (ctrl.u_max - ctrl.u_min) + ctrl.u_min
+    x = torch.from_numpy(z['in.state'])
+    got = m.apply_dynamics(x, u)
+    want, _ = O.apply_dynamics(spec.dynamics, x.view(1, -1).repeat(5000, 1), u)
+    # float32 networks: the reaction-force dims are O(10) and un-scaled by 1/0.12 (float32 state ulp there is 1e-6)
+    tol = 1e-10 if precision == 'f64' else 1e-4
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=tol, atol=tol)
+    # the sampler's decision: argmin of a potential over the next states (here the goal cost, cost.py:11-18)
+    goal = torch.from_numpy(spec.cost.goal if spec.cost.kind == 0 else np.zeros(spec.dynamics.nx))
+    pot = lambda s: ((s - goal)[:, :2] ** 2).sum(dim=1)
+    assert int(pot(got).argmin()) == int(pot(want).argmin())
+    # fewer actions than the handle's K, and a bad start state (guard: rows come back as zeros)
+    got7 = m.apply_dynamics(x, u[:7])
+    np.testing.assert_allclose(got7.numpy(), want[:7].numpy(), rtol=tol, atol=tol)
+    if spec.dynamics.bad_state_norm is not None:
+        bad = m.apply_dynamics(torch.full((spec.dynamics.nx,), 1e6, dtype=torch.double), u[:3])
+        assert torch.all(bad == 0)
+    m.close()

@@ -71,3 +71,18 @@ def test_spec_roundtrip_through_arrays():
 def test_macs_per_step_match_survey():
     assert load_golden('push_nominal')[1].dynamics.macs_per_step == 3523
     assert load_golden('peg_nominal')[1].dynamics.macs_per_step == 3507
+
+
+def test_packaged_spec_roundtrip(tmp_path):
+    """a RolloutSpec saved beside the reference checkpoint reloads to the same problem."""
+    for case in ('push_nominal', 'push_recovery', 'pendulum', 'push_gp_local'):
+        z, spec = load_golden(case)
+        path = str(tmp_path / (case + '.spec.npz'))
+        S.save_spec(path, spec)
+        again = S.load_spec(path)
+        a, b = S.spec_to_arrays(spec), S.spec_to_arrays(again)
+        assert a.keys() == b.keys()
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k])
+    with pytest.raises(ValueError):
+        S.load_spec(str(__import__('os').path.join(__import__('conftest').GOLDEN_DIR, 'push_nominal.npz')))  # not a package
