@@ -38,15 +38,17 @@ def test_every_declared_symbol_is_exported(lib):
 def test_ctypes_structs_match_the_c_layout(tmp_path):
     prog = tmp_path / 'sizes.c'
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "tampc_mppi.h"\nint main(void){'
-                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(tampc_mlp_desc), sizeof(tampc_model_desc),'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(tampc_mlp_desc), sizeof(tampc_model_desc),'
                     'sizeof(tampc_cost_desc), sizeof(tampc_mppi_config), sizeof(tampc_partial),'
-                    'offsetof(tampc_cost_desc, set_goals), offsetof(tampc_model_desc, pendulum), offsetof(tampc_mppi_config, seed));return 0;}')
+                    'offsetof(tampc_cost_desc, set_goals), offsetof(tampc_model_desc, pendulum), offsetof(tampc_mppi_config, seed),'
+                    'sizeof(tampc_gp_desc), offsetof(tampc_gp_desc, lengthscale), offsetof(tampc_gp_desc, rollout_var_cost));return 0;}')
     exe = tmp_path / 'sizes'
     subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(prog), '-o', str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(_lib.MlpDesc), C.sizeof(_lib.ModelDesc), C.sizeof(_lib.CostDesc), C.sizeof(_lib.MppiConfig),
             C.sizeof(_lib.Partial), _lib.CostDesc.set_goals.offset, _lib.ModelDesc.pendulum.offset,
-            _lib.MppiConfig.seed.offset]
+            _lib.MppiConfig.seed.offset, C.sizeof(_lib.GpDesc), _lib.GpDesc.lengthscale.offset,
+            _lib.GpDesc.rollout_var_cost.offset]
     assert got == want
 
 

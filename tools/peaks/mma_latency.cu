@@ -38,6 +38,6 @@ template <int NACC> void run(float* out, long long* cyc, int warps) {
 }
 int main() {
   float* out; long long* cyc; cudaMalloc(&out, 4); cudaMalloc(&cyc, 8);
-  for (int warps : {4, 8}) { run<1>(out, cyc, warps); run<2>(out, cyc, warps); run<3>(out, cyc, warps); run<4>(out, cyc, warps); run<6>(out, cyc, warps); run<8>(out, cyc, warps); run<12>(out, cyc, warps); }
+  for (int warps : {4}) {  // the kernel is bounded to 128 threads: one warp per sub-partition run<1>(out, cyc, warps); run<2>(out, cyc, warps); run<3>(out, cyc, warps); run<4>(out, cyc, warps); run<6>(out, cyc, warps); run<8>(out, cyc, warps); run<12>(out, cyc, warps); }
   return 0;
 }
