@@ -267,7 +267,7 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
   const int nx = d.nx, nu = d.nu;
   if (nx != h->cfg.nx || nu != h->cfg.nu) { h->err = "model nx/nu differ from the handle's"; return TAMPC_ERR_INVALID; }
   if (!(d.leaky_slope >= 0.0 && d.leaky_slope <= 1.0)) { h->err = "leaky_slope must be in [0,1]"; return TAMPC_ERR_UNSUPPORTED; }
-  const ModelVariant* all[] = {variant_rex_push(), variant_rex_peg(), variant_mlp_5_3_32(), variant_mlp_5_3_64(), variant_mlp_5_3_128(),
+  const ModelVariant* all[] = {variant_rex_push(), variant_rex_peg(), variant_mlp_5_3_32(), variant_mlp_5_3_64(), variant_mlp_5_3_128(), variant_mlp_5_3_256(),
                                variant_pendulum()};
   char buf[256];
   if (d.kind == TAMPC_DYN_PENDULUM) {
@@ -309,10 +309,8 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
       pack_mlp<float>(out.f32, net);
       pack_mlp<double>(out.f64, net);
     }
-    if (out.variant->bytes_mma_f64) {
-      pack_mlp_mma(out.mma_f64, net, 1, true);
-      pack_mlp_mma(out.mma_tf32, net, 1, false);
-    }
+    if (out.variant->bytes_mma_f64) pack_mlp_mma(out.mma_f64, net, 1, true);
+    if (out.variant->bytes_mma_tf32) pack_mlp_mma(out.mma_tf32, net, 1, false);
     return TAMPC_OK;
   }
   if (d.kind != TAMPC_DYN_REX) { h->err = "unknown dynamics kind"; return TAMPC_ERR_INVALID; }
@@ -964,7 +962,7 @@ static int install_model(tampc_mppi* h, const tampc_model_desc* desc, const doub
     use_mma = true;
   }
   if (!use_mma && !pm.variant->f64_s1) {
-    h->err = std::string(pm.variant->name) + " has tensor-core kernels only: use precision f64 or tf32x3";
+    h->err = std::string(pm.variant->name) + " has tensor-core kernels only: use precision tf32x3" + (pm.variant->bytes_mma_f64 ? " or f64" : "");
     return TAMPC_ERR_UNSUPPORTED;
   }
   const void* src;
