@@ -36,12 +36,34 @@ TF32_MMA_PEAK_TFLOPS = 278.0  # tools/peaks/mma_peaks mma.sync m16n8k8 tf32
 NCU_DRAM_BYTES_PER_LAUNCH = {'tf32x3': 82688}
 
 
-def load_push_spec(K):
+# The driver's line is the default workload (BASELINE.json configs[1]).  The others exist to put the remaining configs
+# on record with the same harness (profiles/): configs[2] peg, configs[0] pendulum, configs[3]/[4] the synthetic sweep's
+# 1M-sample points, sharded over the GPUs (strong scaling: K is the total).
+WORKLOADS = {
+    'push': dict(golden='push_nominal', K_per_gpu=K_PER_GPU, name='push_rex_extract_K8192_T40_P3'),
+    'peg': dict(golden='peg_nominal', K_per_gpu=32768, name='peg_rex_extract_K32768_T10_P4'),
+    'pendulum': dict(golden='pendulum', K_per_gpu=100, name='pendulum_analytic_K100_T15'),
+    'synth_h32': dict(synthetic=32, K_total=1 << 20, name='synthetic_mlp_H32_K1M_T40_P3'),
+    'synth_h256': dict(synthetic=256, K_total=1 << 20, name='synthetic_mlp_H256_K1M_T40_P3'),
+}
+
+
+def load_spec(workload, world, K=None):
+    """(arrays with in.state / in.U, RolloutSpec) of a workload at `world` GPUs (K overrides the sample count)."""
     from tampc_b200 import spec as S
-    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'push_nominal.npz'))
+    w = WORKLOADS[workload]
+    if 'synthetic' in w:
+        from tampc_b200.synthetic import make_synthetic_spec
+        spec, x0 = make_synthetic_spec(H=w['synthetic'], K=K or w['K_total'], T=40)
+        return {'in.state': x0, 'in.U': np.zeros((40, 3))}, spec
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', w['golden'] + '.npz'))
     spec = S.spec_from_arrays(z)
-    spec.sampler.K = K
+    spec.sampler.K = K or w['K_per_gpu'] * world
     return z, spec
+
+
+def load_push_spec(K):
+    return load_spec('push', 1, K)
 
 
 class ClockSampler:
@@ -92,6 +114,12 @@ def cpu_reference_step(spec, z, state, U, seed):
     return time.perf_counter() - t0
 
 
+def cpu_sample_K(workload):
+    """Sample count of one CPU command: the workload's own K per GPU, bounded so that a command stays ~0.1-0.5 s."""
+    w = WORKLOADS[workload]
+    return min(w.get('K_per_gpu', 8192), 32768)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU torch path (oracle port: /root/reference does not exist on the GPU box),
     float64, all host threads, same config/metric; each step is one full K=8192 command."""
@@ -99,23 +127,24 @@ def run_reference(args, rank, world):
         return
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
-    z, spec = load_push_spec(K_PER_GPU)
+    Kc = cpu_sample_K(args.workload)
+    z, spec = load_spec(args.workload, 1, Kc)
     state, U = z['in.state'].copy(), torch.from_numpy(z['in.U'].copy())
     for i in range(args.warmup):
         cpu_reference_step(spec, z, state, U, 100 + i)
     times = [cpu_reference_step(spec, z, state, U, 200 + i) for i in range(args.steps)]
     T = spec.sampler.T
     ms = 1e3 * float(np.mean(times))
-    val = K_PER_GPU * T / (ms * 1e-3)
+    val = Kc * T / (ms * 1e-3)
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "push_rex_extract_K8192_T40_P3", "K": K_PER_GPU, "T": T, "rollout_replicas_M": 1,
+        "config": {"workload": WORKLOADS[args.workload]['name'], "K": Kc, "T": T, "rollout_replicas_M": 1,
                    "note": "deterministic dynamics: one replica; the reference scripts run M=10 identical replicas"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "{} full commands of K={} T={} (oracle/mppi_oracle.py, torch float64)".format(args.steps, K_PER_GPU, T)},
+                         "sample": "{} full commands of K={} T={} (oracle/mppi_oracle.py, torch float64)".format(args.steps, Kc, T)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "latency_ms_p50": 1e3 * float(np.median(times)), "gpu_launches": 0,
     }
@@ -130,6 +159,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('TAMPC_BENCH_PRECISION', 'tf32x3'))
     ap.add_argument('--cpu-steps', type=int, default=12, help='commands of the CPU baseline sample')
+    ap.add_argument('--workload', default='push', choices=sorted(WORKLOADS))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get('RANK', '0'))
@@ -149,12 +179,13 @@ def main():
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    K = K_PER_GPU * world
-    z, spec = load_push_spec(K)
+    z, spec = load_spec(args.workload, world)
+    K = spec.sampler.K
+    strong = 'K_total' in WORKLOADS[args.workload]
     T = spec.sampler.T
     state = z['in.state'].copy()
     mppi = B200MPPI(spec, precision=args.precision, device=local_rank, rank=rank, world_size=world, seed=1234,
-                    U_init=torch.from_numpy(z['in.U'].copy()), use_torch_stream=True)
+                    U_init=torch.from_numpy(np.asarray(z['in.U']).copy()), use_torch_stream=True, max_horizon=max(T, 64))
     stream = mppi.torch_stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')  # > 126 MB L2
 
@@ -254,7 +285,10 @@ def main():
             # the kernel is compute-bound (it moves ~100 KB of DRAM traffic per launch); which pipe bounds it
             # depends on the arithmetic: every peak below was measured on this pool's B200 with tools/peaks
             # (MEASURED_PEAKS.json holds only the HBM copy and the cuBLAS bf16 tcgen05 GEMM)
-            if args.precision == 'tf32x3':
+            if spec.dynamics.kind == 2:  # analytic pendulum: no network layers, scalar FP32/FP64 arithmetic only
+                bound, peak = "fp32_fma", FP32_PEAK_TFLOPS
+                src = "FFMA2 register-operand peak measured (profiles/fma_peaks_r1.jsonl); ~20 FLOP + 1 sin per sample-step"
+            elif args.precision == 'tf32x3':
                 bound, peak = "tensor", TF32_MMA_PEAK_TFLOPS / 3.0
                 src = ("mma.sync m16n8k8 tf32 measured {:.0f} TFLOP/s (profiles/mma_peaks_r1.jsonl) / 3 products per "
                        "algorithmic MAC (error-compensated 3xTF32 split)").format(TF32_MMA_PEAK_TFLOPS)
@@ -265,7 +299,8 @@ def main():
                 bound, peak = "fp32_fma", FP32_PEAK_TFLOPS
                 src = "FFMA2 register-operand peak measured (profiles/fma_peaks_r1.jsonl)"
             roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                        "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.precision),
+                        "frac": achieved / peak,
+                        "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.precision) if args.workload == 'push' else None,
                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, one "
                                           "ncu --set full capture (profiles/r1c_rollout_split_tf32x3_k8192_ncu_summary.txt)",
                         "kernel": "rollout (fused K x T): rollout_mma_split_kernel at this K (two warps per 16-sample "
@@ -274,18 +309,19 @@ def main():
                         "peak_source": src}
         # CPU baseline: bounded sample of the same workload on the host cores (oracle port, float64)
         torch.set_num_threads(os.cpu_count() or 1)
-        zc, spec_c = load_push_spec(K_PER_GPU)
-        Uc = torch.from_numpy(z['in.U'].copy())
+        Kc = cpu_sample_K(args.workload)
+        zc, spec_c = load_spec(args.workload, 1, Kc)
+        Uc = torch.from_numpy(np.asarray(z['in.U']).copy())
         cpu_reference_step(spec_c, zc, state, Uc, 1)
         cpu_t = [cpu_reference_step(spec_c, zc, state, Uc, 2 + i) for i in range(args.cpu_steps)]
-        cpu_val = K_PER_GPU * T / float(np.mean(cpu_t))
+        cpu_val = Kc * T / float(np.mean(cpu_t))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": {"f64": "f64", "mixed": "f32 networks, f64 state+cost", "f32": "f32",
                       "tf32x3": "3xTF32 (f32-equivalent) networks, f32 state, f64 cost sum"}.get(args.precision, args.precision),
             "data": "synthetic",
-            "config": {"workload": "push_rex_extract_K8192_T40_P3", "K_per_gpu": K_PER_GPU, "K": K, "T": T,
+            "config": {"workload": WORKLOADS[args.workload]['name'], "K_per_gpu": mppi.K_local, "K": K, "T": T,
                        "precision": args.precision, "noise": "on-device Philox4x32-10", "rollout_replicas_M": 1,
                        "l2": "flushed between timed steps (256 MiB memset on the same stream, outside the events)",
                        "parallelism": "samples sharded over {} GPU(s)".format(world)},
@@ -297,7 +333,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "{} commands of K={} T={} (oracle/mppi_oracle.py, torch float64, M=1)".format(
-                                 args.cpu_steps, K_PER_GPU, T)},
+                                 args.cpu_steps, Kc, T)},
             "wall_s_timed_region": wall,
         }
         print(json.dumps(line), flush=True)
