@@ -31,6 +31,7 @@ UNIT = "sample-steps/s"
 FP32_PEAK_TFLOPS = 74.1  # tools/peaks/fma_peaks ffma2_reg on this pool's B200 (profiles/fma_peaks_r1.jsonl)
 FP64_TENSOR_PEAK_TFLOPS = 37.1  # tools/peaks/mma_peaks dmma (profiles/mma_peaks_r1.jsonl)
 TF32_MMA_PEAK_TFLOPS = 278.0  # tools/peaks/mma_peaks mma.sync m16n8k8 tf32
+F16_MMA_PEAK_TFLOPS = 556.0  # tools/peaks/mma_peaks mma.sync m16n8k16 f16
 # DRAM traffic of one rollout launch at K=8192 from the committed ncu capture (the kernel reads its ~45 KB image and
 # the nominal sequence, writes 8*K bytes of costs that stay in L2): compute-bound by four orders of magnitude
 NCU_DRAM_BYTES_PER_LAUNCH = {'tf32x3': 82688}
@@ -292,6 +293,10 @@ def main():
                 bound, peak = "tensor", TF32_MMA_PEAK_TFLOPS / 3.0
                 src = ("mma.sync m16n8k8 tf32 measured {:.0f} TFLOP/s (profiles/mma_peaks_r1.jsonl) / 3 products per "
                        "algorithmic MAC (error-compensated 3xTF32 split)").format(TF32_MMA_PEAK_TFLOPS)
+            elif args.precision == 'f16x3':
+                bound, peak = "tensor", F16_MMA_PEAK_TFLOPS / 3.0
+                src = ("mma.sync m16n8k16 f16 measured {:.0f} TFLOP/s (profiles/mma_peaks_r1.jsonl) / 3 products per "
+                       "algorithmic MAC (error-compensated 3xFP16 split)").format(F16_MMA_PEAK_TFLOPS)
             elif args.precision == 'f64':
                 bound, peak = "tensor", FP64_TENSOR_PEAK_TFLOPS
                 src = "mma.sync m8n8k4 f64 (DMMA) measured (profiles/mma_peaks_r1.jsonl)"
@@ -319,7 +324,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": {"f64": "f64", "mixed": "f32 networks, f64 state+cost", "f32": "f32",
-                      "tf32x3": "3xTF32 (f32-equivalent) networks, f32 state, f64 cost sum"}.get(args.precision, args.precision),
+                      "tf32x3": "3xTF32 (f32-equivalent) networks, f32 state, f64 cost sum",
+                      "f16x3": "3xFP16 (f32-equivalent) networks, f32 state, f64 cost sum"}.get(args.precision, args.precision),
             "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload]['name'], "K_per_gpu": mppi.K_local, "K": K, "T": T,
                        "precision": args.precision, "noise": "on-device Philox4x32-10", "rollout_replicas_M": 1,

@@ -66,8 +66,11 @@ typedef enum tampc_precision {
                            network layers run on the FP64 tensor pipe (DMMA) where the shape has an mma kernel */
   TAMPC_PREC_MIXED = 1, /* networks in float32 (packed FFMA2), state + cost accumulation in float64 */
   TAMPC_PREC_F32 = 2,   /* everything in float32 */
-  TAMPC_PREC_TF32X3 = 3 /* networks on the tensor cores as 3xTF32 (error-compensated split, ~float32 accuracy),
-                           state and cost terms in float32, cost accumulated in float64 */
+  TAMPC_PREC_TF32X3 = 3, /* networks on the tensor cores as 3xTF32 (error-compensated split, ~float32 accuracy),
+                            state and cost terms in float32, cost accumulated in float64 */
+  TAMPC_PREC_F16X3 = 4   /* the same split on the fp16 tensor path (mma.sync.m16n8k16: 11 significant bits like TF32,
+                            half the tensor instructions); low parts carried scaled by 2^11, high parts saturate at
+                            65504.  Shapes with resident-weight tensor kernels only */
 } tampc_precision;
 
 /* where the per-sample action perturbations come from */

@@ -14,8 +14,8 @@ GP_MAX_POINTS, GP_MAX_DIM, MAX_ROLLOUT_SAMPLES = 64, 8, 32
 ABI_VERSION = 1
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
-PREC_F64, PREC_MIXED, PREC_F32, PREC_TF32X3 = 0, 1, 2, 3
-PRECISIONS = {'f64': PREC_F64, 'mixed': PREC_MIXED, 'f32': PREC_F32, 'tf32x3': PREC_TF32X3}
+PREC_F64, PREC_MIXED, PREC_F32, PREC_TF32X3, PREC_F16X3 = 0, 1, 2, 3, 4
+PRECISIONS = {'f64': PREC_F64, 'mixed': PREC_MIXED, 'f32': PREC_F32, 'tf32x3': PREC_TF32X3, 'f16x3': PREC_F16X3}
 NOISE_PHILOX, NOISE_INJECTED, NOISE_ACTIONS = 0, 1, 2
 Q_COST_TOTAL, Q_PERTURBED, Q_NOMINAL, Q_OMEGA, Q_STATS, Q_STATES = 0, 1, 2, 3, 4, 5
 

@@ -18,6 +18,7 @@
 #pragma once
 #include "rollout_kernel.cuh"
 #include "fused_reduce.cuh"
+#include <type_traits>
 
 namespace tampc {
 
@@ -48,6 +49,40 @@ struct PolicyTF32x3 {
   static constexpr int kBlockBytes = 512;
 };
 
+// 3xFP16: the same error-compensated split on mma.sync.m16n8k16.f16 — fp16 carries the same 11 significant bits as TF32
+// but one instruction covers k = 16, so a layer needs half the tensor instructions (192 -> 108 per 16-sample step for the
+// RexExtract shapes).  The low parts would fall into fp16's subnormal range (|lo| <= 2^-11 |a|), so both A_lo and B_lo
+// are carried scaled by 2^11 and their products go to a second accumulator that is folded in with 2^-11 at the end:
+//   out = bias + sum A_hi B_hi + 2^-11 sum (A_lo' B_hi + A_hi B_lo').
+// High parts saturate at fp16's largest finite value (65504): inputs beyond it — only diverged rollouts just below the
+// 1e5 bad-state guard — lose accuracy instead of turning into NaN.
+struct PolicyF16x3 {
+  using T = float;
+  static constexpr int MT = 16;
+  static constexpr int R = 4;
+  static constexpr int PROD = 3;
+  static constexpr int kBlockBytes = 512;  // one (k16, n8) block: 32 lanes x {b0hi, b1hi, b0lo', b1lo'} half2 pairs
+};
+constexpr float kF16LoScale = 2048.f, kF16LoUnscale = 1.f / 2048.f;
+
+__device__ __forceinline__ void mma16816_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, float c0, float c1, float c2, float c3) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
+}
+// {x -> low half, y -> high half}, round to nearest, saturating
+__device__ __forceinline__ uint32_t pack_half2_sat(float x, float y) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(y), "f"(x));
+  return r;
+}
+// (hi, lo') of the pair (x, y): hi = the top 11 significant bits (exact in fp16 within its range), lo' = (v - hi) * 2^11
+__device__ __forceinline__ void split_half2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const float hx = __uint_as_float(__float_as_uint(x) & 0xffffe000u), hy = __uint_as_float(__float_as_uint(y) & 0xffffe000u);
+  hi = pack_half2_sat(hx, hy);
+  lo = pack_half2_sat((x - hx) * kF16LoScale, (y - hy) * kF16LoScale);
+}
+
 // d = a*b + c with separate c (first product of an accumulation chain: c = bias or zero)
 __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b, double c0, double c1) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};" : "=d"(d[0]), "=d"(d[1]) : "d"(a), "d"(b), "d"(c0), "d"(c1));
@@ -62,6 +97,65 @@ __device__ __forceinline__ void mma1688_tf32(float (&d)[4], const uint32_t (&a)[
 template <class P> __host__ __device__ constexpr int mma_layer_bytes(int in8, int out8) {
   return out8 * 8 * (int)sizeof(typename P::T) + in8 * out8 * P::kBlockBytes;
 }
+// fp16: one block per (16 input features, 8 outputs); an odd number of 8-feature input blocks is zero-padded
+template <> __host__ __device__ constexpr int mma_layer_bytes<PolicyF16x3>(int in8, int out8) {
+  return out8 * 8 * (int)sizeof(float) + ((in8 + 1) / 2) * out8 * PolicyF16x3::kBlockBytes;
+}
+
+// 3xFP16 layer: in / out in the accumulator layout (lane (g,t): features 8n+2t, 8n+2t+1 of rows g and g+8), which
+// is also the m16n8k16 A-fragment layout of two consecutive 8-feature blocks — no data movement between layers.
+template <int NM, int IN8, int OUT8, bool ACT>
+__device__ __forceinline__ void mma_layer_f16(const float (&in)[NM][IN8][4], float (&out)[NM][OUT8][4], const unsigned char* __restrict__ wl,
+                                              float slope, int lane) {
+  constexpr int IN16 = (IN8 + 1) / 2;
+  const int t = lane & 3;
+  const float* bias = reinterpret_cast<const float*>(wl);
+  const unsigned char* blocks = wl + OUT8 * 8 * sizeof(float);
+  float accm[NM][OUT8][4], accx[NM][OUT8][4];
+  float b0[OUT8], b1[OUT8];
+#pragma unroll
+  for (int o = 0; o < OUT8; ++o) { b0[o] = bias[o * 8 + 2 * t]; b1[o] = bias[o * 8 + 2 * t + 1]; }
+#pragma unroll
+  for (int k = 0; k < IN16; ++k) {
+    uint32_t ahi[NM][4], alo[NM][4];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      // a0 = (row g; k 2t,2t+1)  a1 = (row g+8; same k)  a2 = (row g; k 2t+8,2t+9)  a3 = (row g+8; same)
+      split_half2(in[m][2 * k][0], in[m][2 * k][1], ahi[m][0], alo[m][0]);
+      split_half2(in[m][2 * k][2], in[m][2 * k][3], ahi[m][1], alo[m][1]);
+      if (2 * k + 1 < IN8) {
+        split_half2(in[m][2 * k + 1][0], in[m][2 * k + 1][1], ahi[m][2], alo[m][2]);
+        split_half2(in[m][2 * k + 1][2], in[m][2 * k + 1][3], ahi[m][3], alo[m][3]);
+      } else {
+        ahi[m][2] = ahi[m][3] = alo[m][2] = alo[m][3] = 0u;
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < OUT8; ++o) {
+      const uint4 w = *reinterpret_cast<const uint4*>(blocks + ((k * OUT8 + o) * 32 + lane) * 16);  // b0hi b1hi b0lo' b1lo'
+#pragma unroll
+      for (int m = 0; m < NM; ++m) {
+        if (k == 0) {
+          mma16816_f16(accm[m][o], ahi[m], w.x, w.y, b0[o], b1[o], b0[o], b1[o]);
+          mma16816_f16(accx[m][o], alo[m], w.x, w.y, 0.f, 0.f, 0.f, 0.f);
+        } else {
+          mma16816_f16(accm[m][o], ahi[m], w.x, w.y, accm[m][o][0], accm[m][o][1], accm[m][o][2], accm[m][o][3]);
+          mma16816_f16(accx[m][o], alo[m], w.x, w.y, accx[m][o][0], accx[m][o][1], accx[m][o][2], accx[m][o][3]);
+        }
+        mma16816_f16(accx[m][o], ahi[m], w.z, w.w, accx[m][o][0], accx[m][o][1], accx[m][o][2], accx[m][o][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < NM; ++m)
+#pragma unroll
+    for (int o = 0; o < OUT8; ++o)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float v = __fmaf_rn(accx[m][o][r], kF16LoUnscale, accm[m][o][r]);
+        out[m][o][r] = ACT ? fmaxf(v, slope * v) : v;
+      }
+}
 
 // out = act(W in + b) for NM m-tiles.  in/out: [m-tile][8-feature block][R] accumulator-layout registers.
 // Narrow outputs (OUT8 < 4) would be one long dependent mma chain per tile; their products are dealt over NS
@@ -70,6 +164,10 @@ template <class P, int NM, int IN8, int OUT8, bool ACT>
 __device__ __forceinline__ void mma_layer(const typename P::T (&in)[NM][IN8][P::R], typename P::T (&out)[NM][OUT8][P::R],
                                           const unsigned char* __restrict__ wl, typename P::T slope, int lane) {
   using T = typename P::T;
+  if constexpr (std::is_same<P, PolicyF16x3>::value) {
+    mma_layer_f16<NM, IN8, OUT8, ACT>(in, out, wl, slope, lane);
+    return;
+  }
   constexpr int NPROD = P::PROD * IN8;                       // products accumulated per output tile
   constexpr int NS_WANT = OUT8 >= 4 ? 1 : (OUT8 == 2 ? 2 : 4);
   constexpr int NS = NS_WANT < NPROD ? NS_WANT : NPROD;      // accumulators per output tile
@@ -199,6 +297,7 @@ template <class P, int NX_, int NU_, int H1, int H2>
 struct ModelMlpMma {
   static_assert(NX_ + NU_ <= 8 && NX_ <= 8, "one 8-feature input/output block");
   using T = typename P::T;
+  using Policy = P;
   using Net = Mlp3Mma<P, 1, H1 / 8, H2 / 8, 1>;
   static constexpr int NX = NX_, NU = NU_;
   static constexpr int kBytes = Net::kBytes;
@@ -230,6 +329,7 @@ template <class P, int NX_, int NU_, int E1, int E2, int NZ, int D1, int D2, int
 struct ModelRexMma {
   static_assert(NX_ + NU_ <= 8 && NZ <= 8 && NV <= 8 && NX_ * NV <= 32, "block limits");
   using T = typename P::T;
+  using Policy = P;
   using Enc = Mlp3Mma<P, 1, E1 / 8, E2 / 8, 1>;
   using Dyn = Mlp3Mma<P, 1, D1 / 8, D2 / 8, 1>;
   static constexpr int CO8 = (NX_ * NV + 7) / 8;
@@ -622,9 +722,9 @@ static __device__ unsigned int g_sm_turn[1024];  // per-SM CTA counter (never re
 
 template <class Model>
 __global__ void __launch_bounds__(128) rollout_mma_split_kernel(const RolloutArgs a) {
-  static_assert(sizeof(typename Model::T) == 4, "role-split variant is for the TF32x3 policy");
+  static_assert(sizeof(typename Model::T) == 4, "role-split variant is for the float32 tensor policies");
   static_assert(Model::NX < 8, "xc rows keep the bad flag in column NX");
-  using P = PolicyTF32x3;
+  using P = typename Model::Policy;
   constexpr int NX = Model::NX, NU = Model::NU, NV = Model::kNV, SW = P::MT, CO8 = Model::CO8;
   using L = SplitSmem<Model>;
   constexpr int CS = L::kCStride;

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cuda_fp16.h>
 #include <string>
 #include <vector>
 
@@ -236,7 +237,49 @@ void pack_layer_mma(std::vector<unsigned char>& blob, const HostLayer& L, int in
       }
 }
 
-void pack_mlp_mma(std::vector<unsigned char>& blob, const std::vector<HostLayer>& m, int out8_last, bool f64) {
+// 3xFP16 layout (mma_rollout.cuh mma_layer_f16): per layer  bias[out8*8] floats  then  ceil(in8/2)*out8 blocks of
+// 32 lanes x 16 bytes.  Lane (g,t) of block (k, o) holds, for output 8o+g, the inputs 16k + {2t, 2t+1} (register b0) and
+// 16k + {2t+8, 2t+9} (b1) as half2 pairs: {b0 hi, b1 hi, b0 lo', b1 lo'} with hi = fp16(w), lo' = fp16((w - hi) * 2^11).
+void pack_layer_f16(std::vector<unsigned char>& blob, const HostLayer& L, int in8, int out8) {
+  auto W = [&](int o, int i) { return (o < L.out && i < L.in) ? L.W[(size_t)o * L.in + i] : 0.0; };
+  auto split = [](double w, uint16_t& hi, uint16_t& lo) {
+    float wf = (float)w;
+    if (wf > 65504.f) wf = 65504.f;
+    if (wf < -65504.f) wf = -65504.f;
+    const __half h = __float2half_rn(wf);
+    const __half l = __float2half_rn((float)((w - (double)__half2float(h)) * 2048.0));
+    memcpy(&hi, &h, 2);
+    memcpy(&lo, &l, 2);
+  };
+  for (int j = 0; j < out8 * 8; ++j) append<float>(blob, j < L.out ? (float)L.b[j] : 0.f);
+  const int in16 = (in8 + 1) / 2;
+  for (int k = 0; k < in16; ++k)
+    for (int o = 0; o < out8; ++o)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3, n = 8 * o + g;
+        const int idx[4] = {16 * k + 2 * t, 16 * k + 2 * t + 1, 16 * k + 2 * t + 8, 16 * k + 2 * t + 9};
+        uint16_t hi[4], lo[4];
+        for (int e = 0; e < 4; ++e) split(idx[e] < in8 * 8 ? W(n, idx[e]) : 0.0, hi[e], lo[e]);
+        for (int e = 0; e < 4; ++e) append<uint16_t>(blob, hi[e]);
+        for (int e = 0; e < 4; ++e) append<uint16_t>(blob, lo[e]);
+      }
+}
+
+// kind: 0 = 3xTF32, 1 = float64 (DMMA), 2 = 3xFP16
+void pack_mlp_mma(std::vector<unsigned char>& blob, const std::vector<HostLayer>& m, int out8_last, int kind);
+void pack_mlp_mma(std::vector<unsigned char>& blob, const std::vector<HostLayer>& m, int out8_last, bool f64) { pack_mlp_mma(blob, m, out8_last, f64 ? 1 : 0); }
+
+void pack_mlp_mma(std::vector<unsigned char>& blob, const std::vector<HostLayer>& m, int out8_last, int kind) {
+  int in8k = 1;
+  if (kind == 2) {
+    for (size_t l = 0; l < m.size(); ++l) {
+      const int out8 = (l + 1 == m.size()) ? out8_last : m[l].out / 8;
+      pack_layer_f16(blob, m[l], in8k, out8);
+      in8k = out8;
+    }
+    return;
+  }
+  const bool f64 = kind == 1;
   int in8 = 1;
   for (size_t l = 0; l < m.size(); ++l) {
     const int out8 = (l + 1 == m.size()) ? out8_last : m[l].out / 8;
@@ -261,6 +304,7 @@ struct PackedModel {
   std::vector<double> f64;
   std::vector<unsigned char> mma_f64;  // mma-path layouts
   std::vector<unsigned char> mma_tf32;
+  std::vector<unsigned char> mma_f16;
 };
 
 int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t n, PackedModel& out) {
@@ -311,6 +355,7 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
     }
     if (out.variant->bytes_mma_f64) pack_mlp_mma(out.mma_f64, net, 1, true);
     if (out.variant->bytes_mma_tf32) pack_mlp_mma(out.mma_tf32, net, 1, false);
+    if (out.variant->bytes_mma_f16) pack_mlp_mma(out.mma_f16, net, 1, 2);
     return TAMPC_OK;
   }
   if (d.kind != TAMPC_DYN_REX) { h->err = "unknown dynamics kind"; return TAMPC_ERR_INVALID; }
@@ -393,14 +438,15 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
     out.f64.push_back(i < nx ? d0[i] : 0.0);
   }
   if (out.variant->bytes_mma_f64) {
-    for (int f64 = 0; f64 < 2; ++f64) {
-      std::vector<unsigned char>& blob = f64 ? out.mma_f64 : out.mma_tf32;
-      pack_mlp_mma(blob, enc, 1, f64);
-      pack_mlp_mma(blob, dyn, 1, f64);
-      pack_mlp_mma(blob, dec, (nx * nv + 7) / 8, f64);
+    for (int kind = 0; kind < 3; ++kind) {  // 0 = 3xTF32, 1 = float64, 2 = 3xFP16
+      if (kind == 2 && !out.variant->bytes_mma_f16) continue;
+      std::vector<unsigned char>& blob = kind == 1 ? out.mma_f64 : (kind == 2 ? out.mma_f16 : out.mma_tf32);
+      pack_mlp_mma(blob, enc, 1, kind);
+      pack_mlp_mma(blob, dyn, 1, kind);
+      pack_mlp_mma(blob, dec, (nx * nv + 7) / 8, kind);
       for (int i = 0; i < 8; ++i) {
         const double v = i < nx ? d0[i] : 0.0;
-        if (f64) append<double>(blob, v); else append<float>(blob, (float)v);
+        if (kind == 1) append<double>(blob, v); else append<float>(blob, (float)v);
       }
     }
   }
@@ -439,7 +485,10 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     return p;
   }
   if (h->use_mma) {
-    const bool f64 = h->cfg.precision == TAMPC_PREC_F64;
+    const bool f64 = h->cfg.precision == TAMPC_PREC_F64, f16 = h->cfg.precision == TAMPC_PREC_F16X3;
+    const rollout_launch_fn* fmma = f64 ? v->f64_mma : (f16 ? v->f16_mma : v->tf32_mma);
+    const rollout_launch_fn fwide = f16 ? v->f16_mma_wide : v->tf32_mma_wide, fsplit = f16 ? v->f16_split : v->tf32_split;
+    const rollout_launch_fn fpipe = f16 ? nullptr : v->tf32_pipe;
     const int mt = f64 ? 8 : 16, max_idx = f64 ? 2 : 1;
     // Resident warps per SM are bounded by shared memory (image ~40 KB per CTA + ~14 KB per warp): about 4 one-warp
     // CTAs, 3 two-warp CTAs or 2 four-warp CTAs.  While everything fits in one wave the kernel is latency-bound and
@@ -448,22 +497,22 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     const bool big = h->img_bytes > 100 * 1024;  // wide networks: one CTA per SM, always four warps sharing the image
     const int cap32 = big ? 0 : 148 * 4, cap64 = big ? 0 : 148 * 3 * 2, cap128 = big ? 148 * 4 : 148 * 2 * 4;
     int idx = 0;  // NM = 1 << idx
-    while (idx < max_idx && (f64 ? v->f64_mma[idx + 1] : v->tf32_mma[idx + 1]) != nullptr && (K + (mt << idx) - 1) / (mt << idx) > cap128) ++idx;
+    while (idx < max_idx && fmma[idx + 1] != nullptr && (K + (mt << idx) - 1) / (mt << idx) > cap128) ++idx;
     const int en = env_int("TAMPC_MMA_NM", 0);
     if (en == 1) idx = 0; else if (en == 2) idx = 1; else if (en == 4 && f64) idx = 2;
     const int warps = (K + (mt << idx) - 1) / (mt << idx);
     p.block = warps <= cap32 ? 32 : (warps <= cap64 ? 64 : 128);
-    p.fn = f64 ? v->f64_mma[idx] : v->tf32_mma[idx];
+    p.fn = fmma[idx];
     if (eb == 32 || eb == 64 || eb == 128) p.block = eb;
     // throughput-bound 3xTF32: eight warps per CTA and two CTAs per SM give 16 resident warps instead of 12.
     // Measured on B200 (push, T=40): a full wave takes 1.18x as long but holds 1.33x the samples (1M: 5.98 -> 5.68 ms),
     // so it is used when it does not add a wave (K=131072: 0.83 vs 0.78 ms).  TAMPC_WIDE=0/1 forces the choice.
-    if (!f64 && idx == 1 && !big && v->tf32_mma_wide && eb == 0) {
+    if (!f64 && idx == 1 && !big && fwide && eb == 0) {
       const int wide_env = env_int("TAMPC_WIDE", -1);
       const int ctas_d = (warps + 3) / 4, ctas_w = (warps + 7) / 8;
       const bool wide = wide_env >= 0 ? wide_env != 0 : (ctas_d > 148 * 3 && ctas_w <= 148 * 2) || ctas_w >= 148 * 2 * 4;
       if (wide) {
-        p.fn = v->tf32_mma_wide;
+        p.fn = fwide;
         p.block = 256;
       }
     }
@@ -481,8 +530,8 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     {
       const int split_env = env_int("TAMPC_SPLIT", -1);
       const bool split = !big && (split_env >= 0 ? split_env != 0 : (K + 15) / 16 <= 5 * 148 + 28);
-      if (!f64 && idx == 0 && v->tf32_split && split && en == 0) {
-        p.fn = v->tf32_split;
+      if (!f64 && idx == 0 && fsplit && split && en == 0) {
+        p.fn = fsplit;
         p.block = 128;
         p.fuse_warps = 0;
         return p;
@@ -490,8 +539,8 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     }
     const int tiles = (K + 15) / 16, pipe_env = env_int("TAMPC_PIPE", -1);
     const bool pipe = !big && (pipe_env >= 0 ? pipe_env != 0 : tiles <= 2 * 148);
-    if (!f64 && idx == 0 && v->tf32_pipe && pipe) {
-      p.fn = v->tf32_pipe;
+    if (!f64 && idx == 0 && fpipe && pipe) {
+      p.fn = fpipe;
       p.block = 64;
       p.fuse_warps = env_int("TAMPC_FUSE", 0) ? tiles : 0;
       return p;
@@ -507,7 +556,8 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     switch (h->cfg.precision) {
       case TAMPC_PREC_F64: p.fn = v->f64_s1; break;
       case TAMPC_PREC_MIXED:
-      case TAMPC_PREC_TF32X3: p.fn = S == 2 ? v->mixed_s2 : v->mixed_s1; break;
+      case TAMPC_PREC_TF32X3:
+      case TAMPC_PREC_F16X3: p.fn = S == 2 ? v->mixed_s2 : v->mixed_s1; break;
       default: p.fn = S == 2 ? v->f32_s2 : v->f32_s1; break;
     }
   }
@@ -522,7 +572,7 @@ int prep_image(tampc_mppi* h) {
   const int prec = h->cfg.precision;
   const int sd = h->use_mma ? h->img_sampler_d_off : -1;
   if (prec == TAMPC_PREC_F64) prep_image_kernel<double, double><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, sd, h->d_cost, h->d_sampler);
-  else if (prec == TAMPC_PREC_MIXED || (prec == TAMPC_PREC_TF32X3 && !h->use_mma))
+  else if (prec == TAMPC_PREC_MIXED || ((prec == TAMPC_PREC_TF32X3 || prec == TAMPC_PREC_F16X3) && !h->use_mma))
     prep_image_kernel<double, float><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, sd, h->d_cost, h->d_sampler);
   else prep_image_kernel<float, float><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, sd, h->d_cost, h->d_sampler);
   CUDA_TRY(h, cudaGetLastError());
@@ -807,7 +857,7 @@ TAMPC_API int tampc_mppi_create(const tampc_mppi_config* cfg, tampc_mppi** out) 
     return TAMPC_ERR_INVALID;
   }
   if (cfg->max_horizon < 1 || cfg->max_horizon > TAMPC_MAX_HORIZON) { g_create_error = "max_horizon out of range (1..128)"; return TAMPC_ERR_INVALID; }
-  if (cfg->precision < TAMPC_PREC_F64 || cfg->precision > TAMPC_PREC_TF32X3) { g_create_error = "unknown precision"; return TAMPC_ERR_INVALID; }
+  if (cfg->precision < TAMPC_PREC_F64 || cfg->precision > TAMPC_PREC_F16X3) { g_create_error = "unknown precision"; return TAMPC_ERR_INVALID; }
   if (!(cfg->lambda_ > 0.0)) { g_create_error = "lambda_ must be positive"; return TAMPC_ERR_INVALID; }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -953,6 +1003,9 @@ static int install_model(tampc_mppi* h, const tampc_model_desc* desc, const doub
   bool use_mma = false;
   if (h->gp_on) {
     if (!pm.variant->gp.f64) { h->err = std::string("no GP-residual kernel compiled for ") + pm.variant->name; return TAMPC_ERR_UNSUPPORTED; }
+  } else if (prec == TAMPC_PREC_F16X3) {
+    use_mma = pm.variant->bytes_mma_f16 != 0;
+    if (!use_mma && pm.variant->kind != TAMPC_DYN_PENDULUM) { h->err = std::string("no 3xFP16 tensor-core kernel for ") + pm.variant->name; return TAMPC_ERR_UNSUPPORTED; }
   } else if (prec == TAMPC_PREC_TF32X3) {
     // shapes without network layers (analytic pendulum) have nothing to put on the tensor cores: the float64
     // state/cost arithmetic of TF32X3 is exactly the MIXED kernel there
@@ -968,8 +1021,9 @@ static int install_model(tampc_mppi* h, const tampc_model_desc* desc, const doub
   const void* src;
   size_t raw_bytes;
   if (use_mma) {
-    const std::vector<unsigned char>& blob = f64 ? pm.mma_f64 : pm.mma_tf32;
-    const int expect = f64 ? pm.variant->bytes_mma_f64 : pm.variant->bytes_mma_tf32;
+    const bool f16 = prec == TAMPC_PREC_F16X3;
+    const std::vector<unsigned char>& blob = f64 ? pm.mma_f64 : (f16 ? pm.mma_f16 : pm.mma_tf32);
+    const int expect = f64 ? pm.variant->bytes_mma_f64 : (f16 ? pm.variant->bytes_mma_f16 : pm.variant->bytes_mma_tf32);
     if ((int)blob.size() != expect) {
       h->err = "internal: packed mma size " + std::to_string(blob.size()) + " != kernel layout " + std::to_string(expect) + " for " + pm.variant->name;
       return TAMPC_ERR_INVALID;
@@ -990,7 +1044,7 @@ static int install_model(tampc_mppi* h, const tampc_model_desc* desc, const doub
   const size_t wbytes = (raw_bytes + 15) & ~size_t(15);
   size_t cost_sz, samp_sz;
   if (f64) { cost_sz = sizeof(CostS<double, double>); samp_sz = sizeof(SamplerS<double>); }
-  else if (prec == TAMPC_PREC_MIXED || (prec == TAMPC_PREC_TF32X3 && !use_mma)) { cost_sz = sizeof(CostS<double, float>); samp_sz = sizeof(SamplerS<double>); }
+  else if (prec == TAMPC_PREC_MIXED || ((prec == TAMPC_PREC_TF32X3 || prec == TAMPC_PREC_F16X3) && !use_mma)) { cost_sz = sizeof(CostS<double, float>); samp_sz = sizeof(SamplerS<double>); }
   else { cost_sz = sizeof(CostS<float, float>); samp_sz = sizeof(SamplerS<float>); }
   const size_t cost_off = wbytes, samp_off = cost_off + ((cost_sz + 15) & ~size_t(15));
   const size_t samp_d_off = samp_off + ((samp_sz + 15) & ~size_t(15));  // mma kernels: float64 SamplerS copy

@@ -6,6 +6,8 @@ const ModelVariant* variant_rex_push() {
         "rex_nx5_nu3_e16-32-5_d32-32-5_c16-32", TAMPC_DYN_REX, {16, 32, 5, 32, 32, 5, 16, 32});
     add_mma<ModelRexMma<PolicyF64, 5, 3, 16, 32, 5, 32, 32, 5, 16, 32>, ModelRexMma<PolicyTF32x3, 5, 3, 16, 32, 5, 32, 32, 5, 16, 32>>(m);
     m.tf32_split = &launch_rollout_mma_split<ModelRexMma<PolicyTF32x3, 5, 3, 16, 32, 5, 32, 32, 5, 16, 32>>;
+    add_f16<ModelRexMma<PolicyF16x3, 5, 3, 16, 32, 5, 32, 32, 5, 16, 32>>(m);
+    m.f16_split = &launch_rollout_mma_split<ModelRexMma<PolicyF16x3, 5, 3, 16, 32, 5, 32, 32, 5, 16, 32>>;
     m.gp = gp_launchers_rex_push();
     return m;
   }();

@@ -19,6 +19,9 @@ struct ModelVariant {
   rollout_launch_fn tf32_mma[2];
   GpLaunchers gp;                 // one-thread-per-(sample, replica) FMA kernels with the online GP residual
   rollout_launch_fn tf32_mma_wide; // NM = 2, 256-thread CTAs, two per SM (throughput-bound K)
+  // 3xFP16 (mma.sync.m16n8k16.f16): same kernels, half the tensor instructions
+  int bytes_mma_f16;
+  rollout_launch_fn f16_mma[2], f16_mma_wide, f16_split;
   rollout_launch_fn tf32_split;   // two warps per 16-sample tile, split by role (RexExtract shapes, latency-bound K)
   rollout_launch_fn tf32_pipe;    // two-warp pipelined 3xTF32 kernel for small K (16 samples per CTA)  // 3xTF32 kernels, NM = 1, 2 (16, 32 samples per warp); float32 state and cost terms, float64 cost sum
 };
@@ -62,6 +65,14 @@ void add_mma(ModelVariant& v) {
 GpLaunchers gp_launchers_rex_push();
 GpLaunchers gp_launchers_rex_peg();
 GpLaunchers gp_launchers_mlp_5_3_32();
+
+template <class MM16>
+void add_f16(ModelVariant& v) {
+  v.bytes_mma_f16 = MM16::kBytes;
+  v.f16_mma[0] = &launch_rollout_mma<MM16, float, float, 1, true>;
+  v.f16_mma[1] = &launch_rollout_mma<MM16, float, float, 2, false>;
+  v.f16_mma_wide = &launch_rollout_mma<MM16, float, float, 2, false, 256>;
+}
 
 const ModelVariant* variant_rex_push();   // nx5 nu3, enc 8-16-32-5, dyn 5-32-32-5, dec 5(2)-16-32-25
 const ModelVariant* variant_rex_peg();    // nx5 nu2, enc 7-16-32-5, ...

@@ -10,15 +10,15 @@ from conftest import GOLDEN_CASES, load_golden
 
 pytestmark = pytest.mark.gpu
 
-COST_RTOL = {'f64': 1e-9, 'tf32x3': 1e-5, 'mixed': 1e-5, 'f32': 1e-5}
-ACTION_ATOL = {'f64': 1e-8, 'tf32x3': 1e-4, 'mixed': 1e-4, 'f32': 1e-4}
+COST_RTOL = {'f64': 1e-9, 'tf32x3': 1e-5, 'f16x3': 1e-5, 'mixed': 1e-5, 'f32': 1e-5}
+ACTION_ATOL = {'f64': 1e-8, 'tf32x3': 1e-4, 'f16x3': 1e-4, 'mixed': 1e-4, 'f32': 1e-4}
 
 
 def _rel(a, b):
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
 
 
-@pytest.mark.parametrize('precision', ['f64', 'tf32x3', 'mixed', 'f32'])
+@pytest.mark.parametrize('precision', ['f64', 'tf32x3', 'f16x3', 'mixed', 'f32'])
 @pytest.mark.parametrize('case', GOLDEN_CASES)
 def test_command_matches_reference_golden(cuda_lib, case, precision):
     from tampc_b200.mppi import B200MPPI

@@ -10,8 +10,8 @@ from tampc_b200 import spec as S
 
 pytestmark = pytest.mark.gpu
 
-PRECISIONS = ['f64', 'tf32x3', 'mixed']
-RTOL = {'f64': 1e-9, 'tf32x3': 1e-5, 'mixed': 1e-5, 'f32': 1e-5}
+PRECISIONS = ['f64', 'tf32x3', 'f16x3', 'mixed']
+RTOL = {'f64': 1e-9, 'tf32x3': 1e-5, 'f16x3': 1e-5, 'mixed': 1e-5, 'f32': 1e-5}
 
 
 def _spec(case, K=None, T=None):
@@ -50,7 +50,7 @@ def test_oracle_parity_at_benchmark_sizes(cuda_lib, case, K, precision):
     m.close()
 
 
-@pytest.mark.parametrize('precision', ['f64', 'tf32x3'])
+@pytest.mark.parametrize('precision', ['f64', 'tf32x3', 'f16x3'])
 def test_philox_path_costs_match_oracle_on_the_device_draw(cuda_lib, precision):
     """Production path: the device draws the noise; its own perturbed actions re-scored by the oracle."""
     from tampc_b200.mppi import B200MPPI
@@ -99,12 +99,12 @@ def test_philox_noise_statistics(cuda_lib):
     m.close(); m2.close()
 
 
-@pytest.mark.parametrize('precision', ['f64', 'tf32x3'])
+@pytest.mark.parametrize('precision', ['f64', 'tf32x3', 'f16x3'])
 def test_sample_shards_reproduce_the_unsharded_costs(cuda_lib, precision):
     """K-shard invariance on one GPU: two handles owning [0,K/2) and [K/2,K) see the same samples (global Philox
     index) and produce the same per-sample costs as one handle owning all K — at the 1M-sample size of config 5."""
     from tampc_b200.mppi import B200MPPI
-    K = 1 << 20 if precision == 'tf32x3' else 1 << 17
+    K = 1 << 17 if precision == 'f64' else 1 << 20
     z, spec = _spec('push_nominal', K, T=10)
     U0 = _U(z, spec)
     full = B200MPPI(spec, precision=precision, U_init=U0, seed=11)

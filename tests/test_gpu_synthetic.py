@@ -11,7 +11,7 @@ from tampc_b200.synthetic import make_synthetic_spec
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('precision', ['f64', 'tf32x3'])
+@pytest.mark.parametrize('precision', ['f64', 'tf32x3', 'f16x3'])
 @pytest.mark.parametrize('H,K,T', [(32, 4096, 40), (32, 1000, 100), (64, 2048, 10), (64, 1024, 40), (128, 2048, 40),
                                    (128, 1000, 10)])
 def test_synthetic_mlp_matches_oracle(cuda_lib, H, K, T, precision):
