@@ -208,7 +208,8 @@ typedef enum tampc_query {
   TAMPC_Q_NOMINAL = 2,    /* double[T*nu]                 : .U */
   TAMPC_Q_OMEGA = 3,      /* double[num_local]            : .omega */
   TAMPC_Q_STATS = 4,      /* double[4]: beta, eta, argmin (global index), launches so far */
-  TAMPC_Q_STATES = 5      /* double[num_local*T*nx]       : rollout states of the last command_ex(keep_states=1) */
+  TAMPC_Q_STATES = 5,     /* double[num_local*T*nx]       : rollout states of the last command_ex(keep_states=1) */
+  TAMPC_Q_NOISE = 6       /* double[num_local*T*nu]       : .noise = perturbed_action - U, post-clamp (controller.py:394) */
 } tampc_query;
 
 typedef struct tampc_mppi tampc_mppi;

@@ -17,7 +17,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE, ERR_NO_DEVICE = 0, -1, -2
 PREC_F64, PREC_MIXED, PREC_F32, PREC_TF32X3, PREC_F16X3 = 0, 1, 2, 3, 4
 PRECISIONS = {'f64': PREC_F64, 'mixed': PREC_MIXED, 'f32': PREC_F32, 'tf32x3': PREC_TF32X3, 'f16x3': PREC_F16X3}
 NOISE_PHILOX, NOISE_INJECTED, NOISE_ACTIONS = 0, 1, 2
-Q_COST_TOTAL, Q_PERTURBED, Q_NOMINAL, Q_OMEGA, Q_STATS, Q_STATES = 0, 1, 2, 3, 4, 5
+Q_COST_TOTAL, Q_PERTURBED, Q_NOMINAL, Q_OMEGA, Q_STATS, Q_STATES, Q_NOISE = 0, 1, 2, 3, 4, 5, 6
 
 EXPORTS = [
     'tampc_mppi_last_error', 'tampc_mppi_abi_version', 'tampc_mppi_create', 'tampc_mppi_destroy',

@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(128) rollout_mma_split_kernel(const RolloutArg
   const int k = live ? kbase + row : a.K_local - 1;
   if (kbase < a.K_local) {
     // every perturbed action of the horizon, drawn by the tile's 64 threads (independent items)
-#pragma unroll 2
+#pragma unroll 5
     for (int item = tid & 63; item < T * SW; item += 64) {
       const int t = item / SW, r = item % SW;
       float u[NU], npost[NU];

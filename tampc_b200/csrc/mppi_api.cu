@@ -1551,6 +1551,7 @@ TAMPC_API int tampc_mppi_query(tampc_mppi* h, int32_t what, double* out, size_t 
       out[0] = h->last_stats[0]; out[1] = h->last_stats[1]; out[2] = h->last_stats[2]; out[3] = (double)h->launches;
       return TAMPC_OK;
     }
+    case TAMPC_Q_NOISE:
     case TAMPC_Q_PERTURBED: {
       if (!h->last_valid) { h->err = "no command has run"; return TAMPC_ERR_STATE; }
       const size_t total = K * h->last_T * h->cfg.nu;
@@ -1562,6 +1563,7 @@ TAMPC_API int tampc_mppi_query(tampc_mppi* h, int32_t what, double* out, size_t 
       p.src = make_src(h, h->last_mode, h->last_call, h->last_T);
       p.K_local = (int)K;
       p.out = h->d_scratch;
+      p.post_clamp_noise = what == TAMPC_Q_NOISE;
       const long long items = (long long)K * h->last_T;
       const int grid = (int)((items + 255) / 256);
       switch (h->cfg.nu) {

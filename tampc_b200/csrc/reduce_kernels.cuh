@@ -316,6 +316,7 @@ struct PerturbedArgs {
   SampleSrc src;
   int K_local;
   double* out;
+  int post_clamp_noise;  // 1: write perturbed - U (controller.py:394) instead of the perturbed action
 };
 
 template <int NU>
@@ -332,7 +333,7 @@ __global__ void perturbed_kernel(const PerturbedArgs a) {
   for (int d = 0; d < NU; ++d) Ut[d] = ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d];
   sample_action<double, NU>(a.src, sp, Ut, k, t, u, npost);
 #pragma unroll
-  for (int d = 0; d < NU; ++d) a.out[i * NU + d] = u[d];
+  for (int d = 0; d < NU; ++d) a.out[i * NU + d] = a.post_clamp_noise ? npost[d] : u[d];
 }
 
 }  // namespace tampc

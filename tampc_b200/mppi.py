@@ -351,8 +351,15 @@ class B200MPPI:
 
     @property
     def noise(self):
-        """Post-clamp noise perturbed_action - U_shifted of the last command (controller.py:394)."""
-        raise NotImplementedError("query perturbed_action; the post-clamp noise is regenerated on the device")
+        """Post-clamp noise perturbed_action - U_shifted of the last command (controller.py:394), regenerated on the
+        device from the same Philox stream (or re-read from the injected draw)."""
+        return torch.from_numpy(self._query(L.Q_NOISE, self.K_local * self.T * self.nu).reshape(self.K_local, self.T, self.nu))
+
+    @property
+    def actions(self):
+        """ExperimentalMPPI.actions (M, K, T, nu) of the last command (controller.py:368,372): the M replicas share the
+        perturbed actions, so one copy is returned with a leading axis of 1."""
+        return self.perturbed_action.unsqueeze(0)
 
     @property
     def stats(self):

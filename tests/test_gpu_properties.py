@@ -230,3 +230,17 @@ def test_predict_next_state_matches_oracle(cuda_lib, case, precision):
         assert got.shape == (1, spec.dynamics.nx)
         np.testing.assert_allclose(got, want.numpy(), rtol=0, atol=1e-10 if precision == 'f64' else 2e-4)
     m.close()
+
+
+def test_noise_and_actions_attributes(cuda_lib):
+    """`.noise` is the POST-clamp perturbation (controller.py:394) and `.actions` the (1,K,T,nu) perturbed actions."""
+    from tampc_b200.mppi import B200MPPI
+    z, spec = load_golden('push_nominal')
+    m = B200MPPI(spec, precision='f64', U_init=torch.from_numpy(z['in.U']))
+    m.command(z['in.state'], noise=z['in.noise'])
+    want = O.command(spec, torch.from_numpy(z['in.state']), torch.from_numpy(z['in.U']), torch.from_numpy(z['in.noise']))
+    np.testing.assert_allclose(m.noise.numpy(), want['noise'].numpy(), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(m.actions.numpy()[0], want['perturbed_action'].numpy(), rtol=0, atol=1e-12)
+    # clamped entries exist in this fixture: the post-clamp noise differs from the injected draw there
+    assert np.any(np.abs(m.noise.numpy() - z['in.noise']) > 1e-6)
+    m.close()
