@@ -74,7 +74,7 @@ class B200MPPI:
         self.u_per_command = 1
         self.running_cost = None
         self.terminal_state_cost = None
-        self.state = None
+        self._state_np = None
         self.step_dependency = True
 
         self.sample_offset, self.K_local = shard_bounds(self.K, rank, world_size)
@@ -252,13 +252,27 @@ class B200MPPI:
         self.U = self.noise_dist.sample((self.T,))
 
     # ------------------------------------------------------------------ command
+    @property
+    def state(self):
+        """MPPI.state: the start state of the last command as a float64 tensor (materialised on access: building a
+        tensor costs microseconds that the command() latency does not need to pay)."""
+        return None if self._state_np is None else torch.from_numpy(self._state_np)
+
+    @state.setter
+    def state(self, value):
+        self._state_np = None if value is None else np.array(torch.as_tensor(value).detach().to('cpu', torch.double).numpy(),
+                                                             dtype=np.float64).reshape(-1)
+
     def _state_array(self, state):
-        if not torch.is_tensor(state):
-            state = torch.as_tensor(np.asarray(state))
-        self.state = state.detach().to('cpu', torch.double)
-        a = np.ascontiguousarray(self.state.numpy().reshape(-1))
+        if isinstance(state, np.ndarray) and state.dtype == np.float64:
+            a = np.array(state, dtype=np.float64).reshape(-1)  # fast path (a private copy: `.state` must not alias the caller's buffer)
+        else:
+            if not torch.is_tensor(state):
+                state = torch.as_tensor(np.asarray(state))
+            a = np.ascontiguousarray(state.detach().to('cpu', torch.double).numpy().reshape(-1))
         if a.shape != (self.nx,):
             raise ValueError("state must have {} entries (per-sample start states are not supported)".format(self.nx))
+        self._state_np = a
         return a
 
     def _arm_gp_draws(self, gp_eps):

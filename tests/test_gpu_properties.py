@@ -244,3 +244,31 @@ def test_noise_and_actions_attributes(cuda_lib):
     # clamped entries exist in this fixture: the post-clamp noise differs from the injected draw there
     assert np.any(np.abs(m.noise.numpy() - z['in.noise']) > 1e-6)
     m.close()
+
+
+@pytest.mark.parametrize('precision', ['f64', 'tf32x3', 'f16x3', 'mixed'])
+@pytest.mark.parametrize('K,T,P', [(1, 40, 3), (17, 7, 0), (33, 128, 16), (4737, 3, 16), (12289, 5, 1)])
+def test_ragged_and_maximum_sizes(cuda_lib, precision, K, T, P):
+    """Edge sizes: a single sample, K that is not a multiple of any tile (idle rows / warps / tiles in every kernel
+    family and on both sides of the role-split / single-warp switch-overs), the longest horizon (TAMPC_MAX_HORIZON) and
+    the largest trap set (TAMPC_MAX_TRAPS), an empty trap set."""
+    from tampc_b200.mppi import B200MPPI
+    z, spec = _spec('push_nominal', K, T)
+    rng = np.random.RandomState(K)
+    spec.cost.trap_x = np.tile(spec.cost.trap_x[:1], (P, 1)) + 0.3 * rng.randn(P, 5) if P else np.zeros((0, 5))
+    spec.cost.trap_u = np.tile(spec.cost.trap_u[:1], (P, 1)) + 0.3 * rng.randn(P, 3) if P else np.zeros((0, 3))
+    U0 = _U(z, spec)
+    noise = O.sample_noise(spec, 17, K=K, T=T)
+    want = O.command(spec, torch.from_numpy(z['in.state']), U0, noise)
+    m = B200MPPI(spec, precision=precision, U_init=U0, max_horizon=128)
+    a = m.command(z['in.state'], noise=noise.numpy())
+    cost = m.cost_total
+    assert cost.shape == (K,)
+    rel = float(((cost - want['cost_total']).abs() / want['cost_total'].abs()).max())
+    # the 1e-5 gate is for the task horizons; 128 steps of float32 state drift further (f64 stays at 1e-9)
+    assert rel < (RTOL[precision] if T <= 40 or precision == 'f64' else 1e-4), rel
+    s = torch.sort(want['cost_total']).values
+    if K == 1 or float(s[1] - s[0]) > 1e-3 * float(s[0].abs()):
+        assert m.stats['argmin'] == want['argmin']
+        assert float((a - want['action']).abs().max()) < 1e-4
+    m.close()
