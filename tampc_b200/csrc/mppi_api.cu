@@ -679,6 +679,23 @@ int ensure_noise(tampc_mppi* h) {
   return TAMPC_OK;
 }
 
+CombineArgs base_combine_args(tampc_mppi* h) {
+  CombineArgs c{};
+  c.sampler = h->d_sampler;
+  c.U = h->d_U[h->cur];
+  c.T = h->T;
+  c.nu = h->cfg.nu;
+  c.U_out = h->d_U[h->cur ^ 1];
+  c.action_out = h->d_action;
+  c.stats_out = h->d_stats;
+  return c;
+}
+
+template <int NU>
+void launch_partials_combine(const ReduceArgs& r, const CombineArgs& c, unsigned int* ticket, int n_chunks, cudaStream_t s) {
+  partials_combine_kernel<NU><<<n_chunks, kCombineThreads, 0, s>>>(r, c, ticket);
+}
+
 template <int NU>
 void launch_partials(const ReduceArgs& r, int n_chunks, cudaStream_t s) {
   partials_kernel<NU><<<n_chunks, kReduceThreads, 0, s>>>(r);
@@ -714,6 +731,32 @@ int run_rollout_and_partials(tampc_mppi* h, int mode, bool keep_states, int fuse
   r.chunk = h->chunk;
   r.nu = h->cfg.nu;
   r.partials = h->d_partials;
+  // latency path: both reduction stages in one launch while a single merging CTA suffices (TAMPC_FUSE_TAIL=0: separate)
+  if (fuse && h->n_chunks <= kCombineThreads && env_int("TAMPC_FUSE_TAIL", 1)) {
+    CombineArgs c = base_combine_args(h);
+    c.partials = h->d_partials;
+    c.n_partials = h->n_chunks;
+    c.group = h->n_chunks;
+    c.solo = 1;
+    c.finalize = fuse == 1;
+    c.partial_out = partial_out ? partial_out : h->d_rank_partial;
+    if (fuse == 1) {
+      c.host_out = h->d_map;
+      c.host_flag = reinterpret_cast<unsigned long long*>(h->d_map + 8);
+      c.seq = ++h->seq;
+    }
+    switch (h->cfg.nu) {
+      case 1: launch_partials_combine<1>(r, c, h->d_ticket, h->n_chunks, h->stream); break;
+      case 2: launch_partials_combine<2>(r, c, h->d_ticket, h->n_chunks, h->stream); break;
+      case 3: launch_partials_combine<3>(r, c, h->d_ticket, h->n_chunks, h->stream); break;
+      default: launch_partials_combine<4>(r, c, h->d_ticket, h->n_chunks, h->stream); break;
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    if (fuse == 1) h->cur ^= 1;
+    *done = true;
+    return TAMPC_OK;
+  }
   switch (h->cfg.nu) {
     case 1: launch_partials<1>(r, h->n_chunks, h->stream); break;
     case 2: launch_partials<2>(r, h->n_chunks, h->stream); break;
@@ -729,14 +772,7 @@ int run_rollout_and_partials(tampc_mppi* h, int mode, bool keep_states, int fuse
 // deterministic two-level tree), then a single CTA finishes: finalize=1 writes the new U / action / stats,
 // finalize=0 writes one merged partial (this rank's contribution) to partial_out.
 int run_combine(tampc_mppi* h, const tampc_partial* partials, int n, int finalize, tampc_partial* partial_out = nullptr) {
-  CombineArgs c{};
-  c.sampler = h->d_sampler;
-  c.U = h->d_U[h->cur];
-  c.T = h->T;
-  c.nu = h->cfg.nu;
-  c.U_out = h->d_U[h->cur ^ 1];
-  c.action_out = h->d_action;
-  c.stats_out = h->d_stats;
+  CombineArgs c = base_combine_args(h);
   while (n > kCombineThreads) {
     const int groups = (n + kCombineThreads - 1) / kCombineThreads;
     if (groups > h->n_partials2) { h->err = "internal: too many partials for the combine scratch"; return TAMPC_ERR_INVALID; }

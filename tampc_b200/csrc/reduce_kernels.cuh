@@ -62,19 +62,20 @@ __device__ __forceinline__ double block_sum(double v, double* s_b, int tid, int 
   return v;
 }
 
-template <int NU>
-__global__ void __launch_bounds__(kReduceThreads) partials_kernel(const ReduceArgs a) {
-  __shared__ double s_w[kReduceThreads];      // weights of the chunk (chunk <= kReduceThreads)
+// One CTA's partial; NT = block size (the chunk holds at most NT samples).
+template <int NU, int NT>
+__device__ __forceinline__ void partials_body(const ReduceArgs& a) {
+  __shared__ double s_w[NT];      // weights of the chunk (chunk <= NT)
   __shared__ SamplerS<double> sp;
   __shared__ double Ush[TAMPC_MAX_HORIZON * kMaxNu];
-  __shared__ double s_acc[kReduceThreads * NU];
+  __shared__ double s_acc[NT * NU];
 
   const int tid = threadIdx.x;
   const int T = a.src.T;
   const int k0 = blockIdx.x * a.chunk;
   const int n = min(a.chunk, a.K_local - k0);
-  stage_sampler<double>(sp, *a.sampler, tid, kReduceThreads);
-  for (int i = tid; i < T * NU; i += kReduceThreads) {
+  stage_sampler<double>(sp, *a.sampler, tid, NT);
+  for (int i = tid; i < T * NU; i += NT) {
     int t = i / NU, d = i % NU, ts = t + 1;
     Ush[t * kMaxNu + d] = ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d];
   }
@@ -84,14 +85,14 @@ __global__ void __launch_bounds__(kReduceThreads) partials_kernel(const ReduceAr
   const double c = tid < n ? a.cost[k0 + tid] : __longlong_as_double(0x7ff0000000000000ll);
   double beta = c;
   long long amin_ll = tid;
-  block_min_arg(beta, amin_ll, s_wb, s_wi, tid, kReduceThreads);
+  block_min_arg(beta, amin_ll, s_wb, s_wi, tid, NT);
   const int amin = (int)amin_ll;
   // ---- weights and their sum
   const double w = tid < n ? exp(-a.sampler->lambda_inv * (c - beta)) : 0.0;
   s_w[tid] = w;
-  const double eta = block_sum(w, s_wb, tid, kReduceThreads);  // (its barriers also publish s_w, sp and Ush)
+  const double eta = block_sum(w, s_wb, tid, NT);  // (its barriers also publish s_w, sp and Ush)
   // ---- weighted post-clamp noise: thread (t, g) sums samples g, g+G, ... of the chunk for step t  (T <= 128)
-  const int G = kReduceThreads / T;
+  const int G = NT / T;
   if (tid < G * T) {
     const int t = tid % T, g = tid / T;
     double acc[NU];
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(kReduceThreads) partials_kernel(const ReduceAr
   }
   __syncthreads();
   tampc_partial& out = a.partials[blockIdx.x];
-  for (int i = tid; i < T * NU; i += kReduceThreads) {
+  for (int i = tid; i < T * NU; i += NT) {
     const int t = i / NU, d = i % NU;
     double sum = 0.0;
     for (int g = 0; g < G; ++g) sum += s_acc[(g * T + t) * NU + d];
@@ -124,10 +125,14 @@ __global__ void __launch_bounds__(kReduceThreads) partials_kernel(const ReduceAr
   }
 }
 
+template <int NU>
+__global__ void __launch_bounds__(kReduceThreads) partials_kernel(const ReduceArgs a) { partials_body<NU, kReduceThreads>(a); }
+
 struct CombineArgs {
   const tampc_partial* partials;
   int n_partials;
   int group;             // partials per CTA: CTA b merges [b*group, min((b+1)*group, n_partials))
+  int solo;              // 1: the calling CTA merges partials [0, n_partials) whatever its blockIdx (fused tail)
   const SamplerD* sampler;
   const double* U;       // nominal BEFORE the shift
   int T, nu;
@@ -150,7 +155,8 @@ __device__ __forceinline__ void combine_body(const CombineArgs& a) {
   __shared__ long long s_wi[32];
   __shared__ double s_part[4][TAMPC_MAX_HORIZON * kMaxNu];
   const int tid = threadIdx.x;
-  const int p0 = blockIdx.x * a.group;
+  const int cta = a.solo ? 0 : (int)blockIdx.x;
+  const int p0 = cta * a.group;
   const int n = min(a.group, a.n_partials - p0);
   const tampc_partial* part = a.partials + p0;
   const double li = a.sampler->lambda_inv;
@@ -208,7 +214,7 @@ __device__ __forceinline__ void combine_body(const CombineArgs& a) {
         if (a.host_out != nullptr) a.host_out[d] = v;  // zero-copy: straight into mapped pinned host memory
       }
     } else {
-      a.partial_out[blockIdx.x].wsum[i] = sum;
+      a.partial_out[cta].wsum[i] = sum;
     }
   }
   if (tid == 0) {
@@ -218,7 +224,7 @@ __device__ __forceinline__ void combine_body(const CombineArgs& a) {
       a.stats_out[2] = (double)arg;
       if (a.host_out != nullptr) { a.host_out[kMaxNu] = beta; a.host_out[kMaxNu + 1] = eta; a.host_out[kMaxNu + 2] = (double)arg; }
     } else {
-      tampc_partial& o = a.partial_out[blockIdx.x];
+      tampc_partial& o = a.partial_out[cta];
       o.beta = beta;
       o.eta = eta;
       o.argmin = arg;
@@ -237,6 +243,25 @@ __device__ __forceinline__ void combine_body(const CombineArgs& a) {
 }
 
 __global__ void __launch_bounds__(kCombineThreads) combine_kernel(const CombineArgs a) { combine_body(a); }
+
+// Both stages in one launch (n_chunks <= kCombineThreads): every CTA writes its partial; the last one to finish
+// (device-scope ticket) merges them.  Saves a launch and the merge kernel's cold start on the latency path of a command.
+template <int NU>
+__global__ void __launch_bounds__(kCombineThreads) partials_combine_kernel(const ReduceArgs r, const CombineArgs c, unsigned int* ticket) {
+  __shared__ int s_last;
+  partials_body<NU, kCombineThreads>(r);
+  __threadfence();  // this CTA's partial is visible device-wide before its ticket is
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = t == gridDim.x - 1;
+    if (s_last) *ticket = 0;  // ready for the next command (stream order)
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  combine_body(c);
+}
 
 // ---- multi-GPU exchange over peer memory ---------------------------------------------------------------------
 // The only inter-GPU step of a K-sharded command is ~1 KB per rank.  Instead of an NCCL all-gather
