@@ -34,7 +34,7 @@ TF32_MMA_PEAK_TFLOPS = 278.0  # tools/peaks/mma_peaks mma.sync m16n8k8 tf32
 F16_MMA_PEAK_TFLOPS = 556.0  # tools/peaks/mma_peaks mma.sync m16n8k16 f16
 # DRAM traffic of one rollout launch at K=8192 from the committed ncu capture (the kernel reads its ~45 KB image and
 # the nominal sequence, writes 8*K bytes of costs that stay in L2): compute-bound by four orders of magnitude
-NCU_DRAM_BYTES_PER_LAUNCH = {'tf32x3': 82688}
+NCU_DRAM_BYTES_PER_LAUNCH = {'tf32x3': 82944, 'f16x3': 70912}
 
 
 # The driver's line is the default workload (BASELINE.json configs[1]).  The others exist to put the remaining configs
