@@ -115,6 +115,27 @@ def cpu_reference_step(spec, z, state, U, seed):
     return time.perf_counter() - t0
 
 
+def torch_cuda_f64_comparator(spec, z, state, U, steps=3):
+    """Secondary comparator: the reference's eager float64 torch op sequence with its tensors on the
+    GPU — what the authors actually ran (tampc/util.py:8 get_device()).  Same oracle port, device 'cuda'."""
+    import torch
+    from oracle import mppi_oracle as O
+    O.DEVICE = 'cuda'
+    try:
+        times = []
+        for i in range(steps + 1):
+            noise = O.sample_noise(spec, 300 + i)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = O.command(spec, torch.from_numpy(state), U, noise)
+            float(out['action'][0])  # the D2H read of the action, like MPC.command's u.cpu().numpy()
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        return float(np.mean(times[1:]))
+    finally:
+        O.DEVICE = 'cpu'
+
+
 def cpu_sample_K(workload):
     """Sample count of one CPU command: the workload's own K per GPU, bounded so that a command stays ~0.1-0.5 s."""
     w = WORKLOADS[workload]
@@ -320,6 +341,7 @@ def main():
         cpu_reference_step(spec_c, zc, state, Uc, 1)
         cpu_t = [cpu_reference_step(spec_c, zc, state, Uc, 2 + i) for i in range(args.cpu_steps)]
         cpu_val = Kc * T / float(np.mean(cpu_t))
+        cuda_t = torch_cuda_f64_comparator(spec_c, zc, state, Uc) if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
@@ -339,7 +361,11 @@ def main():
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "{} commands of K={} T={} (oracle/mppi_oracle.py, torch float64, M=1)".format(
-                                 args.cpu_steps, Kc, T)},
+                                 args.cpu_steps, Kc, T),
+                             "torch_cuda_f64": None if cuda_t is None else {
+                                 "value": Kc * T / cuda_t, "unit": UNIT, "ms_per_command": 1e3 * cuda_t,
+                                 "note": "secondary comparator: the same eager float64 torch op sequence with its tensors "
+                                         "on this GPU (what the reference's authors ran), 3 commands"}},
             "wall_s_timed_region": wall,
         }
         print(json.dumps(line), flush=True)

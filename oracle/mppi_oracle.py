@@ -24,10 +24,15 @@ import torch
 from tampc_b200 import spec as S
 
 DT = torch.float64
+# Where the oracle's tensors live.  'cpu' everywhere except bench.py's secondary comparator, which re-times the same
+# eager float64 op sequence on the GPU — what the reference's authors actually ran (tampc/util.py:8 get_device()).
+DEVICE = 'cpu'
 
 
 def _t(a):
-    return torch.as_tensor(np.asarray(a), dtype=DT)
+    if torch.is_tensor(a):
+        return a.to(device=DEVICE, dtype=DT)
+    return torch.as_tensor(np.asarray(a), dtype=DT, device=DEVICE)
 
 
 def _leaky(x, slope):
@@ -85,13 +90,13 @@ def gp_posterior(d: S.DynamicsSpec, z):
     the nominal network (online_model.py:295-302)."""
     g = d.gp
     X, resid = _t(g.X), _t(g.resid)  # resid = y - m(X), the targets minus the mean function at the training inputs
-    mean = torch.zeros(z.shape[0], resid.shape[1], dtype=DT)
+    mean = torch.zeros(z.shape[0], resid.shape[1], dtype=DT, device=z.device)
     var = torch.zeros_like(mean)
     d2_xx = torch.cdist(X, X).square()
     d2_zx = (z.unsqueeze(1) - X.unsqueeze(0)).square().sum(-1)
     for k in range(resid.shape[1]):
         l2, s, n = float(g.lengthscale[k]) ** 2, float(g.outputscale[k]), float(g.noise[k])
-        Kxx = s * torch.exp(-0.5 * d2_xx / l2) + n * torch.eye(X.shape[0], dtype=DT)
+        Kxx = s * torch.exp(-0.5 * d2_xx / l2) + n * torch.eye(X.shape[0], dtype=DT, device=X.device)
         Kzx = s * torch.exp(-0.5 * d2_zx / l2)
         L = torch.linalg.cholesky(Kxx)
         alpha = torch.cholesky_solve(resid[:, k:k + 1], L)
@@ -197,7 +202,7 @@ def qr_cost(c: S.CostSpec, X, U=None, terminal=False):
 
 def trap_cost(c: S.CostSpec, X, U=None, terminal=False):
     """TrapSetCost (cost.py:154-189) with MPC._trap_cost_reduce (controller.py:245-246)."""
-    total = torch.zeros(X.shape[0], dtype=DT)
+    total = torch.zeros(X.shape[0], dtype=DT, device=X.device)
     if len(c.trap_x) == 0:
         return total
     costs = []
@@ -218,7 +223,7 @@ def trap_cost(c: S.CostSpec, X, U=None, terminal=False):
 def recovery_cost(c: S.CostSpec, X):
     """GoalSetCost with min_cost inside ComposeCost(weights) (cost.py:114-147,65-66,213-235;
     online_controller.py:370-396)."""
-    total = torch.zeros(X.shape[0], dtype=DT)
+    total = torch.zeros(X.shape[0], dtype=DT, device=X.device)
     for G, w in zip(c.goal_sets, c.set_weights):
         per_goal = []
         for g in G:
@@ -243,7 +248,7 @@ def terminal_cost(c: S.CostSpec, X_last):
     """MPC._terminal_cost = multiplier * cost(x_T, terminal=True) (controller.py:251-259); None -> skipped
     (controller.py:376)."""
     if c.kind == S.COST_RECOVERY or c.terminal_multiplier is None:
-        return torch.zeros(X_last.shape[0], dtype=DT)
+        return torch.zeros(X_last.shape[0], dtype=DT, device=X_last.device)
     cost = qr_cost(c, X_last, None, terminal=True)
     if c.use_trap_cost:
         cost = cost + trap_cost(c, X_last, None, terminal=True)
@@ -261,8 +266,8 @@ def rollout_costs_replicated(spec: S.RolloutSpec, state, perturbed_actions, gp_e
     K, T, nu = perturbed_actions.shape
     M = s.rollout_samples
     x = _t(state).view(1, -1).repeat(M * K, 1)
-    cost_samples = torch.zeros(M, K, dtype=DT)
-    cost_var = torch.zeros(K, dtype=DT)
+    cost_samples = torch.zeros(M, K, dtype=DT, device=DEVICE)
+    cost_var = torch.zeros(K, dtype=DT, device=DEVICE)
     states = []
     for t in range(T):
         u = perturbed_actions[:, t].repeat(M, 1)
@@ -288,7 +293,7 @@ def rollout_costs(spec: S.RolloutSpec, state, perturbed_actions, return_states=F
         return rollout_costs_replicated(spec, state, perturbed_actions, gp_eps, return_states)
     K, T, nu = perturbed_actions.shape
     x = _t(state).view(1, -1).repeat(K, 1)
-    total = torch.zeros(K, dtype=DT)
+    total = torch.zeros(K, dtype=DT, device=DEVICE)
     states = []
     for t in range(T):
         x, u_seen = apply_dynamics(spec.dynamics, x, perturbed_actions[:, t])
@@ -363,7 +368,7 @@ def sample_noise(spec: S.RolloutSpec, seed, K=None, T=None):
     K = s.K if K is None else K
     T = s.T if T is None else T
     g = torch.Generator().manual_seed(seed)
-    eps = torch.randn(K, T, s.nu, dtype=DT, generator=g)
+    eps = _t(torch.randn(K, T, s.nu, dtype=DT, generator=g))  # drawn on the host stream, then placed on DEVICE
     return _t(s.noise_mu) + eps @ _t(s.noise_chol).T
 
 

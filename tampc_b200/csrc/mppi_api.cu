@@ -113,6 +113,7 @@ struct tampc_mppi {
   bool gp_eps_armed = false;
   int gp_eps_T = 0;
   uint64_t gp_aux_calls = 0;
+  bool tail_exchanged = false;  // the last fused tail also did the peer exchange
 };
 
 namespace {
@@ -691,6 +692,13 @@ CombineArgs base_combine_args(tampc_mppi* h) {
   return c;
 }
 
+ExchangeArgs make_exchange_args(tampc_mppi* h);
+
+template <int NU>
+void launch_partials_exchange(const ReduceArgs& r, const CombineArgs& c, const ExchangeArgs& e, unsigned int* ticket, int n_chunks, cudaStream_t s) {
+  partials_exchange_kernel<NU><<<n_chunks, kCombineThreads, 0, s>>>(r, c, e, ticket);
+}
+
 template <int NU>
 void launch_partials_combine(const ReduceArgs& r, const CombineArgs& c, unsigned int* ticket, int n_chunks, cudaStream_t s) {
   partials_combine_kernel<NU><<<n_chunks, kCombineThreads, 0, s>>>(r, c, ticket);
@@ -705,6 +713,11 @@ void launch_partials(const ReduceArgs& r, int n_chunks, cudaStream_t s) {
 // caller whether the softmax update already happened inside the rollout launch (small-K tensor-core kernels) or the
 // CTA partials are waiting in d_partials for run_combine.
 int run_rollout_and_partials(tampc_mppi* h, int mode, bool keep_states, int fuse, tampc_partial* partial_out, bool* done) {
+  // fuse = 3: like 2 (rank partial), and the peer exchange + world merge join the same launch when the fused tail applies
+  // (h->tail_exchanged tells the caller whether they did)
+  const bool want_exchange = fuse == 3;
+  if (want_exchange) fuse = 2;
+  h->tail_exchanged = false;
   const int T = h->T;
   const double* U = h->d_U[h->cur];
   h->call++;
@@ -732,6 +745,28 @@ int run_rollout_and_partials(tampc_mppi* h, int mode, bool keep_states, int fuse
   r.nu = h->cfg.nu;
   r.partials = h->d_partials;
   // latency path: both reduction stages in one launch while a single merging CTA suffices (TAMPC_FUSE_TAIL=0: separate)
+  if (want_exchange && h->n_chunks <= kCombineThreads && env_int("TAMPC_FUSE_TAIL", 1)) {
+    CombineArgs c = base_combine_args(h);
+    c.partials = h->d_partials;
+    c.n_partials = h->n_chunks;
+    c.group = h->n_chunks;
+    c.solo = 1;
+    c.finalize = 0;
+    c.partial_out = h->d_rank_partial;
+    const ExchangeArgs e = make_exchange_args(h);
+    switch (h->cfg.nu) {
+      case 1: launch_partials_exchange<1>(r, c, e, h->d_ticket, h->n_chunks, h->stream); break;
+      case 2: launch_partials_exchange<2>(r, c, e, h->d_ticket, h->n_chunks, h->stream); break;
+      case 3: launch_partials_exchange<3>(r, c, e, h->d_ticket, h->n_chunks, h->stream); break;
+      default: launch_partials_exchange<4>(r, c, e, h->d_ticket, h->n_chunks, h->stream); break;
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    h->cur ^= 1;
+    h->tail_exchanged = true;
+    *done = true;
+    return TAMPC_OK;
+  }
   if (fuse && h->n_chunks <= kCombineThreads && env_int("TAMPC_FUSE_TAIL", 1)) {
     CombineArgs c = base_combine_args(h);
     c.partials = h->d_partials;
@@ -807,7 +842,7 @@ int run_combine(tampc_mppi* h, const tampc_partial* partials, int n, int finaliz
 size_t comm_parity_bytes(int world) { return (sizeof(tampc_partial) * world + sizeof(unsigned long long) * kMaxRanks + 255) & ~size_t(255); }
 
 // exchange + merge in one kernel (reduce_kernels.cuh exchange_combine_kernel); this rank's partial is in d_rank_partial
-int run_exchange_combine(tampc_mppi* h) {
+ExchangeArgs make_exchange_args(tampc_mppi* h) {
   ExchangeArgs e{};
   e.c.sampler = h->d_sampler;
   e.c.U = h->d_U[h->cur];
@@ -832,6 +867,11 @@ int run_exchange_combine(tampc_mppi* h) {
     e.peer_slots[p] = reinterpret_cast<tampc_partial*>(h->comm_peer[p] + off);
     e.peer_flags[p] = reinterpret_cast<unsigned long long*>(h->comm_peer[p] + off + sizeof(tampc_partial) * h->comm_world);
   }
+  return e;
+}
+
+int run_exchange_combine(tampc_mppi* h) {
+  const ExchangeArgs e = make_exchange_args(h);
   exchange_combine_kernel<<<1, kCombineThreads, 0, h->stream>>>(e);
   CUDA_TRY(h, cudaGetLastError());
   h->launches++;
@@ -1375,9 +1415,9 @@ TAMPC_API int tampc_mppi_command(tampc_mppi* h, const double* state, int32_t noi
   bool done = false;
   if (h->comm_connected) {
     // K-sharded: rank partial (fused into the rollout or via the partial kernels), then exchange + merge in one kernel
-    if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/2, h->d_rank_partial, &done))) return rc;
+    if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/3, h->d_rank_partial, &done))) return rc;
     if (!done && (rc = run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/0, h->d_rank_partial))) return rc;
-    if ((rc = run_exchange_combine(h))) return rc;
+    if (!h->tail_exchanged && (rc = run_exchange_combine(h))) return rc;
     rc = download_action(h, action);
     if (rc == TAMPC_OK && h->h_map[kMaxNu + 3] < 0.0) {
       h->h_map[kMaxNu + 3] = 0.0;
@@ -1448,9 +1488,9 @@ TAMPC_API int tampc_mppi_command_resident(tampc_mppi* h, int32_t noise_mode) {
   if (noise_mode != kModePhilox && !h->d_noise) { h->err = "resident command with injected noise needs a previous upload"; return TAMPC_ERR_STATE; }
   bool done = false;
   if (h->comm_connected) {
-    if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/2, h->d_rank_partial, &done))) return rc;
+    if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/3, h->d_rank_partial, &done))) return rc;
     if (!done && (rc = run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/0, h->d_rank_partial))) return rc;
-    return run_exchange_combine(h);
+    return h->tail_exchanged ? TAMPC_OK : run_exchange_combine(h);
   }
   if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/1, nullptr, &done))) return rc;
   if (done) return TAMPC_OK;

@@ -289,7 +289,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-__global__ void __launch_bounds__(kCombineThreads) exchange_combine_kernel(const ExchangeArgs e) {
+__device__ __forceinline__ void exchange_body(const ExchangeArgs& e) {
   __shared__ int s_fail;
   const int tid = threadIdx.x;
   const int nw = e.c.T * e.c.nu;
@@ -331,7 +331,33 @@ __global__ void __launch_bounds__(kCombineThreads) exchange_combine_kernel(const
   c.partials = e.peer_slots[e.rank];
   c.n_partials = e.world;
   c.group = e.world;
+  c.solo = 1;
   combine_body(c);
+}
+
+__global__ void __launch_bounds__(kCombineThreads) exchange_combine_kernel(const ExchangeArgs e) { exchange_body(e); }
+
+// K-sharded latency path in one launch: chunk partials -> (last CTA) this rank's merged partial -> peer exchange ->
+// world merge.  `c_rank` must write its merged partial to e.mine.
+template <int NU>
+__global__ void __launch_bounds__(kCombineThreads) partials_exchange_kernel(const ReduceArgs r, const CombineArgs c_rank, const ExchangeArgs e,
+                                                                            unsigned int* ticket) {
+  __shared__ int s_last;
+  partials_body<NU, kCombineThreads>(r);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = t == gridDim.x - 1;
+    if (s_last) *ticket = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  combine_body(c_rank);
+  __threadfence();  // the rank partial written by every thread is visible before any thread forwards it
+  __syncthreads();
+  exchange_body(e);
 }
 
 // ExperimentalMPPI.perturbed_action (K, T, nu), regenerated on request (tampc/env/pybullet_sim.py:127 reads it)
