@@ -248,38 +248,43 @@ def gp_desc(gp, sampler: S.SamplerSpec):
     return d, pb.array()
 
 
+def _fill(carray, values):
+    """Copy a float64 numpy array into the leading entries of a (possibly nested) ctypes double array."""
+    a = np.ascontiguousarray(values, dtype=np.float64)
+    C.memmove(carray, a.ctypes.data, a.nbytes)
+
+
+def _padded(a, shape):
+    out = np.zeros(shape)
+    out[tuple(slice(0, n) for n in a.shape)] = a
+    return out
+
+
 def cost_desc(c: S.CostSpec):
     d = CostDesc()
     d.kind, d.nx, d.nu = c.kind, c.nx, c.nu
     d.ang_mask, d.usim_mask = _mask(c.ang_dims), _mask(c.usim_dims)
-    for i in range(c.nx):
-        d.dist_scale[i] = c.dist_scale[i]
+    _fill(d.dist_scale, c.dist_scale)
     if c.kind == S.COST_GOAL_TRAP:
-        for i in range(c.nx):
-            d.goal[i] = c.goal[i]
-            for j in range(c.nx):
-                d.Q[i * MAX_NX + j] = c.Q[i, j]
-        for i in range(c.nu):
-            for j in range(c.nu):
-                d.R[i * MAX_NU + j] = c.R[i, j]
+        _fill(d.goal, c.goal)
+        _fill(d.Q, _padded(c.Q, (MAX_NX, MAX_NX)))
+        _fill(d.R, _padded(c.R, (MAX_NU, MAX_NU)))
         d.use_trap_cost = int(c.use_trap_cost)
         d.n_traps = len(c.trap_x)
-        for p in range(len(c.trap_x)):
-            for i in range(c.nx):
-                d.trap_x[p][i] = c.trap_x[p, i]
-            for i in range(c.nu):
-                d.trap_u[p][i] = c.trap_u[p, i]
+        if d.n_traps:
+            _fill(d.trap_x, _padded(c.trap_x, (d.n_traps, MAX_NX)))
+            _fill(d.trap_u, _padded(c.trap_u, (d.n_traps, MAX_NU)))
         d.trap_weight = c.trap_weight
         d.has_terminal = int(c.terminal_multiplier is not None)
         d.terminal_multiplier = c.terminal_multiplier if c.terminal_multiplier is not None else 0.0
     else:
         d.n_sets = len(c.goal_sets)
+        sets = np.zeros((MAX_GOAL_SETS, MAX_SET_GOALS, MAX_NX))
         for j, (g, w) in enumerate(zip(c.goal_sets, c.set_weights)):
             d.set_size[j] = len(g)
             d.set_weight[j] = w
-            for k in range(len(g)):
-                for i in range(c.nx):
-                    d.set_goals[j][k][i] = g[k, i]
+            sets[j, :len(g), :c.nx] = g
+        _fill(d.set_goals, sets)
         d.recovery_scale = c.recovery_scale
     return d
 

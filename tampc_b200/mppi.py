@@ -114,6 +114,7 @@ class B200MPPI:
                 if exchange == 'p2p':
                     raise
         self._last_noise = None
+        self._cost_fp = None
         self._cost_cache = None
         self._probe_cache = {}
 
@@ -195,9 +196,41 @@ class B200MPPI:
         goal, recovery sets / MAB weights: online_controller.py:353,400-402,416-418,461-478)."""
         if self._ctrl is None:
             return
-        cost = extract.cost_from_controller(self._ctrl, self.running_cost, self.terminal_state_cost)
-        self.set_cost(cost)
+        fp = self._cost_fingerprint()
+        if fp != self._cost_fp:
+            cost = extract.cost_from_controller(self._ctrl, self.running_cost, self.terminal_state_cost)
+            self.set_cost(cost)
+            self._cost_fp = fp
         self._refresh_dynamics_from_controller()
+
+    def _cost_fingerprint(self):
+        """Everything the cost program is built from, cheap to compare (object identities, in-place version counters,
+        the few scalars): when it is unchanged since the last command the extraction, the descriptor and the device
+        update (~0.2 ms of host time) are skipped."""
+        c = self._ctrl
+        rc, tc = self.running_cost, self.terminal_state_cost
+        gc = c.goal_cost
+        goal = gc.goal
+        fp = [id(getattr(rc, '__func__', rc)), id(getattr(rc, '__self__', None)), id(getattr(tc, '__func__', tc)),
+              id(gc.Q), getattr(gc.Q, '_version', 0), id(gc.R), getattr(gc.R, '_version', 0),
+              None if goal is None else (id(goal), getattr(goal, '_version', 0)),
+              float(c.terminal_cost_multiplier), id(getattr(c, 'trap_cost', None))]
+        traps = c.trap_set
+        if len(traps):
+            tw = c.trap_set_weight
+            fp.append(float(tw.reshape(-1)[0]) if (torch.is_tensor(tw) or isinstance(tw, np.ndarray)) else float(tw))
+            fp.extend((id(x), getattr(x, '_version', 0), id(u), getattr(u, '_version', 0)) for x, u in traps)
+        rcost = getattr(c, 'recovery_cost', None)
+        if rcost is not None:
+            fp.append(id(rcost))
+            w = getattr(rcost, 'weights', None)
+            if w is not None:
+                w = w() if callable(w) else w
+                fp.append(tuple(torch.as_tensor(w).reshape(-1).tolist()))
+            for gs in (list(rcost.fn) if hasattr(rcost, 'fn') else [rcost]):
+                g = gs.goal_set
+                fp.append((id(g), getattr(g, '_version', 0), len(g), float(gs.scale)))
+        return fp
 
     def _refresh_dynamics_from_controller(self):
         """The nominal model object can be swapped between commands (use_temp_local_nominal_model /
