@@ -329,8 +329,8 @@ def main():
                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.precision) if args.workload == 'push' else None,
                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, one "
                                           "ncu --set full capture (profiles/r1c_rollout_split_tf32x3_k8192_ncu_summary.txt)",
-                        "kernel": "rollout (fused K x T): rollout_mma_split_kernel at this K (two warps per 16-sample "
-                                  "tile), rollout_mma_kernel above K=12288",
+                        "kernel": "rollout (fused K x T): rollout_mma_split_kernel at this K (three warps per 16-sample "
+                                  "tile: chain | decoder | cost), rollout_mma_kernel above K=12288",
                         "kernel_ms": roll_ms, "algorithmic_flop_per_launch": K * T * flop_per_step,
                         "peak_source": src}
         # CPU baseline: bounded sample of the same workload on the host cores (oracle port, float64)

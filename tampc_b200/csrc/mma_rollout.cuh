@@ -720,8 +720,12 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volati
 
 static __device__ unsigned int g_sm_turn[1024];  // per-SM CTA counter (never reset: only its parity is used)
 
-template <class Model>
-__global__ void __launch_bounds__(128) rollout_mma_split_kernel(const RolloutArgs a) {
+// ROLES = 2: chain | decoder + cost.  ROLES = 3: chain | decoder | cost — for K small enough that every warp has a
+// sub-partition to itself (<= 2 tiles per SM), where the decoder + cost warp is the longer of the two (measured at
+// K=512: 64 us, 48 us without the cost); the cost warp joins both hand-offs so that nobody can run a step ahead of it.
+template <class Model, int ROLES>
+__global__ void __launch_bounds__(64 * ROLES) rollout_mma_split_kernel(const RolloutArgs a) {
+  static_assert(ROLES == 2 || ROLES == 3, "two or three warps per tile");
   static_assert(sizeof(typename Model::T) == 4, "role-split variant is for the float32 tensor policies");
   static_assert(Model::NX < 8, "xc rows keep the bad flag in column NX");
   using P = typename Model::Policy;
@@ -734,7 +738,8 @@ __global__ void __launch_bounds__(128) rollout_mma_split_kernel(const RolloutArg
   CostS<float, float>& cs = *reinterpret_cast<CostS<float, float>*>(smem_raw + L::kCost);
   SamplerS<float>& sp = *reinterpret_cast<SamplerS<float>*>(smem_raw + L::kSampler);
   float* Ush = reinterpret_cast<float*>(smem_raw + L::kU);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = warp >> 1;
+  constexpr int NTHR = 64 * ROLES, BARN = 32 * ROLES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = warp / ROLES, role0 = warp % ROLES;
   const int T = a.src.T;
   unsigned char* tbase = smem_raw + L::tiles_off(T) + (size_t)tile * L::tile_bytes(T);
   float* xs = reinterpret_cast<float*>(tbase + L::kXs);      // [SW][8] the step's network input rows (x_t | u_t | 0), zero if guarded
@@ -744,13 +749,13 @@ __global__ void __launch_bounds__(128) rollout_mma_split_kernel(const RolloutArg
   float* upre = reinterpret_cast<float*>(tbase + L::kUpre);  // [T][SW][NU] actions the dynamics sees
   float* pcs = reinterpret_cast<float*>(tbase + L::pcs_off(T));  // [T][SW] perturbation cost of (t, sample) (controller.py:395,400)
   {
-    copy_image_async(smem_raw, a.image, (int)L::kU, tid, 128);
+    copy_image_async(smem_raw, a.image, (int)L::kU, tid, NTHR);
     if (tid == 0) {
       unsigned int smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       s_flip = atomicAdd(&g_sm_turn[smid & 1023u], 1u) & 1u;
     }
-    for (int i = tid; i < T * NU; i += 128) {
+    for (int i = tid; i < T * NU; i += NTHR) {
       int t = i / NU, d = i % NU, ts = t + a.shift;
       Ush[t * kMaxNu + d] = (float)(ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d]);
     }
@@ -762,9 +767,9 @@ __global__ void __launch_bounds__(128) rollout_mma_split_kernel(const RolloutArg
   const bool live = kbase + row < a.K_local;
   const int k = live ? kbase + row : a.K_local - 1;
   if (kbase < a.K_local) {
-    // every perturbed action of the horizon, drawn by the tile's 64 threads (independent items)
+    // every perturbed action of the horizon, drawn by the tile's threads (independent items)
 #pragma unroll 5
-    for (int item = tid & 63; item < T * SW; item += 64) {
+    for (int item = tid - tile * BARN; item < T * SW; item += BARN) {
       const int t = item / SW, r = item % SW;
       float u[NU], npost[NU];
       pcs[item] = sample_action<float, NU>(a.src, sp, Ush + t * kMaxNu, min(kbase + r, a.K_local - 1), t, u, npost);
@@ -776,8 +781,10 @@ __global__ void __launch_bounds__(128) rollout_mma_split_kernel(const RolloutArg
   if (kbase >= a.K_local) return;  // (no block-wide barrier below)
   const int bar_x = 1 + 2 * tile, bar_c = 2 + 2 * tile;
   const float slope = (float)a.slope;
+  // two roles: CTAs sharing an SM alternate them, so that every sub-partition gets one chain and one decoder warp
+  const int role = ROLES == 2 ? (int)((role0 ^ s_flip) & 1u) : role0;
 
-  if (((warp ^ s_flip) & 1u) == 0) {
+  if (role == 0) {
     // ================= warp A: encoder + latent dynamics + state update (the recurrence)
     const float bad2 = (float)(a.bad_norm * a.bad_norm);
     const float* d0 = reinterpret_cast<const float*>(w + Model::kOffD0);
@@ -814,7 +821,7 @@ __global__ void __launch_bounds__(128) rollout_mma_split_kernel(const RolloutArg
         reinterpret_cast<float4*>(c)[1] = make_float4(cv[4], cv[5], cv[6], cv[7]);
       }
       __syncwarp();
-      named_bar_arrive(bar_x, 64);
+      named_bar_arrive(bar_x, BARN);
     };
     publish(0);
 #pragma unroll 1
@@ -830,7 +837,7 @@ __global__ void __launch_bounds__(128) rollout_mma_split_kernel(const RolloutArg
       PROF(3);
       store_blocks<P, 1, 1, 8>(vs, v, 0, lane);
       __syncwarp();
-      named_bar_sync(bar_c, 64);  // Cs holds C_t
+      named_bar_sync(bar_c, BARN);  // Cs holds C_t (and, with a cost warp, it has read the rows of step t)
       PROF(0);
       const float* cr = Cs + row * CS;
       const float* vr = vs + row * 8;
@@ -848,9 +855,23 @@ __global__ void __launch_bounds__(128) rollout_mma_split_kernel(const RolloutArg
       publish(t + 1);
       PROF(4);
     }
+  } else if (ROLES == 3 && role == 1) {
+    // ================= warp B (three roles): decoder only
+#pragma unroll 1
+    for (int t = 0; t <= T; ++t) {
+      named_bar_sync(bar_x, BARN);
+      if (t < T) {
+        float in[1][1][P::R], C[1][CO8][P::R];
+        load_blocks<P, 1, 1, 8>(xs, in, lane);
+        Model::Dec::template eval<1>(w + Model::kOffDec, in, C, slope, lane);
+        store_blocks<P, 1, CO8, CS>(Cs, C, 0, lane);
+        __syncwarp();
+        named_bar_arrive(bar_c, BARN);
+      }
+    }
   } else {
-    // ================= warp B: decoder, then the cost of the step that just finished (two lanes per sample share
-    // the trap-set terms)
+    // ================= warp B (two roles): decoder, then the cost of the step that just finished; warp C (three
+    // roles): the cost alone.  Two lanes per sample share the trap-set terms.
     double cost = 0.0;
     float pert = 0.f;
     float x[NX], useen[NU];
@@ -859,19 +880,21 @@ __global__ void __launch_bounds__(128) rollout_mma_split_kernel(const RolloutArg
 #pragma unroll 1
     for (int t = 0; t <= T; ++t) {
       PROF_T0();
-      named_bar_sync(bar_x, 64);  // xs / xc hold step t
+      named_bar_sync(bar_x, BARN);  // xs / xc hold step t
       PROF(7);
       const float* c = xc + row * 8;
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = c[i];
       const bool bad = c[NX] != 0.f;
       if (t < T) {
-        float in[1][1][P::R], C[1][CO8][P::R];
-        load_blocks<P, 1, 1, 8>(xs, in, lane);
-        Model::Dec::template eval<1>(w + Model::kOffDec, in, C, slope, lane);
-        store_blocks<P, 1, CO8, CS>(Cs, C, 0, lane);
-        __syncwarp();
-        named_bar_arrive(bar_c, 64);
+        if (ROLES == 2) {
+          float in[1][1][P::R], C[1][CO8][P::R];
+          load_blocks<P, 1, 1, 8>(xs, in, lane);
+          Model::Dec::template eval<1>(w + Model::kOffDec, in, C, slope, lane);
+          store_blocks<P, 1, CO8, CS>(Cs, C, 0, lane);
+        }
+        __syncwarp();  // (three roles: every lane holds its row of step t before the chain warp may overwrite it)
+        named_bar_arrive(bar_c, BARN);
       }
       PROF(6);
       if (t > 0) {
@@ -899,9 +922,9 @@ __global__ void __launch_bounds__(128) rollout_mma_split_kernel(const RolloutArg
   }
 }
 
-template <class Model>
+template <class Model, int ROLES = 2>
 cudaError_t launch_rollout_mma_split(const RolloutArgs& a, int /*block*/, cudaStream_t stream) {
-  auto kern = rollout_mma_split_kernel<Model>;
+  auto kern = rollout_mma_split_kernel<Model, ROLES>;
   using L = SplitSmem<Model>;
   const size_t smem = L::bytes(a.src.T);
   static size_t configured = 0;
@@ -912,7 +935,7 @@ cudaError_t launch_rollout_mma_split(const RolloutArgs& a, int /*block*/, cudaSt
   }
   const int per_block = L::TILES * L::SW;
   const int grid = (a.K_local + per_block - 1) / per_block;
-  kern<<<grid, 128, smem, stream>>>(a);
+  kern<<<grid, 64 * ROLES, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -532,8 +532,13 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
       const int split_env = env_int("TAMPC_SPLIT", -1);
       const bool split = !big && (split_env >= 0 ? split_env != 0 : (K + 15) / 16 <= 5 * 148 + 28);
       if (!f64 && idx == 0 && fsplit && split && en == 0) {
-        p.fn = fsplit;
-        p.block = 128;
+        // a third warp takes the cost off the decoder warp.  Measured on B200 (push, T=40, 3xTF32): K=500 64 -> 60 us,
+        // 4736 67.5 -> 64, 8192 86.9 -> 77.2, 12288 117 -> 117 (peg K=8192, T=10: 27.9 -> 23.8).  TAMPC_SPLIT3=0/1 forces.
+        const rollout_launch_fn fsplit3 = f16 ? v->f16_split3 : v->tf32_split3;
+        const int s3_env = env_int("TAMPC_SPLIT3", -1);
+        const bool three = fsplit3 && (s3_env >= 0 ? s3_env != 0 : true);
+        p.fn = three ? fsplit3 : fsplit;
+        p.block = three ? 192 : 128;
         p.fuse_warps = 0;
         return p;
       }

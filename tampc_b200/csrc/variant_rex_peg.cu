@@ -8,6 +8,8 @@ const ModelVariant* variant_rex_peg() {
     m.tf32_split = &launch_rollout_mma_split<ModelRexMma<PolicyTF32x3, 5, 2, 16, 32, 5, 32, 32, 5, 16, 32>>;
     add_f16<ModelRexMma<PolicyF16x3, 5, 2, 16, 32, 5, 32, 32, 5, 16, 32>>(m);
     m.f16_split = &launch_rollout_mma_split<ModelRexMma<PolicyF16x3, 5, 2, 16, 32, 5, 32, 32, 5, 16, 32>>;
+    m.tf32_split3 = &launch_rollout_mma_split<ModelRexMma<PolicyTF32x3, 5, 2, 16, 32, 5, 32, 32, 5, 16, 32>, 3>;
+    m.f16_split3 = &launch_rollout_mma_split<ModelRexMma<PolicyF16x3, 5, 2, 16, 32, 5, 32, 32, 5, 16, 32>, 3>;
     m.gp = gp_launchers_rex_peg();
     return m;
   }();

@@ -22,6 +22,7 @@ struct ModelVariant {
   // 3xFP16 (mma.sync.m16n8k16.f16): same kernels, half the tensor instructions
   int bytes_mma_f16;
   rollout_launch_fn f16_mma[2], f16_mma_wide, f16_split;
+  rollout_launch_fn tf32_split3, f16_split3;  // three warps per tile (chain | decoder | cost): K with <= 2 tiles per SM
   rollout_launch_fn tf32_split;   // two warps per 16-sample tile, split by role (RexExtract shapes, latency-bound K)
   rollout_launch_fn tf32_pipe;    // two-warp pipelined 3xTF32 kernel for small K (16 samples per CTA)  // 3xTF32 kernels, NM = 1, 2 (16, 32 samples per warp); float32 state and cost terms, float64 cost sum
 };
