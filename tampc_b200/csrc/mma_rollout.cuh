@@ -739,15 +739,8 @@ __global__ void __launch_bounds__(64 * ROLES) rollout_mma_split_kernel(const Rol
   SamplerS<float>& sp = *reinterpret_cast<SamplerS<float>*>(smem_raw + L::kSampler);
   float* Ush = reinterpret_cast<float*>(smem_raw + L::kU);
   constexpr int NTHR = 64 * ROLES, BARN = 32 * ROLES;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tile = warp / ROLES, role0 = warp % ROLES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = a.src.T;
-  unsigned char* tbase = smem_raw + L::tiles_off(T) + (size_t)tile * L::tile_bytes(T);
-  float* xs = reinterpret_cast<float*>(tbase + L::kXs);      // [SW][8] the step's network input rows (x_t | u_t | 0), zero if guarded
-  float* xc = reinterpret_cast<float*>(tbase + L::kXc);      // [SW][8] the state the cost sees + the guard flag of the step
-  float* vs = reinterpret_cast<float*>(tbase + L::kVs);      // [SW][8] latent output v_t (private to warp A)
-  float* Cs = reinterpret_cast<float*>(tbase + L::kCs);      // [SW][CS] decoder output C_t
-  float* upre = reinterpret_cast<float*>(tbase + L::kUpre);  // [T][SW][NU] actions the dynamics sees
-  float* pcs = reinterpret_cast<float*>(tbase + L::pcs_off(T));  // [T][SW] perturbation cost of (t, sample) (controller.py:395,400)
   {
     copy_image_async(smem_raw, a.image, (int)L::kU, tid, NTHR);
     if (tid == 0) {
@@ -762,6 +755,16 @@ __global__ void __launch_bounds__(64 * ROLES) rollout_mma_split_kernel(const Rol
     copy_image_wait();
   }
   __syncthreads();
+  // (Three roles: reversing the (tile, role) order in every second CTA of an SM was measured and is WORSE — K=8192
+  // 77 -> 97 us: six-warp CTAs already spread their chain warps over the sub-partitions.)
+  const int tile = warp / ROLES, role0 = warp % ROLES;
+  unsigned char* tbase = smem_raw + L::tiles_off(T) + (size_t)tile * L::tile_bytes(T);
+  float* xs = reinterpret_cast<float*>(tbase + L::kXs);      // [SW][8] the step's network input rows (x_t | u_t | 0), zero if guarded
+  float* xc = reinterpret_cast<float*>(tbase + L::kXc);      // [SW][8] the state the cost sees + the guard flag of the step
+  float* vs = reinterpret_cast<float*>(tbase + L::kVs);      // [SW][8] latent output v_t (private to warp A)
+  float* Cs = reinterpret_cast<float*>(tbase + L::kCs);      // [SW][CS] decoder output C_t
+  float* upre = reinterpret_cast<float*>(tbase + L::kUpre);  // [T][SW][NU] actions the dynamics sees
+  float* pcs = reinterpret_cast<float*>(tbase + L::pcs_off(T));  // [T][SW] perturbation cost of (t, sample) (controller.py:395,400)
   const int kbase = (blockIdx.x * L::TILES + tile) * SW;
   const int row = lane % SW, part = lane / SW;
   const bool live = kbase + row < a.K_local;
@@ -769,7 +772,7 @@ __global__ void __launch_bounds__(64 * ROLES) rollout_mma_split_kernel(const Rol
   if (kbase < a.K_local) {
     // every perturbed action of the horizon, drawn by the tile's threads (independent items)
 #pragma unroll 5
-    for (int item = tid - tile * BARN; item < T * SW; item += BARN) {
+    for (int item = role0 * 32 + lane; item < T * SW; item += BARN) {
       const int t = item / SW, r = item % SW;
       float u[NU], npost[NU];
       pcs[item] = sample_action<float, NU>(a.src, sp, Ush + t * kMaxNu, min(kbase + r, a.K_local - 1), t, u, npost);
