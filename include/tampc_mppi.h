@@ -50,6 +50,7 @@ extern "C" {
 #define TAMPC_GP_MAX_POINTS 64 /* OnlineGPMixing.max_data_points defaults to 50 (online_model.py:327) */
 #define TAMPC_GP_MAX_DIM 8
 #define TAMPC_MAX_ROLLOUT_SAMPLES 32
+#define TAMPC_GP_FIT_MAX_POINTS 50 /* hyper-parameter fit: OnlineGPMixing.max_data_points (online_model.py:327) */
 
 typedef enum tampc_status {
   TAMPC_OK = 0,
@@ -227,6 +228,15 @@ TAMPC_API int tampc_mppi_set_cost(tampc_mppi* h, const tampc_cost_desc* desc);
 /* online GP residual (replaces OnlineDynamicsModel.predict, online_model.py:67-99, inside the rollout); call after
  * every OnlineGPMixing update (online_model.py:386-410).  desc->n_points == 0 returns to the nominal network. */
 TAMPC_API int tampc_mppi_set_gp(tampc_mppi* h, const tampc_gp_desc* desc, const double* params, size_t n_params);
+/* Hyper-parameter fit of that GP on the device: `iters` Adam steps (lr as given, torch defaults otherwise) on the negative
+ * exact marginal log-likelihood — replaces OnlineGPMixing._fit_params (online_model.py:412-430; 15 iterations per control
+ * step, 150 at a reset).  Handle-free: runs on `device`.  X (n_points, n_in) inputs, resid (n_points, n_out) targets minus
+ * the mean function; raw_params / adam_m / adam_v hold [raw lengthscale[n_out] | raw outputscale[n_out] | raw task
+ * noise[n_out] | raw global noise] (softplus-constrained, noises additionally +1e-4 each: gpytorch's parameterisation) and
+ * are updated in place together with *adam_step; loss_out[0..1] = loss at the last and the last-but-one iteration. */
+TAMPC_API int tampc_gp_fit(int32_t device, int32_t n_points, int32_t n_in, int32_t n_out, const double* X, const double* resid, int32_t iters,
+                           double lr, double* raw_params, double* adam_m, double* adam_v, int64_t* adam_step, double* loss_out);
+TAMPC_API const char* tampc_gp_fit_last_error(void);
 /* standard normals behind the GP draws of the NEXT command / rollout, (num_local, M, T, n_out) float64, instead of the
  * on-device Philox stream (the equivalent of patching Normal.sample in the reference; parity tests).  One-shot. */
 TAMPC_API int tampc_mppi_set_gp_draws(tampc_mppi* h, const double* eps, size_t n);

@@ -143,6 +143,49 @@ def gp_cases():
     save_case('push_gp_local', ctrl, x.tolist(), 43, 'temporary local GP (6 points, original space), M=10, var cost 0.5')
 
 
+def gp_fit_case():
+    """the hyper-parameter trajectory of the reference's OnlineGPMixing (Adam through the restated
+    gpytorch, oracle/shim/gpytorch) — the constructor's 150 iterations on 30 nominal points, then four `update`s of 15
+    iterations each (optimiser state carried over, online_model.py:386-430).  The device fit (tampc_gp_fit) must land
+    on the same raw parameters from the same (inputs, targets - mean function) at every stage."""
+    ref = rh.load_reference()
+    ctrl, ds, env = rh.build_task('push', num_samples=8, rollout_samples=2, horizon=4)
+    with torch.enable_grad():
+        om = ref.hybrid_model.HybridDynamicsModel.get_local_model(
+            env.state_difference, ctrl.dynamics.pm, 'cpu', ds, preprocessor=ref.util.no_tsf_preprocessor(), allow_update=True,
+            train_slice=slice(0, 30))
+    arrays = {}
+
+    def record(stage, iters):
+        with torch.no_grad():
+            mean = om.gp.forward(om.xu).mean
+        arrays['stage{}.X'.format(stage)] = om.xu.detach().numpy().copy()
+        arrays['stage{}.resid'.format(stage)] = (om.y - mean).detach().numpy().copy()
+        arrays['stage{}.iters'.format(stage)] = np.array(iters)
+        arrays['stage{}.raw_lengthscale'.format(stage)] = om.gp.covar_module.base_kernel.raw_lengthscale.detach().numpy().reshape(-1).copy()
+        arrays['stage{}.raw_outputscale'.format(stage)] = om.gp.covar_module.raw_outputscale.detach().numpy().reshape(-1).copy()
+        arrays['stage{}.raw_task_noises'.format(stage)] = om.likelihood.raw_task_noises.detach().numpy().reshape(-1).copy()
+        arrays['stage{}.raw_noise'.format(stage)] = om.likelihood.raw_noise.detach().numpy().reshape(-1).copy()
+        arrays['stage{}.last_loss'.format(stage)] = np.array(om.last_loss)
+
+    record(0, om.training_iter)
+    g = torch.Generator().manual_seed(12)
+    x = t64(PUSH_TRAP[0])
+    for stage in range(1, 5):
+        u = t64(spec_bounds_sample(ctrl, g))
+        nx_ = x + 0.003 * torch.randn(5, dtype=torch.double, generator=g) * t64([1, 1, 1, 50, 50])
+        with torch.enable_grad():
+            om.update(x, u, nx_)
+        x = nx_
+        record(stage, om.training_iter // 10)
+    arrays['n_stages'] = np.array(5)
+    path = os.path.join(OUT, 'gp_fit.npz')
+    np.savez_compressed(path, **arrays)
+    print('gp_fit: N {} -> {}, final loss {:.6f}, lengthscale raw {}  {:.0f} KB'.format(
+        len(arrays['stage0.X']), len(arrays['stage4.X']), float(arrays['stage4.last_loss']), arrays['stage4.raw_lengthscale'].round(3),
+        os.path.getsize(path) / 1024))
+
+
 def spec_bounds_sample(ctrl, g):
     lo, hi = ctrl.u_min.double(), ctrl.u_max.double()
     return (lo + (hi - lo) * torch.rand(lo.shape[0], dtype=torch.double, generator=g)).tolist()
@@ -153,6 +196,8 @@ def main():
     np.random.seed(0)
     if '--gp-only' in sys.argv:
         return gp_cases()
+    if '--gp-fit-only' in sys.argv:
+        return gp_fit_case()
 
     # 1. pushing, nominal cost (QR + 3 traps + terminal x50), M=2
     ctrl, ds, env = rh.build_task('push', num_samples=256, rollout_samples=2)
@@ -253,6 +298,7 @@ def main():
     save_case('pendulum', ctrl, [math.pi, 1.0], 6, 'analytic pendulum, K=100 T=15 M=20 lambda=1, no trap cost')
 
     gp_cases()
+    gp_fit_case()
 
 
 if __name__ == '__main__':

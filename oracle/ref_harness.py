@@ -46,13 +46,14 @@ def load_reference():
     import types
     ns = types.SimpleNamespace()
     from tampc.controller import controller, online_controller, gating_function
-    from tampc.dynamics import model, hybrid_model, prior
+    from tampc.dynamics import model, hybrid_model, prior, online_model
     from tampc.transform import invariant
     from tampc import cost, util, cfg
     from tampc.env import block_push, peg_in_hole, env as env_mod
     from arm_pytorch_utilities import preprocess, load_data, math_utils
     ns.controller, ns.online_controller, ns.gating_function = controller, online_controller, gating_function
     ns.model, ns.hybrid_model, ns.prior, ns.invariant = model, hybrid_model, prior, invariant
+    ns.online_model = online_model
     ns.cost, ns.util, ns.cfg = cost, util, cfg
     ns.block_push, ns.peg_in_hole, ns.env_mod = block_push, peg_in_hole, env_mod
     ns.preprocess, ns.load_data, ns.math_utils = preprocess, load_data, math_utils

@@ -193,3 +193,20 @@ def make_online_gp(spec: S.RolloutSpec, nominal):
     return types.SimpleNamespace(prior=types.SimpleNamespace(dyn_net=nominal), ds=types.SimpleNamespace(preprocessor=pre),
                                  gp=gp, likelihood=lik, xu=_t(g.X), y=_t(g.resid), use_independent_outputs=True,
                                  sample_dynamics=g.sample)
+
+
+def identity_preprocessor():
+    """A preprocessor whose x side cannot be inverted (like the invariant transform, invariant.py:642-643)."""
+    def invert_x(x):
+        raise RuntimeError("Transform loses information and cannot invert X")
+    return types.SimpleNamespace(invert_x=invert_x, transform_y=lambda y: y, tsf=None)
+
+
+def fake_online_model_module():
+    """Stand-in for the module tampc.dynamics.online_model: just the abstract base B200OnlineGP derives from."""
+    class OnlineDynamicsModel:
+        def __init__(self, ds, state_difference, device=torch.device('cpu')):
+            self.ds, self.state_difference, self.d, self.dtype = ds, state_difference, device, torch.double
+            self.nx, self.nu = ds.config.nx, ds.config.nu
+
+    return types.SimpleNamespace(OnlineDynamicsModel=OnlineDynamicsModel)

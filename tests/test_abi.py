@@ -23,7 +23,7 @@ def lib():
 
 def declared_symbols():
     src = open(HEADER).read()
-    return re.findall(r'TAMPC_API\s+[\w\s\*]+?\b(tampc_mppi_\w+)\s*\(', src)
+    return re.findall(r'TAMPC_API\s+[\w\s\*]+?\b(tampc_(?:mppi|gp)_\w+)\s*\(', src)
 
 
 def test_every_declared_symbol_is_exported(lib):

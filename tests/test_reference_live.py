@@ -122,3 +122,14 @@ def test_oracle_follows_the_live_online_gp_through_updates():
     # leaving non-nominal dynamics restores the plain network (hybrid_model.py:201-202)
     ctrl.dynamics.use_normal_nominal_model()
     assert extract.spec_from_controller(ctrl).dynamics.gp is None
+
+
+def test_device_fitted_gp_class_is_recognised_by_the_reference():
+    """install_gp swaps OnlineGPMixing for a subclass of the reference's own OnlineDynamicsModel: `update()` stays the
+    reference's code and HybridDynamicsModel._uses_local_model_api (hybrid_model.py:185-187) accepts instances."""
+    ref = rh.load_reference()
+    from tampc_b200.online_gp import make_online_gp_class
+    cls = make_online_gp_class(ref.online_model)
+    assert issubclass(cls, ref.online_model.OnlineDynamicsModel)
+    assert cls.update is ref.online_model.OnlineDynamicsModel.update
+    assert not getattr(cls, '__abstractmethods__', None)
