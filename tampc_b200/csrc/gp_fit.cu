@@ -200,8 +200,14 @@ TAMPC_API int tampc_gp_fit(int32_t device, int32_t n_points, int32_t n_in, int32
   const int np = 3 * n_out + 1;
   const size_t bytes_in = sizeof(double) * ((size_t)n_points * n_in + (size_t)n_points * n_out);
   const size_t bytes_st = sizeof(double) * (3 * (size_t)np + 2) + sizeof(long long);
-  unsigned char* dbuf = nullptr;
-  if ((e = cudaMalloc(&dbuf, bytes_in + bytes_st + 64)) != cudaSuccess) return fail(TAMPC_ERR_CUDA, "cudaMalloc", e);
+  // one small scratch buffer per device, kept for the life of the process (a fit runs every control step)
+  constexpr size_t kScratch = sizeof(double) * (2 * (size_t)kFitMaxPoints * TAMPC_GP_MAX_DIM + 3 * (3 * kFitMaxOut + 1) + 2) + 64;
+  static unsigned char* g_scratch[64] = {nullptr};
+  if (device < 0 || device >= 64) return fail(TAMPC_ERR_INVALID, "device ordinal out of range");
+  if (!g_scratch[device] && (e = cudaMalloc(&g_scratch[device], kScratch)) != cudaSuccess) return fail(TAMPC_ERR_CUDA, "cudaMalloc", e);
+  unsigned char* dbuf = g_scratch[device];
+  static_assert(kScratch >= 8, "scratch");
+  if (bytes_in + bytes_st + 64 > kScratch) return fail(TAMPC_ERR_INVALID, "internal: scratch too small");
   double* dX = reinterpret_cast<double*>(dbuf);
   double* dR = dX + (size_t)n_points * n_in;
   double* draw = dR + (size_t)n_points * n_out;
@@ -235,7 +241,6 @@ TAMPC_API int tampc_gp_fit(int32_t device, int32_t n_points, int32_t n_in, int32
   ok = ok && (e = cudaMemcpy(adam_v, dv, sizeof(double) * np, cudaMemcpyDeviceToHost)) == cudaSuccess;
   ok = ok && (e = cudaMemcpy(&step, dstep, sizeof step, cudaMemcpyDeviceToHost)) == cudaSuccess;
   ok = ok && (e = cudaMemcpy(loss_out, dloss, sizeof(double) * 2, cudaMemcpyDeviceToHost)) == cudaSuccess;
-  cudaFree(dbuf);
   if (!ok) return fail(TAMPC_ERR_CUDA, "GP fit", e);
   *adam_step = step;
   return TAMPC_OK;
