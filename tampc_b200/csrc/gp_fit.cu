@@ -79,10 +79,8 @@ __global__ void __launch_bounds__(32 * kFitMaxOut) gp_fit_kernel(const FitArgs a
     const double l = softplus(rl), s = softplus(ro), sig2 = softplus(rt) + 1e-4 + softplus(rn) + 1e-4;
     const double nh = -0.5 / (l * l);
     // ---- K (lower triangle is what the factorisation reads)
-    for (int e = lane; e < n * n; e += 32) {
-      const int i = e / n, j = e % n;
-      V[e] = s * exp(nh * D2[e]) + (i == j ? sig2 : 0.0);
-    }
+    for (int i = 0; i < n; ++i)  // (no runtime integer divisions in the loops of the fit: they cost more than the math)
+      for (int j = lane; j <= i; j += 32) V[i * n + j] = s * exp(nh * D2[i * n + j]) + (i == j ? sig2 : 0.0);
     __syncwarp();
     // ---- Cholesky, in place, lower (right-looking)
     double logdet = 0.0;
@@ -93,10 +91,11 @@ __global__ void __launch_bounds__(32 * kFitMaxOut) gp_fit_kernel(const FitArgs a
       for (int i = j + lane; i < n; i += 32) V[i * n + j] = (i == j) ? piv : V[i * n + j] / piv;
       __syncwarp();
       const int rem = n - j - 1;  // trailing update of the lower triangle: V[i][k] -= V[i][j] V[k][j], j < k <= i
-      for (int e = lane; e < rem * rem; e += 32) {
-        const int i = j + 1 + e / rem, k = j + 1 + e % rem;
-        if (k <= i) V[i * n + k] -= V[i * n + j] * V[k * n + j];
-      }
+      for (int i0 = 0; i0 < rem; i0 += 4)   // 4 x 8 tiles of the trailing block, lower triangle only
+        for (int k0 = 0; k0 <= i0 + 3 && k0 < rem; k0 += 8) {
+          const int i = j + 1 + i0 + (lane >> 3), k = j + 1 + k0 + (lane & 7);
+          if (i < n && k <= i) V[i * n + k] -= V[i * n + j] * V[k * n + j];
+        }
       __syncwarp();
     }
     // ---- w = L^-1 r (forward), alpha = L^-T w (backward)
@@ -123,20 +122,35 @@ __global__ void __launch_bounds__(32 * kFitMaxOut) gp_fit_kernel(const FitArgs a
       for (int i = j + 1 + lane; i < n; i += 32) xt[i] = V[i * n + j];
       __syncwarp();
       for (int i = j + 1 + lane; i < n; i += 32) {  // x <- T x with T = the already inverted trailing block
-        double p = 0.0;
-        for (int k = j + 1; k <= i; ++k) p += V[i * n + k] * xt[k];
-        V[i * n + j] = -ajj * p;
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;  // four partial sums: the dot product is latency-bound otherwise
+        int k = j + 1;
+        for (; k + 3 <= i; k += 4) {
+          p0 += V[i * n + k] * xt[k];
+          p1 += V[i * n + k + 1] * xt[k + 1];
+          p2 += V[i * n + k + 2] * xt[k + 2];
+          p3 += V[i * n + k + 3] * xt[k + 3];
+        }
+        for (; k <= i; ++k) p0 += V[i * n + k] * xt[k];
+        V[i * n + j] = -ajj * ((p0 + p1) + (p2 + p3));
       }
       if (lane == 0) V[j * n + j] = ajj;
       __syncwarp();
     }
     // ---- traces and quadratic forms over the lower triangle (K^-1 = V^T V; E = exp(..), G = E * D2)
     double trE = 0.0, trG = 0.0, trI = 0.0, aEa = 0.0, aGa = 0.0, aa = 0.0;
-    for (int e = lane; e < n * n; e += 32) {
-      const int i = e / n, j = e % n;
-      if (j > i) continue;
-      double kinv = 0.0;
-      for (int k = i; k < n; ++k) kinv += V[k * n + i] * V[k * n + j];
+    for (int i = 0; i < n; ++i)
+    for (int j = lane; j <= i; j += 32) {
+      const int e = i * n + j;
+      double k0 = 0.0, k1 = 0.0, k2 = 0.0, k3 = 0.0;
+      int k = i;
+      for (; k + 3 < n; k += 4) {
+        k0 += V[k * n + i] * V[k * n + j];
+        k1 += V[(k + 1) * n + i] * V[(k + 1) * n + j];
+        k2 += V[(k + 2) * n + i] * V[(k + 2) * n + j];
+        k3 += V[(k + 3) * n + i] * V[(k + 3) * n + j];
+      }
+      for (; k < n; ++k) k0 += V[k * n + i] * V[k * n + j];
+      const double kinv = (k0 + k1) + (k2 + k3);
       const double w = (i == j) ? 1.0 : 2.0;
       const double E = exp(nh * D2[e]), G = E * D2[e];
       trE += w * kinv * E;
