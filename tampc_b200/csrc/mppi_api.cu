@@ -508,6 +508,15 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     // throughput-bound 3xTF32: eight warps per CTA and two CTAs per SM give 16 resident warps instead of 12.
     // Measured on B200 (push, T=40): a full wave takes 1.18x as long but holds 1.33x the samples (1M: 5.98 -> 5.68 ms),
     // so it is used when it does not add a wave (K=131072: 0.83 vs 0.78 ms).  TAMPC_WIDE=0/1 forces the choice.
+    // one balanced wave: when 12 warps per SM are not enough for a single wave but 16 are (56 832 < K <= 75 776), one CTA
+    // per SM with ceil(warps / 148) warps gives every SM the same work (K=65536: 14 warps each instead of 16 on 108 SMs
+    // and 8 on 40).  TAMPC_SM_WAVE=0 disables.
+    const rollout_launch_fn fsm = f16 ? v->f16_mma_sm : v->tf32_mma_sm;
+    if (!f64 && idx == 1 && !big && fsm && eb == 0 && warps > 148 * 12 && warps <= 148 * 16 && env_int("TAMPC_SM_WAVE", 1)) {
+      p.fn = fsm;
+      p.block = 32 * ((warps + 147) / 148);
+      return p;
+    }
     if (!f64 && idx == 1 && !big && fwide && eb == 0) {
       const int wide_env = env_int("TAMPC_WIDE", -1);
       const int ctas_d = (warps + 3) / 4, ctas_w = (warps + 7) / 8;
