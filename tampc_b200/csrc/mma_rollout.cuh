@@ -723,8 +723,10 @@ static __device__ unsigned int g_sm_turn[1024];  // per-SM CTA counter (never re
 // ROLES = 2: chain | decoder + cost.  ROLES = 3: chain | decoder | cost — for K small enough that every warp has a
 // sub-partition to itself (<= 2 tiles per SM), where the decoder + cost warp is the longer of the two (measured at
 // K=512: 64 us, 48 us without the cost); the cost warp joins both hand-offs so that nobody can run a step ahead of it.
-template <class Model, int ROLES>
-__global__ void __launch_bounds__(64 * ROLES) rollout_mma_split_kernel(const RolloutArgs a) {
+// JIT (three roles only): the cost warp draws the actions inside the horizon loop instead of the prologue.
+template <class Model, int ROLES, bool JIT = false>
+__global__ void __launch_bounds__(64 * ROLES, 3) rollout_mma_split_kernel(const RolloutArgs a) {
+  static_assert(!JIT || ROLES == 3, "just-in-time drawing is the cost warp's job");
   static_assert(ROLES == 2 || ROLES == 3, "two or three warps per tile");
   static_assert(sizeof(typename Model::T) == 4, "role-split variant is for the float32 tensor policies");
   static_assert(Model::NX < 8, "xc rows keep the bad flag in column NX");
@@ -769,15 +771,26 @@ __global__ void __launch_bounds__(64 * ROLES) rollout_mma_split_kernel(const Rol
   const int row = lane % SW, part = lane / SW;
   const bool live = kbase + row < a.K_local;
   const int k = live ? kbase + row : a.K_local - 1;
-  if (kbase < a.K_local) {
-    // every perturbed action of the horizon, drawn by the tile's threads (independent items)
-#pragma unroll 5
-    for (int item = role0 * 32 + lane; item < T * SW; item += BARN) {
-      const int t = item / SW, r = item % SW;
-      float u[NU], npost[NU];
-      pcs[item] = sample_action<float, NU>(a.src, sp, Ush + t * kMaxNu, min(kbase + r, a.K_local - 1), t, u, npost);
+  // perturbed action + perturbation-cost term of item (t, r) = t * SW + r of this tile
+  auto draw = [&](int item) {
+    const int t = item / SW, r = item % SW;
+    float u[NU], npost[NU];
+    pcs[item] = sample_action<float, NU>(a.src, sp, Ush + t * kMaxNu, min(kbase + r, a.K_local - 1), t, u, npost);
 #pragma unroll
-      for (int i = 0; i < NU; ++i) upre[item * NU + i] = u[i];
+    for (int i = 0; i < NU; ++i) upre[item * NU + i] = u[i];
+  };
+  if (kbase < a.K_local) {
+    if (JIT) {
+      // the cost warp has slack: it draws the actions two steps ahead inside the horizon loop (32 items = two steps
+      // per draw); only steps 0 and 1 are needed before the loop starts.  Only while every warp has a sub-partition
+      // to itself (<= 2 tiles per SM; measured K=500 60 -> 54 us, 4736 64 -> 57): with four tiles per SM the draws
+      // take issue slots from a chain warp (K=8192 77 -> 80 us), so there they stay in the prologue (JIT = false;
+      // a compile-time switch — as a run-time flag the gain was lost, 60 us at K=500).
+      if (role0 == 2 && lane < T * SW) draw(lane);
+    } else {
+      // every perturbed action of the horizon, drawn by the tile's threads (independent items)
+#pragma unroll 5
+      for (int item = role0 * 32 + lane; item < T * SW; item += BARN) draw(item);
     }
   }
   __syncthreads();
@@ -896,6 +909,10 @@ __global__ void __launch_bounds__(64 * ROLES) rollout_mma_split_kernel(const Rol
           Model::Dec::template eval<1>(w + Model::kOffDec, in, C, slope, lane);
           store_blocks<P, 1, CO8, CS>(Cs, C, 0, lane);
         }
+        if (JIT && (t & 1) == 0) {  // steps t+2, t+3: read by the chain warp after the hand-offs of steps t+1, t+2
+          const int item = (t + 2) * SW + lane;
+          if (item < T * SW) draw(item);
+        }
         __syncwarp();  // (three roles: every lane holds its row of step t before the chain warp may overwrite it)
         named_bar_arrive(bar_c, BARN);
       }
@@ -925,21 +942,29 @@ __global__ void __launch_bounds__(64 * ROLES) rollout_mma_split_kernel(const Rol
   }
 }
 
-template <class Model, int ROLES = 2>
-cudaError_t launch_rollout_mma_split(const RolloutArgs& a, int /*block*/, cudaStream_t stream) {
-  auto kern = rollout_mma_split_kernel<Model, ROLES>;
-  using L = SplitSmem<Model>;
-  const size_t smem = L::bytes(a.src.T);
+template <class Model, int ROLES, bool JIT>
+cudaError_t launch_rollout_mma_split_as(const RolloutArgs& a, int grid, cudaStream_t stream) {
+  auto kern = rollout_mma_split_kernel<Model, ROLES, JIT>;
+  const size_t smem = SplitSmem<Model>::bytes(a.src.T);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  const int per_block = L::TILES * L::SW;
-  const int grid = (a.K_local + per_block - 1) / per_block;
   kern<<<grid, 64 * ROLES, smem, stream>>>(a);
   return cudaGetLastError();
+}
+
+template <class Model, int ROLES = 2>
+cudaError_t launch_rollout_mma_split(const RolloutArgs& a, int /*block*/, cudaStream_t stream) {
+  using L = SplitSmem<Model>;
+  const int per_block = L::TILES * L::SW;
+  const int grid = (a.K_local + per_block - 1) / per_block;
+  if constexpr (ROLES == 3) {
+    if (grid <= 148) return launch_rollout_mma_split_as<Model, 3, true>(a, grid, stream);  // at most one CTA (two tiles) per SM
+  }
+  return launch_rollout_mma_split_as<Model, ROLES, false>(a, grid, stream);
 }
 
 template <class Model>
