@@ -415,33 +415,24 @@ struct MmaSmem {
 // Philox blocks -> instruction-level parallelism), instead of one dependent Philox + Box-Muller chain per step.
 // BLK: largest block the instantiation is launched with.  256 asks for two resident CTAs (<= 128 registers): eight
 // warps share one copy of the image, 16 warps per SM instead of the 12 that three 4-warp CTAs give.
-template <class Model, typename ST, typename CT, int NM, bool PRE, int BLK = 128>
-__global__ void __launch_bounds__(BLK, BLK == 256 ? 2 : 1) rollout_mma_kernel(const RolloutArgs a) {
+// Everything one warp does after the image is staged: SW = 16 * NM samples starting at kbase (8 * NM for float64).
+// warp_index / warps_total: position in the grid-wide list of warps (fused tail only).
+template <class Model, typename ST, typename CT, int NM, bool PRE>
+__device__ __forceinline__ void rollout_mma_warp(const RolloutArgs& a, unsigned char* smem_raw, unsigned char* wbase, int kbase, int lane,
+                                                 int warp_index, int warps_total) {
   using P_T = typename Model::T;
   constexpr int NX = Model::NX, NU = Model::NU;
   constexpr int SW = NM * (sizeof(P_T) == 8 ? PolicyF64::MT : PolicyTF32x3::MT);  // samples per warp
   constexpr int NPARTS = 32 / SW;                                                  // lanes holding the same sample
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   using L = MmaSmem<Model, ST, CT>;
   unsigned char* w = smem_raw;
   CostS<ST, CT>& cs = *reinterpret_cast<CostS<ST, CT>*>(smem_raw + L::kCost);
   SamplerS<ST>& sp = *reinterpret_cast<SamplerS<ST>*>(smem_raw + L::kSampler);
   ST* Ush = reinterpret_cast<ST*>(smem_raw + L::kU);
-  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int T = a.src.T;
-  unsigned char* wbase = smem_raw + L::stage_off(T) + (size_t)warp * L::warp_bytes(T, SW, PRE);
   P_T* stage = reinterpret_cast<P_T*>(wbase);
   float* zpre = reinterpret_cast<float*>(wbase + align16<int>(sizeof(P_T) * Model::kStageElems));  // [T][SW][NU]
-  {
-    copy_image_async(smem_raw, a.image, (int)L::kU, tid, nthr);
-    for (int i = tid; i < T * NU; i += nthr) {
-      int t = i / NU, d = i % NU, ts = t + a.shift;
-      Ush[t * kMaxNu + d] = (ST)(ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d]);
-    }
-    copy_image_wait();
-  }
   const int row = lane % SW, part = lane / SW;
-  const int kbase = (blockIdx.x * (nthr >> 5) + warp) * SW;
   const bool live = kbase + row < a.K_local;
   const int k = live ? kbase + row : a.K_local - 1;
   const bool use_pre = PRE && a.src.mode == kModePhilox;
@@ -455,8 +446,8 @@ __global__ void __launch_bounds__(BLK, BLK == 256 ? 2 : 1) rollout_mma_kernel(co
 #pragma unroll
       for (int i = 0; i < NU; ++i) zpre[item * NU + i] = z[i];
     }
+    __syncwarp();  // the draws are private to the warp
   }
-  __syncthreads();
 
   ST x[NX];
 #pragma unroll
@@ -513,9 +504,58 @@ __global__ void __launch_bounds__(BLK, BLK == 256 ? 2 : 1) rollout_mma_kernel(co
   if (live && part == 0) a.cost_out[k] = total;
   if (a.fuse) {
     total = __shfl_sync(0xffffffffu, total, row);  // mirrors take their sample's total from its part-0 lane
-    fused_tail<NU, SW>(a, *reinterpret_cast<const SamplerS<double>*>(smem_raw + L::kSamplerD), total, row, kbase, lane,
-                       blockIdx.x * (nthr >> 5) + warp, gridDim.x * (nthr >> 5));
+    fused_tail<NU, SW>(a, *reinterpret_cast<const SamplerS<double>*>(smem_raw + L::kSamplerD), total, row, kbase, lane, warp_index,
+                       warps_total);
   }
+}
+
+// The image, the sampler and the shifted nominal sequence, staged once per CTA.
+template <class Model, typename ST, typename CT>
+__device__ __forceinline__ void rollout_mma_stage(const RolloutArgs& a, unsigned char* smem_raw, int tid, int nthr) {
+  using L = MmaSmem<Model, ST, CT>;
+  constexpr int NU = Model::NU;
+  ST* Ush = reinterpret_cast<ST*>(smem_raw + L::kU);
+  const int T = a.src.T;
+  copy_image_async(smem_raw, a.image, (int)L::kU, tid, nthr);
+  for (int i = tid; i < T * NU; i += nthr) {
+    int t = i / NU, d = i % NU, ts = t + a.shift;
+    Ush[t * kMaxNu + d] = (ST)(ts < T ? a.U[ts * NU + d] : a.sampler->u_init[d]);
+  }
+  copy_image_wait();
+  __syncthreads();
+}
+
+template <class Model, typename ST, typename CT, int NM, bool PRE, int BLK = 128>
+__global__ void __launch_bounds__(BLK, BLK == 256 ? 2 : 1) rollout_mma_kernel(const RolloutArgs a) {
+  constexpr int SW = NM * (sizeof(typename Model::T) == 8 ? PolicyF64::MT : PolicyTF32x3::MT);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using L = MmaSmem<Model, ST, CT>;
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  rollout_mma_stage<Model, ST, CT>(a, smem_raw, tid, nthr);
+  unsigned char* wbase = smem_raw + L::stage_off(a.src.T) + (size_t)warp * L::warp_bytes(a.src.T, SW, PRE);
+  const int wi = blockIdx.x * (nthr >> 5) + warp;
+  rollout_mma_warp<Model, ST, CT, NM, PRE>(a, smem_raw, wbase, wi * SW, lane, wi, gridDim.x * (nthr >> 5));
+}
+
+// One balanced wave for 56 832 < K <= 66 304 (3xTF32 / 3xFP16): the tensor pipe belongs to a sub-partition, so a wave
+// lasts as long as its fullest sub-partition.  Sixteen warps per SM, the fourth warp of every sub-partition with ONE
+// m-tile and the other three with two: seven 16-sample tiles per sub-partition (448 samples per SM) instead of the
+// 8 | 8 | 6 | 6 that fourteen two-tile warps give.  Sample order inside the CTA: sub-partition-major.
+template <class Model, typename ST, typename CT>
+__global__ void __launch_bounds__(512, 1) rollout_mma_mix_kernel(const RolloutArgs a) {
+  static_assert(sizeof(typename Model::T) == 4, "mixed tiles: 16-row policies");
+  constexpr int MT = PolicyTF32x3::MT, PER_Q = 7 * MT, PER_CTA = 4 * PER_Q;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using L = MmaSmem<Model, ST, CT>;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  rollout_mma_stage<Model, ST, CT>(a, smem_raw, tid, 512);
+  unsigned char* wbase = smem_raw + L::stage_off(a.src.T) + (size_t)warp * L::warp_bytes(a.src.T, 2 * MT, false);
+  const int q = warp & 3, j = warp >> 2;  // sub-partition, slot on it
+  const int kbase = blockIdx.x * PER_CTA + q * PER_Q + j * 2 * MT;
+  if (kbase >= a.K_local) return;  // (no block-wide barrier below)
+  const int wi = blockIdx.x * 16 + warp, wn = gridDim.x * 16;
+  if (j == 3) rollout_mma_warp<Model, ST, CT, 1, false>(a, smem_raw, wbase, kbase, lane, wi, wn);
+  else rollout_mma_warp<Model, ST, CT, 2, false>(a, smem_raw, wbase, kbase, lane, wi, wn);
 }
 
 // ---- two-warp pipelined variant for small K (latency-bound) ----------------------------------------------
@@ -998,6 +1038,22 @@ cudaError_t launch_rollout_mma(const RolloutArgs& a, int block, cudaStream_t str
   const int per_block = warps * SW;
   const int grid = (a.K_local + per_block - 1) / per_block;
   kern<<<grid, block, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <class Model, typename ST, typename CT>
+cudaError_t launch_rollout_mma_mix(const RolloutArgs& a, int /*block*/, cudaStream_t stream) {
+  auto kern = rollout_mma_mix_kernel<Model, ST, CT>;
+  if (a.fuse) return cudaErrorInvalidValue;  // the fused tail numbers warps by equal sample counts
+  const size_t smem = MmaSmem<Model, ST, CT>::bytes(a.src.T, 16, 2 * PolicyTF32x3::MT, false);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  constexpr int per_block = 4 * 7 * PolicyTF32x3::MT;
+  kern<<<(a.K_local + per_block - 1) / per_block, 512, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

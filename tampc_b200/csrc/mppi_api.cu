@@ -511,6 +511,14 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     // one balanced wave: when 12 warps per SM are not enough for a single wave but 16 are (56 832 < K <= 75 776), one CTA
     // per SM with ceil(warps / 148) warps gives every SM the same work (K=65536: 14 warps each instead of 16 on 108 SMs
     // and 8 on 40).  TAMPC_SM_WAVE=0 disables.
+    // ... and seven tiles per sub-partition (three two-tile warps + one one-tile warp) while 448 samples per SM are
+    // enough: the wave then lasts as long as 3.5 instead of 4 two-tile warps per sub-partition.  TAMPC_MIX=0 disables.
+    const rollout_launch_fn fmix = f16 ? v->f16_mma_mix : v->tf32_mma_mix;
+    if (!f64 && idx == 1 && !big && fmix && eb == 0 && warps > 148 * 12 && K <= 148 * 448 && env_int("TAMPC_MIX", 1) && env_int("TAMPC_SM_WAVE", 1)) {
+      p.fn = fmix;
+      p.block = 512;
+      return p;
+    }
     const rollout_launch_fn fsm = f16 ? v->f16_mma_sm : v->tf32_mma_sm;
     if (!f64 && idx == 1 && !big && fsm && eb == 0 && warps > 148 * 12 && warps <= 148 * 16 && env_int("TAMPC_SM_WAVE", 1)) {
       p.fn = fsm;

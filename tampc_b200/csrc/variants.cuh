@@ -16,16 +16,17 @@ struct ModelVariant {
   int macs;
   rollout_launch_fn f64_s1, mixed_s1, mixed_s2, f32_s1, f32_s2;  // one-thread-per-sample FMA kernels
   rollout_launch_fn f64_mma[3];   // DMMA kernels, NM = 1, 2, 4 m-tiles (8, 16, 32 samples) per warp
-  rollout_launch_fn tf32_mma[2];
+  rollout_launch_fn tf32_mma[2];  // 3xTF32 kernels, NM = 1, 2 (16, 32 samples per warp); float32 state and cost terms, float64 cost sum
   GpLaunchers gp;                 // one-thread-per-(sample, replica) FMA kernels with the online GP residual
   rollout_launch_fn tf32_mma_wide; // NM = 2, 256-thread CTAs, two per SM (throughput-bound K)
   // 3xFP16 (mma.sync.m16n8k16.f16): same kernels, half the tensor instructions
   int bytes_mma_f16;
   rollout_launch_fn f16_mma[2], f16_mma_wide, f16_split;
-  rollout_launch_fn tf32_split3, f16_split3;
-  rollout_launch_fn tf32_mma_sm, f16_mma_sm;  // NM = 2, ONE CTA per SM of up to 16 warps: a single balanced wave (K just above 56k)  // three warps per tile (chain | decoder | cost): K with <= 2 tiles per SM
+  rollout_launch_fn tf32_split3, f16_split3;  // three warps per tile (chain | decoder | cost): latency-bound K
+  rollout_launch_fn tf32_mma_sm, f16_mma_sm;  // NM = 2, ONE CTA per SM of up to 16 warps: a single balanced wave (K just above 56k)
+  rollout_launch_fn tf32_mma_mix, f16_mma_mix;  // one CTA per SM, seven tiles per sub-partition (56 832 < K <= 66 304)
   rollout_launch_fn tf32_split;   // two warps per 16-sample tile, split by role (RexExtract shapes, latency-bound K)
-  rollout_launch_fn tf32_pipe;    // two-warp pipelined 3xTF32 kernel for small K (16 samples per CTA)  // 3xTF32 kernels, NM = 1, 2 (16, 32 samples per warp); float32 state and cost terms, float64 cost sum
+  rollout_launch_fn tf32_pipe;    // two-warp pipelined 3xTF32 kernel for small K (16 samples per CTA)
 };
 
 template <class MF, class MD, bool WITH_S2>
@@ -61,6 +62,7 @@ void add_mma(ModelVariant& v) {
   v.tf32_mma[1] = &launch_rollout_mma<MM32, float, float, 2, false>;
   v.tf32_mma_wide = &launch_rollout_mma<MM32, float, float, 2, false, 256>;
   v.tf32_mma_sm = &launch_rollout_mma<MM32, float, float, 2, false, 512>;
+  if constexpr (MM32::kBytes <= 100 * 1024) v.tf32_mma_mix = &launch_rollout_mma_mix<MM32, float, float>;
   v.tf32_pipe = &launch_rollout_mma_pipe<MM32>;
 }
 
@@ -76,6 +78,7 @@ void add_f16(ModelVariant& v) {
   v.f16_mma[1] = &launch_rollout_mma<MM16, float, float, 2, false>;
   v.f16_mma_wide = &launch_rollout_mma<MM16, float, float, 2, false, 256>;
   v.f16_mma_sm = &launch_rollout_mma<MM16, float, float, 2, false, 512>;
+  if constexpr (MM16::kBytes <= 100 * 1024) v.f16_mma_mix = &launch_rollout_mma_mix<MM16, float, float>;
 }
 
 const ModelVariant* variant_rex_push();   // nx5 nu3, enc 8-16-32-5, dyn 5-32-32-5, dec 5(2)-16-32-25

@@ -272,3 +272,28 @@ def test_ragged_and_maximum_sizes(cuda_lib, precision, K, T, P):
         assert m.stats['argmin'] == want['argmin']
         assert float((a - want['action']).abs().max()) < 1e-4
     m.close()
+
+
+@pytest.mark.parametrize('precision', ['tf32x3', 'f16x3'])
+@pytest.mark.parametrize('K', [56833, 65536, 66304, 66305])
+def test_balanced_wave_kernels(cuda_lib, monkeypatch, precision, K):
+    """56 832 < K <= 66 304 runs the one-CTA-per-SM kernel with seven tiles per sub-partition (one- and two-tile warps
+    in one CTA; sample order sub-partition-major, the last CTA ragged), above it the 16-warp wave.  Oracle parity, and
+    agreement with the default kernels to float32 rounding (a one-tile warp sums a sample's running cost over two
+    lanes, a two-tile warp over one: the order of the float32 additions differs, nothing else)."""
+    from tampc_b200.mppi import B200MPPI
+    z, spec = _spec('push_nominal', K, 5)
+    U0 = _U(z, spec)
+    noise = O.sample_noise(spec, 23, K=K, T=5)
+    want = O.command(spec, torch.from_numpy(z['in.state']), U0, noise)
+    m = B200MPPI(spec, precision=precision, U_init=U0)
+    a = m.command(z['in.state'], noise=noise.numpy())
+    cost = m.cost_total.clone()
+    assert float(((cost - want['cost_total']).abs() / want['cost_total'].abs()).max()) < RTOL[precision]
+    assert m.stats['argmin'] == want['argmin']
+    assert float((a - want['action']).abs().max()) < 1e-4
+    monkeypatch.setenv('TAMPC_SM_WAVE', '0')
+    m.U = U0.clone()
+    m.command(z['in.state'], noise=noise.numpy())
+    assert float(((m.cost_total - cost).abs() / cost.abs()).max()) < 1e-6
+    m.close()
