@@ -15,6 +15,13 @@
 
 namespace tampc {
 
+// Programmatic dependent launch (sm_90+): the softmax-update launch that follows a rollout is placed on the SMs while
+// the rollout still runs and blocks in grid_dep_wait() until the rollout grid has completed and its stores are visible.
+// Both are no-ops in a launch without the programmatic-serialization attribute.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+
 constexpr int kMaxNx = TAMPC_MAX_NX;
 constexpr int kMaxNu = TAMPC_MAX_NU;
 constexpr double kPi = 3.141592653589793;

@@ -516,6 +516,7 @@ __device__ __forceinline__ void rollout_mma_stage(const RolloutArgs& a, unsigned
   constexpr int NU = Model::NU;
   ST* Ush = reinterpret_cast<ST*>(smem_raw + L::kU);
   const int T = a.src.T;
+  grid_dep_launch();  // the softmax-update launch may take its place behind this grid now
   copy_image_async(smem_raw, a.image, (int)L::kU, tid, nthr);
   for (int i = tid; i < T * NU; i += nthr) {
     int t = i / NU, d = i % NU, ts = t + a.shift;
@@ -784,6 +785,7 @@ __global__ void __launch_bounds__(64 * ROLES, 3) rollout_mma_split_kernel(const 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = a.src.T;
   {
+    grid_dep_launch();  // the softmax-update launch may take its place behind this grid now
     copy_image_async(smem_raw, a.image, (int)L::kU, tid, NTHR);
     if (tid == 0) {
       unsigned int smid;

@@ -716,14 +716,33 @@ CombineArgs base_combine_args(tampc_mppi* h) {
 
 ExchangeArgs make_exchange_args(tampc_mppi* h);
 
+// The tail launches are programmatic dependents of the rollout launch in front of them (TAMPC_PDL=0: plain stream
+// order): their CTAs are placed while the rollout still runs and wait in grid_dep_wait() for its completion, so the
+// launch latency and the staging of the sampler constants are off the command's critical path.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_dependent(void (*kern)(KArgs...), int grid, int block, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const int pdl = env_int("TAMPC_PDL", 1);
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int NU>
 void launch_partials_exchange(const ReduceArgs& r, const CombineArgs& c, const ExchangeArgs& e, unsigned int* ticket, int n_chunks, cudaStream_t s) {
-  partials_exchange_kernel<NU><<<n_chunks, kCombineThreads, 0, s>>>(r, c, e, ticket);
+  launch_dependent(partials_exchange_kernel<NU>, n_chunks, kCombineThreads, s, r, c, e, ticket);
 }
 
 template <int NU>
 void launch_partials_combine(const ReduceArgs& r, const CombineArgs& c, unsigned int* ticket, int n_chunks, cudaStream_t s) {
-  partials_combine_kernel<NU><<<n_chunks, kCombineThreads, 0, s>>>(r, c, ticket);
+  launch_dependent(partials_combine_kernel<NU>, n_chunks, kCombineThreads, s, r, c, ticket);
 }
 
 template <int NU>

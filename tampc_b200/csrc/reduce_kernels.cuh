@@ -82,6 +82,7 @@ __device__ __forceinline__ void partials_body(const ReduceArgs& a) {
   // ---- block min / argmin (lowest index wins ties, like torch.min / argmin over a 1-D tensor)
   __shared__ double s_wb[32];
   __shared__ long long s_wi[32];
+  grid_dep_wait();  // the costs come from the rollout launch in front (everything staged above predates it)
   const double c = tid < n ? a.cost[k0 + tid] : __longlong_as_double(0x7ff0000000000000ll);
   double beta = c;
   long long amin_ll = tid;
