@@ -21,6 +21,17 @@ namespace tampc {
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Flag-in-data publication of a double to memory somebody else polls (mapped pinned host memory; peer memory): two
+// 8-byte words, each = 32 bits of the value | the 32-bit sequence number of the command.  An aligned 8-byte store is
+// never torn, so the reader needs no flag behind the data and the writer no fence in front of a flag: it polls the
+// words themselves until both carry the sequence number it waits for.  slot = index of the value (16 bytes apart).
+constexpr int kHostSlots = 8;  // action[kMaxNu], beta, eta, argmin, error
+__device__ __forceinline__ void ll_publish(unsigned long long* base, int slot, double v, unsigned long long seq) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v), tag = (seq & 0xffffffffull) << 32;
+  volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(base) + 2 * slot;
+  w[0] = (b & 0xffffffffull) | tag;
+  w[1] = (b >> 32) | tag;
+}
 
 constexpr int kMaxNx = TAMPC_MAX_NX;
 constexpr int kMaxNu = TAMPC_MAX_NU;

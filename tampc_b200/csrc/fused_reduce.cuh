@@ -179,7 +179,7 @@ __device__ __forceinline__ void last_warp_combine(const RolloutArgs& a, int n, i
         a.U_out[i] = v;
         if (t == 0) {
           a.action_out[d] = v;
-          if (a.host_out != nullptr) a.host_out[d] = v;
+          if (a.host_ll != nullptr) ll_publish(a.host_ll, d, v, a.seq);
         }
       }
     }
@@ -187,14 +187,10 @@ __device__ __forceinline__ void last_warp_combine(const RolloutArgs& a, int n, i
       a.stats_out[0] = b;
       a.stats_out[1] = eta;
       a.stats_out[2] = (double)bi;
-      if (a.host_out != nullptr) { a.host_out[kMaxNu] = b; a.host_out[kMaxNu + 1] = eta; a.host_out[kMaxNu + 2] = (double)bi; }
-    }
-    if (a.host_out != nullptr) {
-      __threadfence_system();
-      __syncwarp();
-      if (lane == 0) {
-        *reinterpret_cast<volatile unsigned long long*>(a.host_flag) = a.seq;
-        __threadfence_system();
+      if (a.host_ll != nullptr) {
+        ll_publish(a.host_ll, kMaxNu, b, a.seq);
+        ll_publish(a.host_ll, kMaxNu + 1, eta, a.seq);
+        ll_publish(a.host_ll, kMaxNu + 2, (double)bi, a.seq);
       }
     }
   } else {

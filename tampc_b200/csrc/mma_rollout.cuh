@@ -764,6 +764,14 @@ static __device__ unsigned int g_sm_turn[1024];  // per-SM CTA counter (never re
 // ROLES = 2: chain | decoder + cost.  ROLES = 3: chain | decoder | cost — for K small enough that every warp has a
 // sub-partition to itself (<= 2 tiles per SM), where the decoder + cost warp is the longer of the two (measured at
 // K=512: 64 us, 48 us without the cost); the cost warp joins both hand-offs so that nobody can run a step ahead of it.
+// Unrolling of the prologue's draw loop in the role-split kernels.  Not unrolled: the bench flushes L2 between commands,
+// so every launch fetches its code cold, and the prologue runs once — 1 100 fewer instructions to fetch beat the
+// instruction-level parallelism of five draws in flight (K=8192: 76.1 -> 74.3 us; unroll 2: 74.6).
+#ifndef TAMPC_DRAW_UNROLL
+#define TAMPC_DRAW_UNROLL 1
+#endif
+constexpr int kDrawUnroll = TAMPC_DRAW_UNROLL;
+
 // JIT (three roles only): the cost warp draws the actions inside the horizon loop instead of the prologue.
 template <class Model, int ROLES, bool JIT = false>
 __global__ void __launch_bounds__(64 * ROLES, 3) rollout_mma_split_kernel(const RolloutArgs a) {
@@ -831,7 +839,7 @@ __global__ void __launch_bounds__(64 * ROLES, 3) rollout_mma_split_kernel(const 
       if (role0 == 2 && lane < T * SW) draw(lane);
     } else {
       // every perturbed action of the horizon, drawn by the tile's threads (independent items)
-#pragma unroll 5
+#pragma unroll kDrawUnroll
       for (int item = role0 * 32 + lane; item < T * SW; item += BARN) draw(item);
     }
   }

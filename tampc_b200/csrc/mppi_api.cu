@@ -85,8 +85,8 @@ struct tampc_mppi {
   int img_cost_off = 0, img_sampler_off = 0, img_sampler_d_off = 0, img_bytes = 0;  // shared-memory image offsets inside d_weights
 
   double* h_pin = nullptr;  // pinned staging: [0..15] in, [16..31] out
-  double* h_map = nullptr;  // mapped pinned result block written by the combine kernel: action[4], stats[3], flag
-  double* d_map = nullptr;  // device alias of h_map
+  unsigned long long* h_map = nullptr;  // mapped pinned result block published by the combine kernel (ll_publish): kHostSlots x 2 words
+  unsigned long long* d_map = nullptr;  // device alias of h_map
   unsigned long long seq = 0;
   double state_host[kMaxNx] = {0};  // start state of the next rollout (passed to the kernels by value)
   int n_chunks = 0, chunk = 0;
@@ -679,8 +679,7 @@ int launch_rollout_for(tampc_mppi* h, int mode, int shift, const double* d_U, in
     a.stats_out = h->d_stats;
     a.partial_out = partial_out ? partial_out : h->d_rank_partial;
     if (fuse == 1) {
-      a.host_out = h->d_map;
-      a.host_flag = reinterpret_cast<unsigned long long*>(h->d_map + 8);
+      a.host_ll = h->d_map;
       a.seq = ++h->seq;
     }
     if (fused) *fused = true;
@@ -817,8 +816,7 @@ int run_rollout_and_partials(tampc_mppi* h, int mode, bool keep_states, int fuse
     c.finalize = fuse == 1;
     c.partial_out = partial_out ? partial_out : h->d_rank_partial;
     if (fuse == 1) {
-      c.host_out = h->d_map;
-      c.host_flag = reinterpret_cast<unsigned long long*>(h->d_map + 8);
+      c.host_ll = h->d_map;
       c.seq = ++h->seq;
     }
     switch (h->cfg.nu) {
@@ -869,8 +867,7 @@ int run_combine(tampc_mppi* h, const tampc_partial* partials, int n, int finaliz
   c.finalize = finalize;
   c.partial_out = partial_out ? partial_out : h->d_rank_partial;
   if (finalize) {
-    c.host_out = h->d_map;
-    c.host_flag = reinterpret_cast<unsigned long long*>(h->d_map + 8);
+    c.host_ll = h->d_map;
     c.seq = ++h->seq;
   }
   combine_kernel<<<1, kCombineThreads, 0, h->stream>>>(c);
@@ -894,8 +891,7 @@ ExchangeArgs make_exchange_args(tampc_mppi* h) {
   e.c.action_out = h->d_action;
   e.c.stats_out = h->d_stats;
   e.c.partial_out = h->d_rank_partial;
-  e.c.host_out = h->d_map;
-  e.c.host_flag = reinterpret_cast<unsigned long long*>(h->d_map + 8);
+  e.c.host_ll = h->d_map;
   e.c.seq = ++h->seq;
   e.mine = h->d_rank_partial;
   e.rank = h->comm_rank;
@@ -938,20 +934,45 @@ int upload_noise(tampc_mppi* h, int mode, const double* noise, int T) {
 // The combine kernel stores action and stats straight into mapped pinned memory and then publishes the sequence
 // number; poll for it (a few microseconds sooner than a stream synchronise), fall back to the synchronise so that a
 // faulted kernel surfaces as an error instead of a hang.
+// One value of the result block if both of its words carry the command's sequence number.
+bool ll_read(const volatile unsigned long long* base, int slot, uint32_t seq32, double* out) {
+  const unsigned long long w0 = base[2 * slot], w1 = base[2 * slot + 1];
+  if ((uint32_t)(w0 >> 32) != seq32 || (uint32_t)(w1 >> 32) != seq32) return false;
+  const unsigned long long b = (w0 & 0xffffffffull) | (w1 << 32);
+  memcpy(out, &b, sizeof(double));
+  return true;
+}
+
+// 0: not there yet, 1: action + stats complete, -1: the kernel reported a peer-exchange timeout
+int ll_poll(tampc_mppi* h, double* vals) {
+  const uint32_t seq32 = (uint32_t)h->seq;
+  double err;
+  if (ll_read(h->h_map, kMaxNu + 3, seq32, &err)) return -1;
+  for (int d = 0; d < h->cfg.nu; ++d)
+    if (!ll_read(h->h_map, d, seq32, vals + d)) return 0;
+  for (int i = 0; i < 3; ++i)
+    if (!ll_read(h->h_map, kMaxNu + i, seq32, vals + kMaxNu + i)) return 0;
+  return 1;
+}
+
 int download_action(tampc_mppi* h, double* action) {
-  volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(h->h_map + 8);
-  bool seen = false;
-  for (int spin = 0; spin < 200000; ++spin) {
-    if (*flag == h->seq) { seen = true; break; }
-    if ((spin & 1023) == 1023 && cudaStreamQuery(h->stream) != cudaErrorNotReady) break;
+  double vals[kHostSlots];
+  int got = 0;
+  for (int spin = 0; spin < 200000 && got == 0; ++spin) {
+    got = ll_poll(h, vals);
+    if (got == 0 && (spin & 1023) == 1023 && cudaStreamQuery(h->stream) != cudaErrorNotReady) break;
   }
-  if (!seen) {
+  if (got == 0) {
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    if (*flag != h->seq) { h->err = "combine kernel did not publish its result"; return TAMPC_ERR_CUDA; }
+    got = ll_poll(h, vals);
+    if (got == 0) { h->err = "combine kernel did not publish its result"; return TAMPC_ERR_CUDA; }
   }
-  __sync_synchronize();
-  memcpy(action, h->h_map, sizeof(double) * h->cfg.nu);
-  memcpy(h->last_stats, h->h_map + kMaxNu, sizeof(double) * 3);
+  if (got < 0) {
+    h->err = "peer exchange timed out: a rank did not reach this command";
+    return TAMPC_ERR_CUDA;
+  }
+  memcpy(action, vals, sizeof(double) * h->cfg.nu);
+  memcpy(h->last_stats, vals + kMaxNu, sizeof(double) * 3);
   return TAMPC_OK;
 }
 
@@ -1063,8 +1084,8 @@ TAMPC_API int tampc_mppi_create(const tampc_mppi_config* cfg, tampc_mppi** out) 
   CREATE_TRY(cudaMalloc(&h->d_action, sizeof(double) * kMaxNu));
   CREATE_TRY(cudaMalloc(&h->d_stats, sizeof(double) * 4));
   CREATE_TRY(cudaMallocHost(&h->h_pin, sizeof(double) * 32));
-  CREATE_TRY(cudaHostAlloc(&h->h_map, sizeof(double) * 16, cudaHostAllocMapped));
-  memset(h->h_map, 0, sizeof(double) * 16);
+  CREATE_TRY(cudaHostAlloc(&h->h_map, sizeof(unsigned long long) * 2 * kHostSlots, cudaHostAllocMapped));
+  memset(h->h_map, 0, sizeof(unsigned long long) * 2 * kHostSlots);
   CREATE_TRY(cudaHostGetDevicePointer(&h->d_map, h->h_map, 0));
   SamplerD sd{};
   for (int i = 0; i < nu; ++i) {
@@ -1459,13 +1480,7 @@ TAMPC_API int tampc_mppi_command(tampc_mppi* h, const double* state, int32_t noi
     if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/3, h->d_rank_partial, &done))) return rc;
     if (!done && (rc = run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/0, h->d_rank_partial))) return rc;
     if (!h->tail_exchanged && (rc = run_exchange_combine(h))) return rc;
-    rc = download_action(h, action);
-    if (rc == TAMPC_OK && h->h_map[kMaxNu + 3] < 0.0) {
-      h->h_map[kMaxNu + 3] = 0.0;
-      h->err = "peer exchange timed out: a rank did not reach this command";
-      return TAMPC_ERR_CUDA;
-    }
-    return rc;
+    return download_action(h, action);  // (a peer-exchange timeout comes back through the result block's error slot)
   }
   if (h->cfg.num_local != h->cfg.num_samples) {
     h->err = "sharded handle: use command_begin/finish with an all-gather, or connect the peer exchange (comm_init/comm_connect)";

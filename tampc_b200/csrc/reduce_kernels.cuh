@@ -142,9 +142,8 @@ struct CombineArgs {
   double* action_out;    // (nu,) = U_out[0]
   double* stats_out;     // beta, eta, argmin
   tampc_partial* partial_out;
-  double* host_out;      // optional mapped pinned host memory: action[kMaxNu], stats[3] written straight to the host,
-  unsigned long long* host_flag;  // then the sequence number (after a system-scope fence) the host polls for
-  unsigned long long seq;
+  unsigned long long* host_ll;  // optional mapped pinned host memory: action[kMaxNu], stats[3] published straight to the
+  unsigned long long seq;       // host, every word tagged with this sequence number (ll_publish: no flag, no fence)
 };
 
 constexpr int kCombineThreads = 512;  // also the largest group; combine_body deals partials over 4 x 128 threads
@@ -212,7 +211,7 @@ __device__ __forceinline__ void combine_body(const CombineArgs& a) {
       a.U_out[i] = v;
       if (t == 0) {
         a.action_out[d] = v;
-        if (a.host_out != nullptr) a.host_out[d] = v;  // zero-copy: straight into mapped pinned host memory
+        if (a.host_ll != nullptr) ll_publish(a.host_ll, d, v, a.seq);  // zero-copy: straight into mapped pinned host memory
       }
     } else {
       a.partial_out[cta].wsum[i] = sum;
@@ -223,22 +222,17 @@ __device__ __forceinline__ void combine_body(const CombineArgs& a) {
       a.stats_out[0] = beta;
       a.stats_out[1] = eta;
       a.stats_out[2] = (double)arg;
-      if (a.host_out != nullptr) { a.host_out[kMaxNu] = beta; a.host_out[kMaxNu + 1] = eta; a.host_out[kMaxNu + 2] = (double)arg; }
+      if (a.host_ll != nullptr) {
+        ll_publish(a.host_ll, kMaxNu, beta, a.seq);
+        ll_publish(a.host_ll, kMaxNu + 1, eta, a.seq);
+        ll_publish(a.host_ll, kMaxNu + 2, (double)arg, a.seq);
+      }
     } else {
       tampc_partial& o = a.partial_out[cta];
       o.beta = beta;
       o.eta = eta;
       o.argmin = arg;
       o.count = cnt;
-    }
-  }
-  if (a.finalize && a.host_out != nullptr) {
-    // publish: order every thread's host stores before the sequence number the host polls for
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-      *reinterpret_cast<volatile unsigned long long*>(a.host_flag) = a.seq;
-      __threadfence_system();
     }
   }
 }
@@ -319,11 +313,7 @@ __device__ __forceinline__ void exchange_body(const ExchangeArgs& e) {
   if (s_fail) {
     if (tid == 0) {
       *e.error_out = 1;
-      if (e.c.host_out != nullptr) {  // wake the host: it reads the error flag after the sequence number
-        e.c.host_out[kMaxNu + 3] = -1.0;
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long*>(e.c.host_flag) = e.c.seq;
-      }
+      if (e.c.host_ll != nullptr) ll_publish(e.c.host_ll, kMaxNu + 3, -1.0, e.c.seq);  // wake the host: its error slot
     }
     return;
   }

@@ -34,8 +34,7 @@ struct RolloutArgs {
   double* U_out;
   double* action_out;
   double* stats_out;
-  double* host_out;         // mapped pinned host memory (action, stats) or null
-  unsigned long long* host_flag;
+  unsigned long long* host_ll;  // mapped pinned host memory (action, stats; ll_publish) or null
   unsigned long long seq;
   tampc_partial* partial_out;
   // online GP residual (gp_rollout.cuh): shared-memory block, M rollout replicas per sample, variance penalty,
