@@ -26,11 +26,22 @@ __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol
 // never torn, so the reader needs no flag behind the data and the writer no fence in front of a flag: it polls the
 // words themselves until both carry the sequence number it waits for.  slot = index of the value (16 bytes apart).
 constexpr int kHostSlots = 8;  // action[kMaxNu], beta, eta, argmin, error
-__device__ __forceinline__ void ll_publish(unsigned long long* base, int slot, double v, unsigned long long seq) {
-  const unsigned long long b = (unsigned long long)__double_as_longlong(v), tag = (seq & 0xffffffffull) << 32;
+__device__ __forceinline__ void ll_publish_bits(unsigned long long* base, int slot, unsigned long long b, unsigned long long seq) {
+  const unsigned long long tag = (seq & 0xffffffffull) << 32;
   volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(base) + 2 * slot;
   w[0] = (b & 0xffffffffull) | tag;
   w[1] = (b >> 32) | tag;
+}
+__device__ __forceinline__ void ll_publish(unsigned long long* base, int slot, double v, unsigned long long seq) {
+  ll_publish_bits(base, slot, (unsigned long long)__double_as_longlong(v), seq);
+}
+// the value of a slot once both of its words carry seq
+__device__ __forceinline__ bool ll_try_read(const unsigned long long* base, int slot, unsigned long long seq, unsigned long long* bits) {
+  const volatile unsigned long long* w = reinterpret_cast<const volatile unsigned long long*>(base) + 2 * slot;
+  const unsigned long long w0 = w[0], w1 = w[1], tag = seq & 0xffffffffull;
+  if ((w0 >> 32) != tag || (w1 >> 32) != tag) return false;
+  *bits = (w0 & 0xffffffffull) | (w1 << 32);
+  return true;
 }
 
 constexpr int kMaxNx = TAMPC_MAX_NX;

@@ -69,6 +69,7 @@ struct tampc_mppi {
   unsigned char* comm_local = nullptr;
   unsigned char* comm_peer[kMaxRanks] = {nullptr};
   int* d_comm_error = nullptr;
+  tampc_partial* d_world_partials = nullptr;  // the world's partials decoded out of the exchange buffer (kMaxRanks)
   unsigned long long comm_seq = 0;
   unsigned int* d_ticket = nullptr;      // fused-reduction ticket counter
   PartialHdr* d_phdr = nullptr;          // fused-reduction per-warp partials (compact)
@@ -877,7 +878,7 @@ int run_combine(tampc_mppi* h, const tampc_partial* partials, int n, int finaliz
   return TAMPC_OK;
 }
 
-size_t comm_parity_bytes(int world) { return (sizeof(tampc_partial) * world + sizeof(unsigned long long) * kMaxRanks + 255) & ~size_t(255); }
+size_t comm_parity_bytes(int world) { return (sizeof(unsigned long long) * 2 * kPartialWords * world + 255) & ~size_t(255); }
 
 // exchange + merge in one kernel (reduce_kernels.cuh exchange_combine_kernel); this rank's partial is in d_rank_partial
 ExchangeArgs make_exchange_args(tampc_mppi* h) {
@@ -895,14 +896,14 @@ ExchangeArgs make_exchange_args(tampc_mppi* h) {
   e.c.seq = ++h->seq;
   e.mine = h->d_rank_partial;
   e.rank = h->comm_rank;
-  e.world = h->comm_world;
+  e.world_size = h->comm_world;
+  e.world = h->d_world_partials;
   e.seq = ++h->comm_seq;
   e.timeout_ns = 2000000000ll * (long long)env_int("TAMPC_COMM_TIMEOUT_S", 2) / 2;
   e.error_out = h->d_comm_error;
   const size_t off = (e.seq & 1) * comm_parity_bytes(h->comm_world);
   for (int p = 0; p < h->comm_world; ++p) {
-    e.peer_slots[p] = reinterpret_cast<tampc_partial*>(h->comm_peer[p] + off);
-    e.peer_flags[p] = reinterpret_cast<unsigned long long*>(h->comm_peer[p] + off + sizeof(tampc_partial) * h->comm_world);
+    e.peer_ll[p] = reinterpret_cast<unsigned long long*>(h->comm_peer[p] + off);
   }
   return e;
 }
@@ -1116,7 +1117,7 @@ TAMPC_API void tampc_mppi_destroy(tampc_mppi* h) {
   cudaFree(h->d_rank_partial); cudaFree(h->d_action); cudaFree(h->d_stats); cudaFree(h->d_weights);
   for (int p = 0; p < h->comm_world; ++p)
     if (h->comm_connected && p != h->comm_rank && h->comm_peer[p]) cudaIpcCloseMemHandle(h->comm_peer[p]);
-  cudaFree(h->comm_local); cudaFree(h->d_comm_error);
+  cudaFree(h->comm_local); cudaFree(h->d_comm_error); cudaFree(h->d_world_partials);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->h_map) cudaFreeHost(h->h_map);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -1501,6 +1502,7 @@ TAMPC_API int tampc_mppi_comm_init(tampc_mppi* h, int32_t rank, int32_t world, v
     CUDA_TRY(h, cudaMalloc(&h->comm_local, bytes));
     CUDA_TRY(h, cudaMemset(h->comm_local, 0, bytes));
     CUDA_TRY(h, cudaMalloc(&h->d_comm_error, sizeof(int)));
+    CUDA_TRY(h, cudaMalloc(&h->d_world_partials, sizeof(tampc_partial) * kMaxRanks));
     CUDA_TRY(h, cudaMemset(h->d_comm_error, 0, sizeof(int)));
   }
   h->comm_rank = rank;

@@ -261,18 +261,21 @@ __global__ void __launch_bounds__(kCombineThreads) partials_combine_kernel(const
 // ---- multi-GPU exchange over peer memory ---------------------------------------------------------------------
 // The only inter-GPU step of a K-sharded command is ~1 KB per rank.  Instead of an NCCL all-gather
 // (a separate launch plus host-side collective bookkeeping: ~45 us measured at 2 ranks) the merge kernel itself does
-// the exchange: every rank stores its merged partial straight into slot[rank] of every peer's exchange buffer (P2P
-// stores over NVLink to CUDA-IPC mapped memory), publishes a per-rank sequence flag at system scope, waits for the
-// world's flags in its own buffer, and then runs the same deterministic combine as the single-GPU path — so every
-// rank finishes with a bitwise-identical U.  Buffers are double-buffered on the sequence parity: a rank can run at
-// most one command ahead of a peer (it needs the peer's flag of command n to finish n), never two.
+// the exchange: every rank stores its merged partial straight into area[rank] of every peer's exchange buffer (P2P
+// stores over NVLink to CUDA-IPC mapped memory) with the command's sequence number inside every 8-byte word
+// (ll_publish), polls the world's words in its own buffer until they carry that number — no flag, no system-scope
+// fence on either side — and then runs the same deterministic combine as the single-GPU path, so every rank
+// finishes with a bitwise-identical U.  Buffers are double-buffered on the sequence parity: a rank can run at most
+// one command ahead of a peer (it needs the peer's words of command n to finish n), never two.
 constexpr int kMaxRanks = 8;
+constexpr int kPartialWords = 4 + TAMPC_MAX_HORIZON * TAMPC_MAX_NU;  // a tampc_partial as 64-bit values: beta, eta, argmin, count, wsum
+static_assert(sizeof(tampc_partial) == sizeof(unsigned long long) * kPartialWords, "tampc_partial is kPartialWords 64-bit values");
 struct ExchangeArgs {
   CombineArgs c;                         // finalize = 1; partials / n_partials are filled in by the kernel
   const tampc_partial* mine;             // this rank's merged partial (device-local)
-  tampc_partial* peer_slots[kMaxRanks];  // slot array (world entries) of this parity in every rank's buffer
-  unsigned long long* peer_flags[kMaxRanks];
-  int rank, world;
+  unsigned long long* peer_ll[kMaxRanks];  // this parity's area in every rank's buffer: [source rank][kPartialWords][2 words]
+  tampc_partial* world;                  // device-local scratch: the world's partials, decoded, in rank order
+  int rank, world_size;
   unsigned long long seq;
   long long timeout_ns;
   int* error_out;                        // device int: set to 1 if a peer never arrived
@@ -287,29 +290,31 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ void exchange_body(const ExchangeArgs& e) {
   __shared__ int s_fail;
   const int tid = threadIdx.x;
-  const int nw = e.c.T * e.c.nu;
+  const int nv = 4 + e.c.T * e.c.nu;  // values of a partial in use
   if (tid == 0) s_fail = 0;
-  // 1. my partial -> slot[rank] on every rank (header = 4 x 8 bytes, then T*nu sums)
-  for (int p = 0; p < e.world; ++p) {
-    tampc_partial* dst = e.peer_slots[p] + e.rank;
-    for (int i = tid; i < nw; i += kCombineThreads) dst->wsum[i] = e.mine->wsum[i];
-    if (tid == 0) { dst->beta = e.mine->beta; dst->eta = e.mine->eta; dst->argmin = e.mine->argmin; dst->count = e.mine->count; }
-  }
-  __threadfence_system();
   __syncthreads();
-  // 2. publish, 3. wait for everyone (bounded)
-  if (tid < e.world) {
-    *reinterpret_cast<volatile unsigned long long*>(e.peer_flags[tid] + e.rank) = e.seq;
-    __threadfence_system();
-    volatile unsigned long long* mine = reinterpret_cast<volatile unsigned long long*>(e.peer_flags[e.rank] + tid);
-    const unsigned long long t0 = globaltimer_ns();
-    while (*mine != e.seq) {
-      if ((long long)(globaltimer_ns() - t0) > e.timeout_ns) { s_fail = 1; break; }
-      __nanosleep(200);
+  // 1. my partial -> area[rank] on every rank
+  const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(e.mine);
+  for (int i = tid; i < nv; i += kCombineThreads) {
+    const unsigned long long b = mine[i];
+    for (int p = 0; p < e.world_size; ++p) ll_publish_bits(e.peer_ll[p] + (size_t)e.rank * kPartialWords * 2, i, b, e.seq);
+  }
+  // 2. the world's partials out of my own buffer, as they arrive (bounded wait)
+  const unsigned long long t0 = globaltimer_ns();
+  for (int it = tid; it < e.world_size * nv; it += kCombineThreads) {
+    const int p = it / nv, i = it - p * nv;
+    const unsigned long long* src = e.peer_ll[e.rank] + (size_t)p * kPartialWords * 2;
+    unsigned long long b = 0;
+    int spins = 0;
+    while (!ll_try_read(src, i, e.seq, &b)) {
+      if (++spins > 64) {
+        if ((long long)(globaltimer_ns() - t0) > e.timeout_ns) { s_fail = 1; break; }
+        __nanosleep(50);
+      }
     }
-    __threadfence_system();
+    reinterpret_cast<unsigned long long*>(e.world + p)[i] = b;
   }
-  __syncthreads();
+  __syncthreads();  // (also makes the decoded partials visible to the CTA's other threads)
   if (s_fail) {
     if (tid == 0) {
       *e.error_out = 1;
@@ -319,9 +324,9 @@ __device__ __forceinline__ void exchange_body(const ExchangeArgs& e) {
   }
   // 4. the same merge as on one GPU, over the world's partials in rank order
   CombineArgs c = e.c;
-  c.partials = e.peer_slots[e.rank];
-  c.n_partials = e.world;
-  c.group = e.world;
+  c.partials = e.world;
+  c.n_partials = e.world_size;
+  c.group = e.world_size;
   c.solo = 1;
   combine_body(c);
 }
