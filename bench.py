@@ -34,7 +34,7 @@ TF32_MMA_PEAK_TFLOPS = 278.0  # tools/peaks/mma_peaks mma.sync m16n8k8 tf32
 F16_MMA_PEAK_TFLOPS = 556.0  # tools/peaks/mma_peaks mma.sync m16n8k16 f16
 # DRAM traffic of one rollout launch at K=8192 from the committed ncu capture (the kernel reads its ~45 KB image and
 # the nominal sequence, writes 8*K bytes of costs that stay in L2): compute-bound by four orders of magnitude
-NCU_DRAM_BYTES_PER_LAUNCH = {'tf32x3': 94464, 'f16x3': 70912}
+NCU_DRAM_BYTES_PER_LAUNCH = {'tf32x3': 75776, 'f16x3': 70912}
 
 
 # The driver's line is the default workload (BASELINE.json configs[1]).  The others exist to put the remaining configs
@@ -328,7 +328,7 @@ def main():
                         "frac": achieved / peak,
                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.precision) if args.workload == 'push' else None,
                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, one "
-                                          "ncu --set full capture (profiles/r1g_rollout_split3_tf32x3_k8192_ncu_summary.txt)",
+                                          "ncu --set full capture (profiles/r1h_rollout_split3_tf32x3_k8192_ncu_summary.txt; f16x3: r1e_rollout_split_f16x3_k8192_ncu_summary.txt)",
                         "kernel": "rollout (fused K x T): rollout_mma_split_kernel at this K (three warps per 16-sample "
                                   "tile: chain | decoder | cost), rollout_mma_kernel above K=12288",
                         "kernel_ms": roll_ms, "algorithmic_flop_per_launch": K * T * flop_per_step,
