@@ -63,7 +63,7 @@ struct tampc_mppi {
   double* d_predict = nullptr;  // action + cost scratch of tampc_mppi_predict
   tampc_partial* d_partials = nullptr;
   int n_partial_slots = 0;
-  // peer-memory exchange (multi-GPU): [parity][slots world | flags world]
+  // peer-memory exchange (multi-GPU): [parity][source rank][kPartialWords values][2 tagged words] (reduce_kernels.cuh)
   int comm_rank = 0, comm_world = 0;
   bool comm_connected = false;
   unsigned char* comm_local = nullptr;
@@ -736,13 +736,13 @@ cudaError_t launch_dependent(void (*kern)(KArgs...), int grid, int block, cudaSt
 }
 
 template <int NU>
-void launch_partials_exchange(const ReduceArgs& r, const CombineArgs& c, const ExchangeArgs& e, unsigned int* ticket, int n_chunks, cudaStream_t s) {
-  launch_dependent(partials_exchange_kernel<NU>, n_chunks, kCombineThreads, s, r, c, e, ticket);
+cudaError_t launch_partials_exchange(const ReduceArgs& r, const CombineArgs& c, const ExchangeArgs& e, unsigned int* ticket, int n_chunks, cudaStream_t s) {
+  return launch_dependent(partials_exchange_kernel<NU>, n_chunks, kCombineThreads, s, r, c, e, ticket);
 }
 
 template <int NU>
-void launch_partials_combine(const ReduceArgs& r, const CombineArgs& c, unsigned int* ticket, int n_chunks, cudaStream_t s) {
-  launch_dependent(partials_combine_kernel<NU>, n_chunks, kCombineThreads, s, r, c, ticket);
+cudaError_t launch_partials_combine(const ReduceArgs& r, const CombineArgs& c, unsigned int* ticket, int n_chunks, cudaStream_t s) {
+  return launch_dependent(partials_combine_kernel<NU>, n_chunks, kCombineThreads, s, r, c, ticket);
 }
 
 template <int NU>
@@ -795,12 +795,14 @@ int run_rollout_and_partials(tampc_mppi* h, int mode, bool keep_states, int fuse
     c.finalize = 0;
     c.partial_out = h->d_rank_partial;
     const ExchangeArgs e = make_exchange_args(h);
+    cudaError_t le;
     switch (h->cfg.nu) {
-      case 1: launch_partials_exchange<1>(r, c, e, h->d_ticket, h->n_chunks, h->stream); break;
-      case 2: launch_partials_exchange<2>(r, c, e, h->d_ticket, h->n_chunks, h->stream); break;
-      case 3: launch_partials_exchange<3>(r, c, e, h->d_ticket, h->n_chunks, h->stream); break;
-      default: launch_partials_exchange<4>(r, c, e, h->d_ticket, h->n_chunks, h->stream); break;
+      case 1: le = launch_partials_exchange<1>(r, c, e, h->d_ticket, h->n_chunks, h->stream); break;
+      case 2: le = launch_partials_exchange<2>(r, c, e, h->d_ticket, h->n_chunks, h->stream); break;
+      case 3: le = launch_partials_exchange<3>(r, c, e, h->d_ticket, h->n_chunks, h->stream); break;
+      default: le = launch_partials_exchange<4>(r, c, e, h->d_ticket, h->n_chunks, h->stream); break;
     }
+    CUDA_TRY(h, le);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
     h->cur ^= 1;
@@ -820,12 +822,14 @@ int run_rollout_and_partials(tampc_mppi* h, int mode, bool keep_states, int fuse
       c.host_ll = h->d_map;
       c.seq = ++h->seq;
     }
+    cudaError_t le;
     switch (h->cfg.nu) {
-      case 1: launch_partials_combine<1>(r, c, h->d_ticket, h->n_chunks, h->stream); break;
-      case 2: launch_partials_combine<2>(r, c, h->d_ticket, h->n_chunks, h->stream); break;
-      case 3: launch_partials_combine<3>(r, c, h->d_ticket, h->n_chunks, h->stream); break;
-      default: launch_partials_combine<4>(r, c, h->d_ticket, h->n_chunks, h->stream); break;
+      case 1: le = launch_partials_combine<1>(r, c, h->d_ticket, h->n_chunks, h->stream); break;
+      case 2: le = launch_partials_combine<2>(r, c, h->d_ticket, h->n_chunks, h->stream); break;
+      case 3: le = launch_partials_combine<3>(r, c, h->d_ticket, h->n_chunks, h->stream); break;
+      default: le = launch_partials_combine<4>(r, c, h->d_ticket, h->n_chunks, h->stream); break;
     }
+    CUDA_TRY(h, le);
     CUDA_TRY(h, cudaGetLastError());
     h->launches++;
     if (fuse == 1) h->cur ^= 1;
