@@ -1,3 +1,5 @@
+# End-of-round measurement pass (one GPU): bench arms, workloads, K sweep, ncu launch list and --set full captures.
+#   gpurun -- bash tools/final_run.sh ; outputs under gpurun_out/r1h/, summaries copied to profiles/r1h_*
 set -x
 mkdir -p gpurun_out/r1h
 cd /root/repo

@@ -1,3 +1,5 @@
+"""Rollout kernel, whole command and their difference (the softmax-update tail) at the bench's K=8192, with and without
+the L2 flush between commands:  python tools/flush_test.py   (B200; device-timed with CUDA events)."""
 import sys, os, numpy as np, torch
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 from conftest import load_golden
