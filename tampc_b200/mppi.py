@@ -75,6 +75,8 @@ class B200MPPI:
         self.running_cost = None
         self.terminal_state_cost = None
         self._state_np = None
+        self._x_buf, self._act_buf = np.zeros(self.nx), np.zeros(self.nu)  # command()'s persistent host buffers
+        self._x_ptr, self._act_ptr = L.dptr(self._x_buf), L.dptr(self._act_buf)
         self.step_dependency = True
 
         self.sample_offset, self.K_local = shard_bounds(self.K, rank, world_size)
@@ -289,7 +291,7 @@ class B200MPPI:
     def state(self):
         """MPPI.state: the start state of the last command as a float64 tensor (materialised on access: building a
         tensor costs microseconds that the command() latency does not need to pay)."""
-        return None if self._state_np is None else torch.from_numpy(self._state_np)
+        return None if self._state_np is None else torch.from_numpy(self._state_np.copy())
 
     @state.setter
     def state(self, value):
@@ -330,7 +332,15 @@ class B200MPPI:
         gp_eps: optional (T,M,K,ny) standard normals behind the GP residual's draws (parity tests)."""
         self._refresh_from_controller()
         self._arm_gp_draws(gp_eps)
-        x = self._state_array(state)
+        # The state and the action go through two persistent buffers whose ctypes pointers are built once: building a
+        # numpy array, its `.ctypes` view and a POINTER per command cost ~6 us of host time, as much as the whole
+        # softmax update costs on the device.
+        x = self._x_buf
+        if isinstance(state, np.ndarray) and state.dtype == np.float64 and state.shape == x.shape:
+            np.copyto(x, state)
+        else:
+            np.copyto(x, self._state_array(state))
+        self._state_np = x
         mode, nptr, local = L.NOISE_PHILOX, None, None
         if noise is not None:
             n = torch.as_tensor(noise).detach().to('cpu', torch.double).numpy()
@@ -338,12 +348,14 @@ class B200MPPI:
                 raise ValueError("noise must be (K,T,nu) = {}".format((self.K, self.T, self.nu)))
             local = np.ascontiguousarray(n[self.sample_offset:self.sample_offset + self.K_local])
             mode, nptr = L.NOISE_INJECTED, L.dptr(local)
-        action = np.empty(self.nu)
-        if self.world_size == 1:
-            self._check(self._lib.tampc_mppi_command(self._h, L.dptr(x), mode, nptr, L.dptr(action)))
+        if self.world_size == 1 or self._p2p:
+            # (sharded over peer memory: the merge kernel does the exchange itself, nothing to do on the host)
+            rc = self._lib.tampc_mppi_command(self._h, self._x_ptr, mode, nptr, self._act_ptr)
+            if rc != L.OK:
+                self._check(rc)
         else:
-            self._command_sharded(x, mode, nptr, action)
-        return torch.from_numpy(action)
+            self._command_sharded(x, mode, nptr, self._act_buf)
+        return torch.from_numpy(self._act_buf.copy())
 
     def _connect_peers(self):
         """Exchange CUDA IPC handles of the ranks' exchange buffers (torch.distributed is only the plumbing)."""
