@@ -297,3 +297,29 @@ def test_balanced_wave_kernels(cuda_lib, monkeypatch, precision, K):
     m.command(z['in.state'], noise=noise.numpy())
     assert float(((m.cost_total - cost).abs() / cost.abs()).max()) < 1e-6
     m.close()
+
+
+@pytest.mark.parametrize('precision', ['tf32x3', 'f64'])
+def test_opt_in_fused_update_matches_the_default_tail(cuda_lib, monkeypatch, precision):
+    """TAMPC_FUSE=1 (with the role-split kernels off) runs the softmax update inside the rollout launch and publishes
+    the result block from there; action, nominal sequence and stats must agree with the two-launch default."""
+    from tampc_b200.mppi import B200MPPI
+    z, spec = _spec('push_nominal', 500)
+    U0 = _U(z, spec)
+    noise = O.sample_noise(spec, 5, K=500)
+
+    def run():
+        m = B200MPPI(spec, precision=precision, U_init=U0)
+        a = m.command(z['in.state'], noise=noise.numpy())
+        out = (a.clone(), m.U.clone(), dict(m.stats), m.stats['launches'])
+        m.close()
+        return out
+
+    a0, U_0, st0, n0 = run()
+    monkeypatch.setenv('TAMPC_SPLIT', '0')
+    monkeypatch.setenv('TAMPC_FUSE', '1')
+    a1, U_1, st1, n1 = run()
+    assert n1 < n0  # one launch instead of two: the fused path really ran
+    assert st1['argmin'] == st0['argmin']
+    assert float((a1 - a0).abs().max()) < 1e-6
+    assert float((U_1 - U_0).abs().max()) < 1e-6
