@@ -42,7 +42,7 @@ extern "C" {
 
 #define TAMPC_MAX_NX 8
 #define TAMPC_MAX_NU 4
-#define TAMPC_MAX_TRAPS 16
+#define TAMPC_MAX_TRAPS 64
 #define TAMPC_MAX_GOAL_SETS 2
 #define TAMPC_MAX_SET_GOALS 8
 #define TAMPC_MAX_LAYERS 4
@@ -265,6 +265,9 @@ TAMPC_API int tampc_mppi_command_finish(tampc_mppi* h, const void* partials_dev,
 #define TAMPC_MAX_RANKS 8
 TAMPC_API int tampc_mppi_comm_init(tampc_mppi* h, int32_t rank, int32_t world, void* handle_out);
 TAMPC_API int tampc_mppi_comm_connect(tampc_mppi* h, const void* handles);
+/* Unmap the peers (after a failed connect on any rank, or a peer-exchange timeout: the command that timed out leaves
+ * the nominal sequence as it was and further sharded commands are refused until comm_init + comm_connect ran again). */
+TAMPC_API int tampc_mppi_comm_disconnect(tampc_mppi* h);
 
 /* ExperimentalMPPI._compute_rollout_costs(perturbed_actions): costs of caller-given actions (K_local,T,nu), no U update */
 TAMPC_API int tampc_mppi_rollout_costs(tampc_mppi* h, const double* state, const double* actions, int32_t horizon, double* cost_out,
@@ -275,6 +278,11 @@ TAMPC_API int tampc_mppi_get_rollouts(tampc_mppi* h, const double* state, double
 /* ControllerWithModelPrediction.predict_next_state (controller.py:312-313, online_controller.py:47-58): one step of the
  * nominal dynamics (guard, network, constrain_state) from `state` under `action`; next_state[nx]. */
 TAMPC_API int tampc_mppi_predict(tampc_mppi* h, const double* state, const double* action, double* next_state);
+/* OnlineMPC.predict_next_state (online_controller.py:47-58): the reference swaps the ORIGINAL nominal network in for this
+ * call (hybrid dynamics with class NOMINAL) — no online GP residual, no bad-state guard, no constrain_state.  Its result
+ * feeds diff_predicted, which drives the trap / local-model state machine, so it must stay the nominal prediction even
+ * while a GP residual is installed for the rollouts. */
+TAMPC_API int tampc_mppi_predict_nominal(tampc_mppi* h, const double* state, const double* action, double* next_state);
 
 TAMPC_API int tampc_mppi_query(tampc_mppi* h, int32_t what, double* out, size_t n_doubles);
 /* device pointer to the per-sample costs of the last rollout (double[num_local]); valid until the next call */

@@ -9,7 +9,7 @@ import numpy as np
 
 from . import spec as S
 
-MAX_NX, MAX_NU, MAX_TRAPS, MAX_GOAL_SETS, MAX_SET_GOALS, MAX_LAYERS, MAX_HORIZON = 8, 4, 16, 2, 8, 4, 128
+MAX_NX, MAX_NU, MAX_TRAPS, MAX_GOAL_SETS, MAX_SET_GOALS, MAX_LAYERS, MAX_HORIZON = 8, 4, 64, 2, 8, 4, 128
 GP_MAX_POINTS, GP_MAX_DIM, MAX_ROLLOUT_SAMPLES, GP_FIT_MAX_POINTS = 64, 8, 32, 50
 ABI_VERSION = 1
 
@@ -24,7 +24,7 @@ EXPORTS = [
     'tampc_mppi_set_model', 'tampc_mppi_set_cost', 'tampc_mppi_set_nominal', 'tampc_mppi_get_nominal',
     'tampc_mppi_command', 'tampc_mppi_command_begin', 'tampc_mppi_command_finish', 'tampc_mppi_rollout_costs',
     'tampc_mppi_get_rollouts', 'tampc_mppi_query', 'tampc_mppi_device_costs', 'tampc_mppi_synchronize',
-    'tampc_mppi_command_resident', 'tampc_mppi_set_state_resident', 'tampc_mppi_rollout_resident', 'tampc_mppi_comm_init', 'tampc_mppi_comm_connect', 'tampc_mppi_predict',
+    'tampc_mppi_command_resident', 'tampc_mppi_set_state_resident', 'tampc_mppi_rollout_resident', 'tampc_mppi_comm_init', 'tampc_mppi_comm_connect', 'tampc_mppi_comm_disconnect', 'tampc_mppi_predict', 'tampc_mppi_predict_nominal',
     'tampc_mppi_set_gp', 'tampc_mppi_set_gp_draws', 'tampc_gp_fit', 'tampc_gp_fit_last_error',
 ]
 
@@ -130,7 +130,9 @@ def load():
     lib.tampc_mppi_rollout_resident.argtypes = [vp, i32]
     lib.tampc_mppi_comm_init.argtypes = [vp, i32, i32, vp]
     lib.tampc_mppi_comm_connect.argtypes = [vp, vp]
+    lib.tampc_mppi_comm_disconnect.argtypes = [vp]
     lib.tampc_mppi_predict.argtypes = [vp, dp, dp, dp]
+    lib.tampc_mppi_predict_nominal.argtypes = [vp, dp, dp, dp]
     lib.tampc_mppi_set_gp.argtypes = [vp, C.POINTER(GpDesc), dp, C.c_size_t]
     lib.tampc_mppi_set_gp_draws.argtypes = [vp, dp, C.c_size_t]
     lib.tampc_gp_fit.argtypes = [i32, i32, i32, i32, dp, dp, i32, C.c_double, dp, dp, dp, C.POINTER(C.c_int64), dp]

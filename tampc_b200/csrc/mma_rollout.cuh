@@ -1012,7 +1012,12 @@ cudaError_t launch_rollout_mma_split(const RolloutArgs& a, int /*block*/, cudaSt
   const int per_block = L::TILES * L::SW;
   const int grid = (a.K_local + per_block - 1) / per_block;
   if constexpr (ROLES == 3) {
-    if (grid <= 148) return launch_rollout_mma_split_as<Model, 3, true>(a, grid, stream);  // at most one CTA (two tiles) per SM
+    static const int n_sm = [] {
+      int dev = 0, n = 148;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+      return n;
+    }();
+    if (grid <= n_sm) return launch_rollout_mma_split_as<Model, 3, true>(a, grid, stream);  // at most one CTA (two tiles) per SM
   }
   return launch_rollout_mma_split_as<Model, ROLES, false>(a, grid, stream);
 }

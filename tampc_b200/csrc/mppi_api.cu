@@ -48,6 +48,7 @@ struct tampc_mppi {
   tampc_model_desc model{};
   bool has_model = false, has_cost = false, has_nominal = false;
   int T = 0;
+  int n_sm = 148;
   uint64_t call = 0;
   long long launches = 0;
 
@@ -66,6 +67,7 @@ struct tampc_mppi {
   // peer-memory exchange (multi-GPU): [parity][source rank][kPartialWords values][2 tagged words] (reduce_kernels.cuh)
   int comm_rank = 0, comm_world = 0;
   bool comm_connected = false;
+  bool comm_broken = false;  // a peer exchange timed out: U / sequence numbers of the ranks may disagree until a reconnect
   unsigned char* comm_local = nullptr;
   unsigned char* comm_peer[kMaxRanks] = {nullptr};
   int* d_comm_error = nullptr;
@@ -470,11 +472,12 @@ struct LaunchPlan {
   int fuse_warps = 0;
 };
 
-constexpr int kMaxFusedWarps = 148 * 4;  // fused update only while one warp per SM sub-partition (latency-bound sizes)
+constexpr int kMaxFusedWarps = 160 * 4;  // capacity of the fused-update scratch: one warp per SM sub-partition (latency-bound sizes)
 
 LaunchPlan choose_launch(const tampc_mppi* h, int K) {
   const ModelVariant* v = h->variant;
   LaunchPlan p;
+  const int SM = h->n_sm;  // cudaDeviceProp::multiProcessorCount (148 on B200); the thresholds below are per SM
   const int eb = env_int("TAMPC_BLOCK", 0);
   if (h->gp_on) {
     // one thread per (sample, replica), FMA-layout networks; float32 networks for every precision but F64
@@ -497,7 +500,7 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     // the smallest tile (most warps) wins; a second wave costs a full kernel time, so beyond one wave of the
     // smallest tile move to the next tile size (measured on B200, tools/perf_sweep.py).
     const bool big = h->img_bytes > 100 * 1024;  // wide networks: one CTA per SM, always four warps sharing the image
-    const int cap32 = big ? 0 : 148 * 4, cap64 = big ? 0 : 148 * 3 * 2, cap128 = big ? 148 * 4 : 148 * 2 * 4;
+    const int cap32 = big ? 0 : SM * 4, cap64 = big ? 0 : SM * 3 * 2, cap128 = big ? SM * 4 : SM * 2 * 4;
     int idx = 0;  // NM = 1 << idx
     while (idx < max_idx && fmma[idx + 1] != nullptr && (K + (mt << idx) - 1) / (mt << idx) > cap128) ++idx;
     const int en = env_int("TAMPC_MMA_NM", 0);
@@ -510,26 +513,26 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     // Measured on B200 (push, T=40): a full wave takes 1.18x as long but holds 1.33x the samples (1M: 5.98 -> 5.68 ms),
     // so it is used when it does not add a wave (K=131072: 0.83 vs 0.78 ms).  TAMPC_WIDE=0/1 forces the choice.
     // one balanced wave: when 12 warps per SM are not enough for a single wave but 16 are (56 832 < K <= 75 776), one CTA
-    // per SM with ceil(warps / 148) warps gives every SM the same work (K=65536: 14 warps each instead of 16 on 108 SMs
+    // per SM with ceil(warps / SM) warps gives every SM the same work (K=65536: 14 warps each instead of 16 on 108 SMs
     // and 8 on 40).  TAMPC_SM_WAVE=0 disables.
     // ... and seven tiles per sub-partition (three two-tile warps + one one-tile warp) while 448 samples per SM are
     // enough: the wave then lasts as long as 3.5 instead of 4 two-tile warps per sub-partition.  TAMPC_MIX=0 disables.
     const rollout_launch_fn fmix = f16 ? v->f16_mma_mix : v->tf32_mma_mix;
-    if (!f64 && idx == 1 && !big && fmix && eb == 0 && warps > 148 * 12 && K <= 148 * 448 && env_int("TAMPC_MIX", 1) && env_int("TAMPC_SM_WAVE", 1)) {
+    if (!f64 && idx == 1 && !big && fmix && eb == 0 && warps > SM * 12 && K <= SM * 448 && env_int("TAMPC_MIX", 1) && env_int("TAMPC_SM_WAVE", 1)) {
       p.fn = fmix;
       p.block = 512;
       return p;
     }
     const rollout_launch_fn fsm = f16 ? v->f16_mma_sm : v->tf32_mma_sm;
-    if (!f64 && idx == 1 && !big && fsm && eb == 0 && warps > 148 * 12 && warps <= 148 * 16 && env_int("TAMPC_SM_WAVE", 1)) {
+    if (!f64 && idx == 1 && !big && fsm && eb == 0 && warps > SM * 12 && warps <= SM * 16 && env_int("TAMPC_SM_WAVE", 1)) {
       p.fn = fsm;
-      p.block = 32 * ((warps + 147) / 148);
+      p.block = 32 * ((warps + SM - 1) / SM);
       return p;
     }
     if (!f64 && idx == 1 && !big && fwide && eb == 0) {
       const int wide_env = env_int("TAMPC_WIDE", -1);
       const int ctas_d = (warps + 3) / 4, ctas_w = (warps + 7) / 8;
-      const bool wide = wide_env >= 0 ? wide_env != 0 : (ctas_d > 148 * 3 && ctas_w <= 148 * 2) || ctas_w >= 148 * 2 * 4;
+      const bool wide = wide_env >= 0 ? wide_env != 0 : (ctas_d > SM * 3 && ctas_w <= SM * 2) || ctas_w >= SM * 2 * 4;
       if (wide) {
         p.fn = fwide;
         p.block = 256;
@@ -548,7 +551,7 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     // kernel takes over.  TAMPC_SPLIT=0/1 forces the choice.
     {
       const int split_env = env_int("TAMPC_SPLIT", -1);
-      const bool split = !big && (split_env >= 0 ? split_env != 0 : (K + 15) / 16 <= 5 * 148 + 28);
+      const bool split = !big && (split_env >= 0 ? split_env != 0 : (K + 15) / 16 <= 5 * SM + 28);
       if (!f64 && idx == 0 && fsplit && split && en == 0) {
         // a third warp takes the cost off the decoder warp.  Measured on B200 (push, T=40, 3xTF32): K=500 64 -> 60 us,
         // 4736 67.5 -> 64, 8192 86.9 -> 77.2, 12288 117 -> 117 (peg K=8192, T=10: 27.9 -> 23.8).  TAMPC_SPLIT3=0/1 forces.
@@ -562,7 +565,7 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
       }
     }
     const int tiles = (K + 15) / 16, pipe_env = env_int("TAMPC_PIPE", -1);
-    const bool pipe = !big && (pipe_env >= 0 ? pipe_env != 0 : tiles <= 2 * 148);
+    const bool pipe = !big && (pipe_env >= 0 ? pipe_env != 0 : tiles <= 2 * SM);
     if (!f64 && idx == 0 && fpipe && pipe) {
       p.fn = fpipe;
       p.block = 64;
@@ -572,11 +575,11 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
   } else {
     const bool f64 = h->cfg.precision == TAMPC_PREC_F64;
     const bool has_s2 = !f64 && v->mixed_s2 != nullptr;
-    int S = (has_s2 && K >= 2 * 148 * 128 * 2) ? 2 : 1;
+    int S = (has_s2 && K >= 2 * SM * 128 * 2) ? 2 : 1;
     const int es = env_int("TAMPC_SAMPLES_PER_THREAD", 0);
     if (es == 1 || (es == 2 && has_s2)) S = es;
     const int threads = (K + S - 1) / S;
-    p.block = threads >= 2 * 148 * 128 ? 128 : (threads >= 2 * 148 * 64 ? 64 : 32);
+    p.block = threads >= 2 * SM * 128 ? 128 : (threads >= 2 * SM * 64 ? 64 : 32);
     switch (h->cfg.precision) {
       case TAMPC_PREC_F64: p.fn = v->f64_s1; break;
       case TAMPC_PREC_MIXED:
@@ -973,7 +976,14 @@ int download_action(tampc_mppi* h, double* action) {
     if (got == 0) { h->err = "combine kernel did not publish its result"; return TAMPC_ERR_CUDA; }
   }
   if (got < 0) {
-    h->err = "peer exchange timed out: a rank did not reach this command";
+    // the exchange kernel returned before writing the new nominal sequence: the flip done at launch time would make the
+    // next command read a stale buffer, and the ranks' sequence numbers no longer agree — undo the flip, keep the
+    // pre-command U, and refuse further sharded commands until the peers are connected again
+    h->cur ^= 1;
+    h->comm_broken = true;
+    cudaMemsetAsync(h->d_comm_error, 0, sizeof(int), h->stream);
+    h->err = "peer exchange timed out: a rank did not reach this command (nominal sequence left as before the command; "
+             "call comm_disconnect + comm_init + comm_connect on every rank to resume)";
     return TAMPC_ERR_CUDA;
   }
   memcpy(action, vals, sizeof(double) * h->cfg.nu);
@@ -1050,6 +1060,7 @@ TAMPC_API int tampc_mppi_create(const tampc_mppi_config* cfg, tampc_mppi** out) 
   }
   tampc_mppi* h = new tampc_mppi();
   h->cfg = *cfg;
+  h->n_sm = prop.multiProcessorCount;
   auto fail = [&](const std::string& msg, int code) {
     g_create_error = msg;
     tampc_mppi_destroy(h);
@@ -1120,7 +1131,7 @@ TAMPC_API void tampc_mppi_destroy(tampc_mppi* h) {
   cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_predict); cudaFree(h->d_partials); cudaFree(h->d_partials2); cudaFree(h->d_ticket); cudaFree(h->d_phdr); cudaFree(h->d_pwsum);
   cudaFree(h->d_rank_partial); cudaFree(h->d_action); cudaFree(h->d_stats); cudaFree(h->d_weights);
   for (int p = 0; p < h->comm_world; ++p)
-    if (h->comm_connected && p != h->comm_rank && h->comm_peer[p]) cudaIpcCloseMemHandle(h->comm_peer[p]);
+    if (p != h->comm_rank && h->comm_peer[p] && h->comm_peer[p] != h->comm_local) cudaIpcCloseMemHandle(h->comm_peer[p]);
   cudaFree(h->comm_local); cudaFree(h->d_comm_error); cudaFree(h->d_world_partials);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   if (h->h_map) cudaFreeHost(h->h_map);
@@ -1480,6 +1491,7 @@ TAMPC_API int tampc_mppi_command(tampc_mppi* h, const double* state, int32_t noi
   if ((rc = upload_state(h, state))) return rc;
   if ((rc = upload_noise(h, noise_mode, noise, h->T))) return rc;
   bool done = false;
+  if (h->comm_connected && h->comm_broken) { h->err = "peer exchange broken by an earlier timeout: reconnect the ranks first"; return TAMPC_ERR_STATE; }
   if (h->comm_connected) {
     // K-sharded: rank partial (fused into the rollout or via the partial kernels), then exchange + merge in one kernel
     if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/3, h->d_rank_partial, &done))) return rc;
@@ -1501,13 +1513,20 @@ TAMPC_API int tampc_mppi_comm_init(tampc_mppi* h, int32_t rank, int32_t world, v
   if (world < 2 || world > kMaxRanks || rank < 0 || rank >= world) { h->err = "comm_init: need 2 <= world <= 8 and 0 <= rank < world"; return TAMPC_ERR_INVALID; }
   static_assert(sizeof(cudaIpcMemHandle_t) == TAMPC_IPC_HANDLE_BYTES, "IPC handle size");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  if (!h->comm_local) {
+  if (h->comm_connected) { h->err = "comm_init on a connected handle: call comm_disconnect first"; return TAMPC_ERR_STATE; }
+  {
+    // (re)allocate for this world size; zeroed in stream order with the kernels that will poll it, and the zeroes are in
+    // memory before the IPC handle leaves this process (a peer's first store can only follow its comm_connect)
     const size_t bytes = 2 * comm_parity_bytes(world);
-    CUDA_TRY(h, cudaMalloc(&h->comm_local, bytes));
-    CUDA_TRY(h, cudaMemset(h->comm_local, 0, bytes));
-    CUDA_TRY(h, cudaMalloc(&h->d_comm_error, sizeof(int)));
-    CUDA_TRY(h, cudaMalloc(&h->d_world_partials, sizeof(tampc_partial) * kMaxRanks));
-    CUDA_TRY(h, cudaMemset(h->d_comm_error, 0, sizeof(int)));
+    if (h->comm_local && world != h->comm_world) { cudaFree(h->comm_local); h->comm_local = nullptr; }
+    if (!h->comm_local) CUDA_TRY(h, cudaMalloc(&h->comm_local, bytes));
+    if (!h->d_comm_error) CUDA_TRY(h, cudaMalloc(&h->d_comm_error, sizeof(int)));
+    if (!h->d_world_partials) CUDA_TRY(h, cudaMalloc(&h->d_world_partials, sizeof(tampc_partial) * kMaxRanks));
+    CUDA_TRY(h, cudaMemsetAsync(h->comm_local, 0, bytes, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_comm_error, 0, sizeof(int), h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->comm_seq = 0;
+    h->comm_broken = false;
   }
   h->comm_rank = rank;
   h->comm_world = world;
@@ -1527,10 +1546,32 @@ TAMPC_API int tampc_mppi_comm_connect(tampc_mppi* h, const void* handles) {
     cudaIpcMemHandle_t hd;
     memcpy(&hd, hb + (size_t)p * TAMPC_IPC_HANDLE_BYTES, sizeof hd);
     void* ptr = nullptr;
-    CUDA_TRY(h, cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    const cudaError_t oe = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (oe != cudaSuccess) {
+      for (int q = 0; q < p; ++q) {
+        if (q != h->comm_rank && h->comm_peer[q]) cudaIpcCloseMemHandle(h->comm_peer[q]);
+        h->comm_peer[q] = nullptr;
+      }
+      h->comm_peer[h->comm_rank] = nullptr;
+      h->err = std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(p) + "): " + cudaGetErrorString(oe);
+      return TAMPC_ERR_CUDA;
+    }
     h->comm_peer[p] = reinterpret_cast<unsigned char*>(ptr);
   }
   h->comm_connected = true;
+  return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_comm_disconnect(tampc_mppi* h) {
+  if (!h) return TAMPC_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (int p = 0; p < h->comm_world; ++p) {
+    if (p != h->comm_rank && h->comm_peer[p] && h->comm_peer[p] != h->comm_local) cudaIpcCloseMemHandle(h->comm_peer[p]);
+    h->comm_peer[p] = nullptr;
+  }
+  h->comm_connected = false;
+  h->comm_broken = false;
   return TAMPC_OK;
 }
 
@@ -1549,6 +1590,7 @@ TAMPC_API int tampc_mppi_command_resident(tampc_mppi* h, int32_t noise_mode) {
   if (rc) return rc;
   if (noise_mode != kModePhilox && !h->d_noise) { h->err = "resident command with injected noise needs a previous upload"; return TAMPC_ERR_STATE; }
   bool done = false;
+  if (h->comm_connected && h->comm_broken) { h->err = "peer exchange broken by an earlier timeout: reconnect the ranks first"; return TAMPC_ERR_STATE; }
   if (h->comm_connected) {
     if ((rc = run_rollout_and_partials(h, noise_mode, false, /*fuse=*/3, h->d_rank_partial, &done))) return rc;
     if (!done && (rc = run_combine(h, h->d_partials, h->n_chunks, /*finalize=*/0, h->d_rank_partial))) return rc;
@@ -1621,7 +1663,10 @@ TAMPC_API int tampc_mppi_get_rollouts(tampc_mppi* h, const double* state, double
   return TAMPC_OK;
 }
 
-TAMPC_API int tampc_mppi_predict(tampc_mppi* h, const double* state, const double* action, double* next_state) {
+// One step from `state` under `action`.  nominal_only = false: OnlineMPC._apply_dynamics (guard, network + GP residual,
+// constrain_state; controller.py:312-313).  nominal_only = true: OnlineMPC.predict_next_state (online_controller.py:47-58),
+// which swaps in the ORIGINAL nominal network for the call — no GP residual, no guard, no constrain_state.
+static int predict_impl(tampc_mppi* h, const double* state, const double* action, double* next_state, bool nominal_only) {
   if (!h || !state || !action || !next_state) return TAMPC_ERR_INVALID;
   if (!h->has_model || !h->has_cost) { h->err = "set_model / set_cost first"; return TAMPC_ERR_STATE; }
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
@@ -1629,9 +1674,8 @@ TAMPC_API int tampc_mppi_predict(tampc_mppi* h, const double* state, const doubl
   if ((rc = upload_state(h, state))) return rc;
   if ((rc = ensure_states(h))) return rc;
   // a one-sample, one-step "nominal" rollout whose nominal sequence is the given action
-  double* d_act = h->d_stats + 3;  // scratch: d_stats has 4 doubles, [3] is free; nu <= 4 needs its own buffer
   if (!h->d_predict) CUDA_TRY(h, cudaMalloc(&h->d_predict, sizeof(double) * (kMaxNu + 1)));
-  d_act = h->d_predict;
+  double* d_act = h->d_predict;
   CUDA_TRY(h, cudaMemcpyAsync(d_act, action, sizeof(double) * h->cfg.nu, cudaMemcpyHostToDevice, h->stream));
   RolloutArgs a{};
   a.image = h->d_weights;
@@ -1646,11 +1690,21 @@ TAMPC_API int tampc_mppi_predict(tampc_mppi* h, const double* state, const doubl
   a.K_local = 1;
   a.cost_out = h->d_predict + kMaxNu;
   a.states_out = h->d_states;
-  a.wrap_mask = h->model.wrap_mask;
-  a.has_guard = h->model.has_bad_state_guard;
+  a.wrap_mask = nominal_only ? 0u : h->model.wrap_mask;
+  a.has_guard = nominal_only ? 0 : h->model.has_bad_state_guard;
   a.bad_norm = h->model.bad_state_norm;
-  if ((rc = apply_gp_args(h, a, 1))) return rc;
-  const LaunchPlan plan = choose_launch(h, 1);
+  LaunchPlan plan;
+  if (nominal_only) {
+    // with a GP installed the image is in the FMA layout of the (sample, replica) kernels: the plain FMA kernels of
+    // the same precision read it as it is and know nothing of the residual
+    const bool gp_saved = h->gp_on;
+    h->gp_on = false;
+    plan = choose_launch(h, 1);
+    h->gp_on = gp_saved;
+  } else {
+    if ((rc = apply_gp_args(h, a, 1))) return rc;
+    plan = choose_launch(h, 1);
+  }
   if (!plan.fn) { h->err = "no kernel compiled for this precision"; return TAMPC_ERR_UNSUPPORTED; }
   CUDA_TRY(h, plan.fn(a, plan.block, h->stream));
   h->launches++;
@@ -1658,6 +1712,14 @@ TAMPC_API int tampc_mppi_predict(tampc_mppi* h, const double* state, const doubl
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->states_valid = false;
   return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_predict(tampc_mppi* h, const double* state, const double* action, double* next_state) {
+  return predict_impl(h, state, action, next_state, false);
+}
+
+TAMPC_API int tampc_mppi_predict_nominal(tampc_mppi* h, const double* state, const double* action, double* next_state) {
+  return predict_impl(h, state, action, next_state, true);
 }
 
 TAMPC_API int tampc_mppi_query(tampc_mppi* h, int32_t what, double* out, size_t n) {

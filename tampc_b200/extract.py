@@ -400,8 +400,16 @@ def cost_from_controller(ctrl, running_cost=None, terminal_state_cost='unset') -
         if getattr(ctrl.trap_cost, 'goal_weights', None) is not None:
             raise UnsupportedSpec("TrapSetCost.goal_weights are not used by the reference controllers")
         if len(ctrl.trap_set):
-            trap_x = np.stack([_np(x).reshape(nx) for x, _ in ctrl.trap_set])
-            trap_u = np.stack([_np(u).reshape(nu) for _, u in ctrl.trap_set])
+            traps = list(ctrl.trap_set)
+            if len(traps) > S.MAX_TRAPS:
+                # the reference appends a trap at every _start_recovery_mode without bound (online_controller.py:353);
+                # the cost program holds TAMPC_MAX_TRAPS: keep the most recent ones rather than abort mid-episode
+                import warnings
+                warnings.warn("trap set of {} exceeds TAMPC_MAX_TRAPS={}: the {} most recent traps are used".format(
+                    len(traps), S.MAX_TRAPS, S.MAX_TRAPS), RuntimeWarning, stacklevel=2)
+                traps = traps[-S.MAX_TRAPS:]
+            trap_x = np.stack([_np(x).reshape(nx) for x, _ in traps])
+            trap_u = np.stack([_np(u).reshape(nu) for _, u in traps])
     tw = ctrl.trap_set_weight
     tw = float(_np(tw).reshape(-1)[0]) if (torch.is_tensor(tw) or isinstance(tw, np.ndarray)) else float(tw)
     return S.CostSpec(kind=S.COST_GOAL_TRAP, nx=nx, nu=nu, ang_dims=ang, dist_scale=dist_scale, Q=_np(gc.Q), R=_np(gc.R),

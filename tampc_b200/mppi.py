@@ -110,11 +110,7 @@ class B200MPPI:
         self._gather = None
         self._p2p = False
         if world_size > 1 and exchange in ('auto', 'p2p'):
-            try:
-                self._connect_peers()
-            except Exception:
-                if exchange == 'p2p':
-                    raise
+            self._connect_peers(required=exchange == 'p2p')
         self._last_noise = None
         self._cost_fp = None
         self._cost_cache = None
@@ -357,17 +353,39 @@ class B200MPPI:
             self._command_sharded(x, mode, nptr, self._act_buf)
         return torch.from_numpy(self._act_buf.copy())
 
-    def _connect_peers(self):
-        """Exchange CUDA IPC handles of the ranks' exchange buffers (torch.distributed is only the plumbing)."""
+    def _connect_peers(self, required=False):
+        """Exchange CUDA IPC handles of the ranks' exchange buffers (torch.distributed is only the plumbing).
+
+        The decision to use the peer exchange is COLLECTIVE: a rank whose comm_init / cudaIpcOpenMemHandle fails still
+        takes part in every collective below, the ranks agree (all_reduce MIN of an ok flag) and either all of them
+        use the peer exchange or all of them fall back to the NCCL all-gather (or all raise when it was required)."""
         import torch.distributed as dist
+        err = None
         mine = (C.c_ubyte * L.IPC_HANDLE_BYTES)()
-        self._check(self._lib.tampc_mppi_comm_init(self._h, self.rank, self.world_size, C.cast(mine, C.c_void_p)))
+        try:
+            self._check(self._lib.tampc_mppi_comm_init(self._h, self.rank, self.world_size, C.cast(mine, C.c_void_p)))
+        except Exception as e:  # noqa: BLE001 - reported collectively below
+            err = e
         handles = [None] * self.world_size
-        dist.all_gather_object(handles, bytes(mine), group=self.group)
-        blob = (C.c_ubyte * (L.IPC_HANDLE_BYTES * self.world_size)).from_buffer_copy(b''.join(handles))
-        self._check(self._lib.tampc_mppi_comm_connect(self._h, C.cast(blob, C.c_void_p)))
+        dist.all_gather_object(handles, (err is None, bytes(mine)), group=self.group)
+        if err is None and all(ok for ok, _ in handles):
+            try:
+                blob = (C.c_ubyte * (L.IPC_HANDLE_BYTES * self.world_size)).from_buffer_copy(b''.join(h for _, h in handles))
+                self._check(self._lib.tampc_mppi_comm_connect(self._h, C.cast(blob, C.c_void_p)))
+            except Exception as e:  # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer rank could not export its exchange buffer")
+        oks = [None] * self.world_size
+        dist.all_gather_object(oks, err is None, group=self.group)
+        self._p2p = all(oks)
+        if not self._p2p:
+            # every rank leaves the peer exchange together; ranks that did connect drop their mappings
+            self._check(self._lib.tampc_mppi_comm_disconnect(self._h))
+            if required:
+                raise RuntimeError("peer exchange (exchange='p2p') could not be set up on every rank: {}".format(
+                    err if err is not None else "a peer rank failed"))
         dist.barrier(group=self.group)
-        self._p2p = True
 
     def _command_sharded(self, x, mode, nptr, action):
         """K-sharded command: local rollout + partial, one all_gather of tampc_partial (NCCL over NVLink), identical
@@ -433,13 +451,19 @@ class B200MPPI:
         self._check(self._lib.tampc_mppi_get_rollouts(self._h, L.dptr(x), L.dptr(out)))
         return torch.from_numpy(out).unsqueeze(0).repeat(num_rollouts, 1, 1)
 
-    def predict_next_state(self, state, control):
-        """ControllerWithModelPrediction.predict_next_state (controller.py:312-313): one step of the nominal dynamics,
-        returned as a (1, nx) float64 ndarray like the reference."""
+    def predict_next_state(self, state, control, nominal_only=False):
+        """ControllerWithModelPrediction.predict_next_state: one step from `state` under `control`, returned as a
+        (1, nx) float64 ndarray like the reference.
+
+        nominal_only=False is MPC.predict_next_state (controller.py:312-313) = `_apply_dynamics`: guard, the dynamics the
+        rollouts use (incl. an installed GP residual), constrain_state.  nominal_only=True is OnlineMPC.predict_next_state
+        (online_controller.py:47-58), which deliberately swaps the ORIGINAL nominal network in for the call: no GP residual,
+        no guard, no constrain_state — its result feeds diff_predicted and with it the trap / local-model state machine."""
         x = self._state_array(state)
         u = np.ascontiguousarray(torch.as_tensor(control).detach().to('cpu', torch.double).numpy().reshape(-1))
         out = np.empty(self.nx)
-        self._check(self._lib.tampc_mppi_predict(self._h, L.dptr(x), L.dptr(u), L.dptr(out)))
+        fn = self._lib.tampc_mppi_predict_nominal if nominal_only else self._lib.tampc_mppi_predict
+        self._check(fn(self._h, L.dptr(x), L.dptr(u), L.dptr(out)))
         return out.reshape(1, -1)
 
     def apply_dynamics(self, state, actions):
@@ -491,14 +515,37 @@ class B200MPPI:
         self._check(self._lib.tampc_mppi_synchronize(self._h))
 
 
+def _original_nominal_network(ctrl):
+    """The network OnlineMPC.predict_next_state evaluates (online_controller.py:47-58): dynamics._original_nominal_model,
+    or its prior.dyn_net if that is an online model.  None for controllers without a hybrid dynamics object."""
+    dyn = getattr(ctrl, 'dynamics', None)
+    orig = getattr(dyn, '_original_nominal_model', None)
+    if orig is None:
+        return None
+    if hasattr(orig, 'prior') and not hasattr(orig, 'model'):
+        orig = getattr(orig.prior, 'dyn_net', None)
+    return orig
+
+
 def install(ctrl, predict_on_device=True, **kwargs):
     """Swap `ctrl.mpc` (an ExperimentalMPPI built at controller.py:418-421) for a B200MPPI bound to `ctrl`.
 
     The controller's own state machine (trap detection, recovery, MAB; online_controller.py:437-515) is untouched:
-    it keeps assigning `ctrl.mpc.running_cost / terminal_state_cost`, calling `change_horizon` and `command`."""
+    it keeps assigning `ctrl.mpc.running_cost / terminal_state_cost`, calling `change_horizon` and `command`.
+
+    predict_on_device: also serve `ctrl.predict_next_state` (called once per control step, controller.py:306) with one
+    30 us launch.  For an OnlineMPC that is the ORIGINAL NOMINAL network only (no GP residual, guard or constrain_state,
+    online_controller.py:47-58) and only if that network is the one the kernels hold; for a plain MPC it is
+    `_apply_dynamics` (controller.py:312-313).  Otherwise the controller's own host method stays in place."""
     mpc = B200MPPI.from_controller(ctrl, **kwargs)
     ctrl.mpc = mpc
     if predict_on_device and hasattr(ctrl, 'predict_next_state'):
-        # MPC.command calls this once per control step (controller.py:306): one 30 us launch instead of a host forward
-        ctrl.predict_next_state = mpc.predict_next_state
+        dyn = getattr(ctrl, 'dynamics', None)
+        if hasattr(dyn, '_original_nominal_model'):
+            cur = getattr(dyn, 'nominal_model', None)
+            held = cur.prior.dyn_net if (hasattr(cur, 'prior') and not hasattr(cur, 'model')) else cur
+            if _original_nominal_network(ctrl) is held:
+                ctrl.predict_next_state = lambda state, control: mpc.predict_next_state(state, control, nominal_only=True)
+        else:
+            ctrl.predict_next_state = mpc.predict_next_state
     return mpc

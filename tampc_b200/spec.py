@@ -18,7 +18,7 @@ COS_SIM_EPS = 1e-8  # torch.cosine_similarity default eps (cost.py:70, block_pus
 
 MAX_NX = 8
 MAX_NU = 4
-MAX_TRAPS = 16
+MAX_TRAPS = 64
 MAX_GOAL_SETS = 2
 MAX_SET_GOALS = 8
 MAX_LAYERS = 4

@@ -247,7 +247,7 @@ def test_noise_and_actions_attributes(cuda_lib):
 
 
 @pytest.mark.parametrize('precision', ['f64', 'tf32x3', 'f16x3', 'mixed'])
-@pytest.mark.parametrize('K,T,P', [(1, 40, 3), (17, 7, 0), (33, 128, 16), (4737, 3, 16), (12289, 5, 1)])
+@pytest.mark.parametrize('K,T,P', [(1, 40, 3), (17, 7, 0), (33, 128, 16), (4737, 3, 64), (12289, 5, 1)])
 def test_ragged_and_maximum_sizes(cuda_lib, precision, K, T, P):
     """Edge sizes: a single sample, K that is not a multiple of any tile (idle rows / warps / tiles in every kernel
     family and on both sides of the role-split / single-warp switch-overs), the longest horizon (TAMPC_MAX_HORIZON) and
