@@ -285,6 +285,9 @@ TAMPC_API int tampc_mppi_predict(tampc_mppi* h, const double* state, const doubl
 TAMPC_API int tampc_mppi_predict_nominal(tampc_mppi* h, const double* state, const double* action, double* next_state);
 
 TAMPC_API int tampc_mppi_query(tampc_mppi* h, int32_t what, double* out, size_t n_doubles);
+/* which rollout kernel family and arithmetic a command of this handle runs (static string; "none" before set_model):
+ * the precision asked for in the config is a request, e.g. TF32X3 on the analytic pendulum runs the FMA kernel */
+TAMPC_API const char* tampc_mppi_kernel_name(tampc_mppi* h);
 /* device pointer to the per-sample costs of the last rollout (double[num_local]); valid until the next call */
 TAMPC_API int tampc_mppi_device_costs(tampc_mppi* h, void** dev_ptr);
 TAMPC_API int tampc_mppi_synchronize(tampc_mppi* h);

@@ -258,6 +258,12 @@ def terminal_cost(c: S.CostSpec, X_last):
 # ------------------------------------------------------------------------------------------------
 # MPPI
 
+# True: roll a deterministic model out M = rollout_samples times too, exactly as controller.py:355-380 does (what the
+# reference scripts execute at M=10); False: one replica (identical results).  bench.py's
+# `reference_M10` leg sets it to time the reference's literal work.
+LITERAL_REPLICAS = False
+
+
 def rollout_costs_replicated(spec: S.RolloutSpec, state, perturbed_actions, gp_eps, return_states=False):
     """ExperimentalMPPI._compute_rollout_costs (controller.py:340-381) with a stochastic (GP-sampled) model: M
     replicas per sample, cost = mean over replicas + rollout_var_cost * sum_t var_M(c_t) * discount^t.
@@ -289,7 +295,7 @@ def rollout_costs_replicated(spec: S.RolloutSpec, state, perturbed_actions, gp_e
 def rollout_costs(spec: S.RolloutSpec, state, perturbed_actions, return_states=False, gp_eps=None):
     """ExperimentalMPPI._compute_rollout_costs (controller.py:340-381) for a deterministic model: all M replicas
     are identical, so mean over M = one rollout and the variance term is 0 (SURVEY.md §7 #2)."""
-    if spec.dynamics.gp is not None:
+    if spec.dynamics.gp is not None or (LITERAL_REPLICAS and spec.sampler.rollout_samples > 1):
         return rollout_costs_replicated(spec, state, perturbed_actions, gp_eps, return_states)
     K, T, nu = perturbed_actions.shape
     x = _t(state).view(1, -1).repeat(K, 1)

@@ -464,6 +464,7 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
 // more samples per warp re-use each weight fragment.  TAMPC_SAMPLES_PER_THREAD / TAMPC_MMA_NM / TAMPC_BLOCK override.
 struct LaunchPlan {
   rollout_launch_fn fn = nullptr;
+  const char* name = "none";  // kernel family + arithmetic that will run (tampc_mppi_kernel_name)
   int block = 128;
   // > 0: the kernel can run the fused softmax update (fused_reduce.cuh); number of partial slots (warps) it uses.
   // Opt-in (TAMPC_FUSE=1): measured on B200 it saves ~3 us per command when the softmax is peaked (lambda = 0.01
@@ -482,9 +483,9 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
   if (h->gp_on) {
     // one thread per (sample, replica), FMA-layout networks; float32 networks for every precision but F64
     switch (h->cfg.precision) {
-      case TAMPC_PREC_F64: p.fn = v->gp.f64; break;
-      case TAMPC_PREC_F32: p.fn = v->gp.f32; break;
-      default: p.fn = v->gp.mixed; break;
+      case TAMPC_PREC_F64: p.fn = v->gp.f64; p.name = "rollout_gp_kernel f64 (DFMA)"; break;
+      case TAMPC_PREC_F32: p.fn = v->gp.f32; p.name = "rollout_gp_kernel f32 (FFMA2)"; break;
+      default: p.fn = v->gp.mixed; p.name = "rollout_gp_kernel f32 networks (FFMA2), f64 state+cost"; break;
     }
     p.block = 128;
     return p;
@@ -508,6 +509,7 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     const int warps = (K + (mt << idx) - 1) / (mt << idx);
     p.block = warps <= cap32 ? 32 : (warps <= cap64 ? 64 : 128);
     p.fn = fmma[idx];
+    p.name = f64 ? "rollout_mma_kernel f64 (DMMA m8n8k4)" : (f16 ? "rollout_mma_kernel 3xFP16 (HMMA m16n8k16)" : (big ? "rollout_mma(_stream)_kernel 3xTF32 (HMMA m16n8k8)" : "rollout_mma_kernel 3xTF32 (HMMA m16n8k8)"));
     if (eb == 32 || eb == 64 || eb == 128) p.block = eb;
     // throughput-bound 3xTF32: eight warps per CTA and two CTAs per SM give 16 resident warps instead of 12.
     // Measured on B200 (push, T=40): a full wave takes 1.18x as long but holds 1.33x the samples (1M: 5.98 -> 5.68 ms),
@@ -520,6 +522,7 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     const rollout_launch_fn fmix = f16 ? v->f16_mma_mix : v->tf32_mma_mix;
     if (!f64 && idx == 1 && !big && fmix && eb == 0 && warps > SM * 12 && K <= SM * 448 && env_int("TAMPC_MIX", 1) && env_int("TAMPC_SM_WAVE", 1)) {
       p.fn = fmix;
+      p.name = f16 ? "rollout_mma_mix_kernel 3xFP16 (HMMA m16n8k16)" : "rollout_mma_mix_kernel 3xTF32 (HMMA m16n8k8)";
       p.block = 512;
       return p;
     }
@@ -559,6 +562,7 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
         const int s3_env = env_int("TAMPC_SPLIT3", -1);
         const bool three = fsplit3 && (s3_env >= 0 ? s3_env != 0 : true);
         p.fn = three ? fsplit3 : fsplit;
+        p.name = f16 ? "rollout_mma_split_kernel 3xFP16 (HMMA m16n8k16)" : "rollout_mma_split_kernel 3xTF32 (HMMA m16n8k8)";
         p.block = three ? 192 : 128;
         p.fuse_warps = 0;
         return p;
@@ -568,6 +572,7 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     const bool pipe = !big && (pipe_env >= 0 ? pipe_env != 0 : tiles <= 2 * SM);
     if (!f64 && idx == 0 && fpipe && pipe) {
       p.fn = fpipe;
+      p.name = "rollout_mma_pipe_kernel 3xTF32 (HMMA m16n8k8)";
       p.block = 64;
       p.fuse_warps = env_int("TAMPC_FUSE", 0) ? tiles : 0;
       return p;
@@ -581,11 +586,15 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     const int threads = (K + S - 1) / S;
     p.block = threads >= 2 * SM * 128 ? 128 : (threads >= 2 * SM * 64 ? 64 : 32);
     switch (h->cfg.precision) {
-      case TAMPC_PREC_F64: p.fn = v->f64_s1; break;
+      case TAMPC_PREC_F64: p.fn = v->f64_s1; p.name = "rollout_kernel f64 (DFMA)"; break;
       case TAMPC_PREC_MIXED:
       case TAMPC_PREC_TF32X3:
-      case TAMPC_PREC_F16X3: p.fn = S == 2 ? v->mixed_s2 : v->mixed_s1; break;
-      default: p.fn = S == 2 ? v->f32_s2 : v->f32_s1; break;
+      case TAMPC_PREC_F16X3:
+        // shapes without network layers (analytic pendulum) have nothing for the tensor cores: the FMA kernel runs
+        p.fn = S == 2 ? v->mixed_s2 : v->mixed_s1;
+        p.name = "rollout_kernel f32 arithmetic (FFMA2), f64 state+cost";
+        break;
+      default: p.fn = S == 2 ? v->f32_s2 : v->f32_s1; p.name = "rollout_kernel f32 (FFMA2)"; break;
     }
   }
   if (eb == 32 || eb == 64 || eb == 128) p.block = eb;
@@ -1788,6 +1797,11 @@ TAMPC_API int tampc_mppi_query(tampc_mppi* h, int32_t what, double* out, size_t 
     }
     default: h->err = "unknown query"; return TAMPC_ERR_INVALID;
   }
+}
+
+TAMPC_API const char* tampc_mppi_kernel_name(tampc_mppi* h) {
+  if (!h || !h->has_model) return "none";
+  return choose_launch(h, h->cfg.num_local).name;
 }
 
 TAMPC_API int tampc_mppi_device_costs(tampc_mppi* h, void** dev_ptr) {

@@ -439,6 +439,11 @@ class B200MPPI:
         return self.perturbed_action.unsqueeze(0)
 
     @property
+    def kernel_name(self):
+        """Rollout kernel family + arithmetic a command of this handle runs (the precision argument is a request)."""
+        return self._lib.tampc_mppi_kernel_name(self._h).decode()
+
+    @property
     def stats(self):
         s = self._query(L.Q_STATS, 4)
         return {'beta': s[0], 'eta': s[1], 'argmin': int(s[2]), 'launches': int(s[3])}

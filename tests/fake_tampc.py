@@ -119,7 +119,7 @@ def make_controller(spec: S.RolloutSpec, U):
     cfg = types.SimpleNamespace(predict_difference=True, predict_all_dims=True)
     ds = types.SimpleNamespace(preprocessor=types.SimpleNamespace(tsf=tsf), original_config=lambda: cfg)
     nominal = types.SimpleNamespace(model=net, ds=ds)
-    ctrl.dynamics = types.SimpleNamespace(nominal_model=nominal, num_local_models=lambda: 0)
+    ctrl.dynamics = types.SimpleNamespace(nominal_model=nominal, _original_nominal_model=nominal, num_local_models=lambda: 0)  # hybrid_model.py:113
     # ---- cost wiring of MPC.__init__ (controller.py:216-230)
     ctrl.goal_cost = types.SimpleNamespace(Q=_t(c.Q) if c.kind == S.COST_GOAL_TRAP else torch.eye(d.nx, dtype=torch.double),
                                            R=_t(c.R) if c.kind == S.COST_GOAL_TRAP else torch.eye(d.nu, dtype=torch.double),

@@ -23,7 +23,12 @@ def test_install_on_live_controller_reproduces_reference(cuda_lib, case):
             continue
         np.testing.assert_allclose(np.asarray(a[k], dtype=float), np.asarray(b[k], dtype=float), rtol=0, atol=1e-12, err_msg=k)
     mpc = install(ctrl, precision='f64')
-    assert ctrl.mpc is mpc and ctrl.predict_next_state == mpc.predict_next_state
+    assert ctrl.mpc is mpc
+    # OnlineMPC.predict_next_state on the device: the nominal network only (online_controller.py:47-58)
+    from oracle import mppi_oracle as O
+    x, u = torch.from_numpy(z['in.state']), torch.from_numpy(z['in.U'][0])
+    want = O.predict(spec.dynamics, x.view(1, -1), u.view(1, -1)).numpy()
+    np.testing.assert_allclose(ctrl.predict_next_state(x, u), want, rtol=0, atol=1e-10)
     action = ctrl.mpc.command(torch.from_numpy(z['in.state']), noise=z['in.noise']).numpy()
     np.testing.assert_allclose(action, z['ref.action'], rtol=0, atol=1e-8)
     rel = np.max(np.abs(mpc.cost_total.numpy() - z['ref.cost_total']) / np.abs(z['ref.cost_total']))
@@ -102,6 +107,18 @@ def test_online_gp_is_followed_when_the_nominal_model_is_swapped(cuda_lib, case)
     rel = np.max(np.abs(mpc.cost_total.numpy() - z['ref.cost_total']) / np.abs(z['ref.cost_total']))
     assert rel < 1e-9 and mpc.stats['argmin'] == int(z['ref.argmin'])
     np.testing.assert_allclose(action, z['ref.action'], rtol=0, atol=1e-8)
+    # predict_next_state stays the ORIGINAL nominal network while the GP serves the rollouts (online_controller.py:47-58):
+    # its error against the observed state is what detects (leaving) non-nominal dynamics
+    from oracle import mppi_oracle as O
+    import copy
+    d_nom = copy.copy(spec.dynamics)
+    d_nom.gp = None
+    x, u = torch.from_numpy(z['in.state']), torch.from_numpy(z['in.U'][0])
+    want = O.predict(d_nom, x.view(1, -1), u.view(1, -1)).numpy()
+    np.testing.assert_allclose(ctrl.predict_next_state(x, u), want, rtol=0, atol=1e-10)
+    big = torch.tensor([2e5, 0., 9., 0., 0.], dtype=torch.double)  # beyond the guard, yaw outside (-pi, pi]: neither applies here
+    np.testing.assert_allclose(ctrl.predict_next_state(big, u), O.predict(d_nom, big.view(1, -1), u.view(1, -1)).numpy(), rtol=1e-9, atol=1e-6)
+    assert np.max(np.abs(mpc.predict_next_state(x, u) - want)) > 1e-9  # (the full _apply_dynamics step does include the residual)
     # a GP update between commands (new data point): the next command must see it
     g2 = fake_tampc.make_online_gp(spec, nominal)
     g2.xu, g2.y = g2.xu[:-1], g2.y[:-1]

@@ -119,9 +119,26 @@ def test_oracle_follows_the_live_online_gp_through_updates():
         rel = ((out['cost_total'] - ctrl.mpc.cost_total).abs() / ctrl.mpc.cost_total.abs()).max().item()
         assert rel < 1e-10 and out['argmin'] == int(ctrl.mpc.cost_total.argmin())
         assert (out['action'] - a_ref).abs().max().item() < 1e-11
+        # OnlineMPC.predict_next_state (online_controller.py:47-58) ignores the installed GP: it evaluates the ORIGINAL
+        # nominal network, without guard or constrain_state — what tampc_mppi_predict_nominal serves on the device
+        nominal_only = O.predict(_without_gp(spec.dynamics), x.view(1, -1), u.view(1, -1))
+        with torch.no_grad():
+            got = torch.from_numpy(ctrl.predict_next_state(x.clone(), u.clone()))
+        assert (got - nominal_only).abs().max().item() < 1e-12
+        with_gp, _ = O.apply_dynamics(spec.dynamics, x.view(1, -1), u.view(1, -1), torch.zeros(1, 5, dtype=torch.double))
+        assert (with_gp - nominal_only).abs().max().item() > 1e-9
+        from tampc_b200.mppi import _original_nominal_network
+        assert _original_nominal_network(ctrl) is ctrl.dynamics.nominal_model.prior.dyn_net
     # leaving non-nominal dynamics restores the plain network (hybrid_model.py:201-202)
     ctrl.dynamics.use_normal_nominal_model()
     assert extract.spec_from_controller(ctrl).dynamics.gp is None
+
+
+def _without_gp(d):
+    import copy
+    d = copy.copy(d)
+    d.gp = None
+    return d
 
 
 def test_device_fitted_gp_class_is_recognised_by_the_reference():
