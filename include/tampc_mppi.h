@@ -87,7 +87,12 @@ typedef enum tampc_dyn_kind {
   TAMPC_DYN_PENDULUM = 2 /* scripts/pendulum.py:223-241 */
 } tampc_dyn_kind;
 
-typedef enum tampc_cost_kind { TAMPC_COST_GOAL_TRAP = 0, TAMPC_COST_RECOVERY = 1 } tampc_cost_kind;
+typedef enum tampc_cost_kind {
+  TAMPC_COST_GOAL_TRAP = 0, /* MPC._running_cost: QR goal cost + trap-set cost (+ terminal) */
+  TAMPC_COST_RECOVERY = 1,  /* OnlineMPPI._recovery_running_cost: weighted min-distance goal sets */
+  TAMPC_COST_APF = 2        /* APFVO / APFSP potentials on the NEXT state only (online_controller.py:554-664; cost.py:236-289):
+                               [use_goal] d'Qd  +  gain * sum_i clamp((1/rho_i - 1/rho0)^2, 0, 1e5) [rho_i <= rho0]  +  [helicoid] */
+} tampc_cost_kind;
 
 /* Sequential(Linear, LeakyReLU, ..., Linear).  dims[0..n_layers]; w_off/b_off index the float64 `params`
  * array passed to tampc_mppi_set_model; W is row-major (out, in) as in torch.nn.Linear.weight. */
@@ -172,6 +177,14 @@ typedef struct tampc_cost_desc {
   double set_goals[TAMPC_MAX_GOAL_SETS][TAMPC_MAX_SET_GOALS][TAMPC_MAX_NX];
   double set_weight[TAMPC_MAX_GOAL_SETS];
   double recovery_scale;
+  /* APF program (TAMPC_COST_APF): goal / Q as above (no action term: the reference passes U=None); repulsive states in
+   * trap_x[0..n_traps) (APFVO's trap_set holds states only, online_controller.py:580-581) */
+  int32_t apf_use_goal;   /* 1: add the goal cost d'Qd (APFVO always; APFSP when no obstacle is active) */
+  int32_t apf_helicoid;   /* 1: APFHelicoid2D(rxy, oxy) (cost.py:268-289) */
+  int32_t apf_clockwise;
+  double apf_max_dist;    /* ArtificialRepulsionCost.max_dist_influence (rho0) */
+  double apf_gain;        /* ArtificialRepulsionCost.gain */
+  double apf_rxy[2], apf_oxy[2];
 } tampc_cost_desc;
 
 typedef struct tampc_mppi_config {
@@ -283,6 +296,17 @@ TAMPC_API int tampc_mppi_predict(tampc_mppi* h, const double* state, const doubl
  * feeds diff_predicted, which drives the trap / local-model state machine, so it must stay the nominal prediction even
  * while a GP residual is installed for the rollouts. */
 TAMPC_API int tampc_mppi_predict_nominal(tampc_mppi* h, const double* state, const double* action, double* next_state);
+
+/* One-step action selection of the APF baselines (online_controller.py:583-590, 657-664): push `n` candidate actions
+ * (n <= num_local, host (n, nu)) through _apply_dynamics from `state`, evaluate the installed cost program on the next
+ * states, take the argmin ON THE DEVICE (lowest index wins ties, like torch.argmin).  index_out: winning row; cost_out:
+ * its cost; next_state_out[nx]: the state it leads to.  One rollout launch + one argmin launch, one small D2H. */
+TAMPC_API int tampc_mppi_select_action(tampc_mppi* h, const double* state, const double* actions, int32_t n, int64_t* index_out, double* cost_out,
+                                       double* next_state_out);
+/* goal_cost(x) and trap_cost(x) of OnlineMPPI.normalize_trapset_cost_to_state (online_controller.py:517-530) for n states
+ * (host (n, nx)): the QR goal cost without an action term and the raw trap-set cost with c_u = 1 (U=None, cost.py:177),
+ * unweighted.  Uses the installed GOAL_TRAP cost program. */
+TAMPC_API int tampc_mppi_state_costs(tampc_mppi* h, const double* states, int32_t n, double* goal_cost_out, double* trap_cost_out);
 
 TAMPC_API int tampc_mppi_query(tampc_mppi* h, int32_t what, double* out, size_t n_doubles);
 /* which rollout kernel family and arithmetic a command of this handle runs (static string; "none" before set_model):

@@ -233,11 +233,63 @@ def recovery_cost(c: S.CostSpec, X):
     return total
 
 
+def apf_cost(c: S.CostSpec, X):
+    """The APF baselines' potential of the next states (U=None): APFVO's ComposeCost([goal_cost, ArtificialRepulsionCost])
+    (online_controller.py:561-564, cost.py:236-265), APFSP's goal_cost | APFHelicoid2D (online_controller.py:639-662,
+    cost.py:268-289)."""
+    total = torch.zeros(X.shape[0], dtype=DT, device=DEVICE)
+    if c.apf_use_goal:
+        d = compare_to_goal(c, X, _t(c.goal))
+        total = total + torch.einsum('ni,ij,nj->n', d, _t(c.Q), d)  # qr_cost with U=None (cost.py:11-18)
+    rep = torch.zeros_like(total)
+    for s in c.trap_x:
+        rho = state_dist(c, compare_to_goal(c, X, _t(s)))
+        inside = rho <= c.apf_max_dist
+        v = torch.zeros_like(rho)
+        v[inside] = (1 / rho[inside] - 1 / c.apf_max_dist).square()
+        rep = rep + torch.clamp(v, 0, S.TRAP_MAX_COST)
+    total = total + rep * c.apf_gain
+    if c.apf_helicoid is not None:
+        rxy, oxy, cw = c.apf_helicoid
+        orig = _t(oxy) - _t(rxy)
+        orig = torch.atan2(orig[1], orig[0])
+        d = _t(oxy) - X[:, :2]
+        ang = orig - torch.atan2(d[:, 1], d[:, 0])
+        ang = torch.where(ang > math.pi, ang - 2 * math.pi, ang)   # math_utils.angular_diff_batch: one wrap
+        ang = torch.where(ang < -math.pi, ang + 2 * math.pi, ang)
+        total = total + ang * torch.norm(d, dim=1) * (1 if cw else -1)
+    return total
+
+
+def select_action(spec: S.RolloutSpec, state, actions):
+    """APFVO / APFSP action selection (online_controller.py:583-590, 657-664): argmin of the potential of the states the
+    candidate actions lead to.  Returns (index, cost (n,), next_states (n, nx))."""
+    x = _t(state).view(1, -1).repeat(actions.shape[0], 1)
+    nxt, _ = apply_dynamics(spec.dynamics, x, _t(actions))
+    c = apf_cost(spec.cost, nxt)
+    return int(torch.argmin(c)), c, nxt
+
+
+def normalize_trapset_cost_to_state(c: S.CostSpec, x):
+    """OnlineMPPI.normalize_trapset_cost_to_state (online_controller.py:517-530): goal_cost(x) / trap_cost(x) with the raw
+    (unweighted, U=None -> c_u = 1) TrapSetCost summed over the traps (controller.py:245-246, cost.py:154-189)."""
+    x = _t(x).view(1, -1)
+    d = compare_to_goal(c, x, _t(c.goal))
+    goal = torch.einsum('ni,ij,nj->n', d, _t(c.Q), d)
+    trap = torch.zeros(1, dtype=DT, device=DEVICE)
+    for tx in c.trap_x:
+        cx = state_dist(c, compare_to_goal(c, x, _t(tx))).square()
+        trap = trap + torch.clamp(1 / cx, 0, S.TRAP_MAX_COST)
+    return goal / trap, goal, trap
+
+
 def running_cost(c: S.CostSpec, X, U):
     """MPC._running_cost -> ComposeCost([goal_cost, trap_cost]) (controller.py:227,248-249; cost.py:213-235)
     or OnlineMPPI._recovery_running_cost (online_controller.py:188-189)."""
     if c.kind == S.COST_RECOVERY:
         return recovery_cost(c, X)
+    if c.kind == S.COST_APF:
+        return apf_cost(c, X)
     cost = qr_cost(c, X, U)
     if c.use_trap_cost:
         cost = cost + trap_cost(c, X, U)

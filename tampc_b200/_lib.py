@@ -23,7 +23,7 @@ EXPORTS = [
     'tampc_mppi_last_error', 'tampc_mppi_abi_version', 'tampc_mppi_create', 'tampc_mppi_destroy',
     'tampc_mppi_set_model', 'tampc_mppi_set_cost', 'tampc_mppi_set_nominal', 'tampc_mppi_get_nominal',
     'tampc_mppi_command', 'tampc_mppi_command_begin', 'tampc_mppi_command_finish', 'tampc_mppi_rollout_costs',
-    'tampc_mppi_get_rollouts', 'tampc_mppi_query', 'tampc_mppi_kernel_name', 'tampc_mppi_device_costs', 'tampc_mppi_synchronize',
+    'tampc_mppi_get_rollouts', 'tampc_mppi_query', 'tampc_mppi_select_action', 'tampc_mppi_state_costs', 'tampc_mppi_kernel_name', 'tampc_mppi_device_costs', 'tampc_mppi_synchronize',
     'tampc_mppi_command_resident', 'tampc_mppi_set_state_resident', 'tampc_mppi_rollout_resident', 'tampc_mppi_comm_init', 'tampc_mppi_comm_connect', 'tampc_mppi_comm_disconnect', 'tampc_mppi_predict', 'tampc_mppi_predict_nominal',
     'tampc_mppi_set_gp', 'tampc_mppi_set_gp_draws', 'tampc_gp_fit', 'tampc_gp_fit_last_error',
 ]
@@ -65,7 +65,9 @@ class CostDesc(C.Structure):
                 ('trap_weight', C.c_double), ('has_terminal', C.c_int32), ('terminal_multiplier', C.c_double),
                 ('n_sets', C.c_int32), ('set_size', C.c_int32 * MAX_GOAL_SETS),
                 ('set_goals', ((C.c_double * MAX_NX) * MAX_SET_GOALS) * MAX_GOAL_SETS),
-                ('set_weight', C.c_double * MAX_GOAL_SETS), ('recovery_scale', C.c_double)]
+                ('set_weight', C.c_double * MAX_GOAL_SETS), ('recovery_scale', C.c_double),
+                ('apf_use_goal', C.c_int32), ('apf_helicoid', C.c_int32), ('apf_clockwise', C.c_int32),
+                ('apf_max_dist', C.c_double), ('apf_gain', C.c_double), ('apf_rxy', C.c_double * 2), ('apf_oxy', C.c_double * 2)]
 
 
 class MppiConfig(C.Structure):
@@ -123,6 +125,8 @@ def load():
     lib.tampc_mppi_rollout_costs.argtypes = [vp, dp, dp, i32, dp, dp]
     lib.tampc_mppi_get_rollouts.argtypes = [vp, dp, dp]
     lib.tampc_mppi_query.argtypes = [vp, i32, dp, C.c_size_t]
+    lib.tampc_mppi_select_action.argtypes = [vp, dp, dp, i32, C.POINTER(C.c_int64), dp, dp]
+    lib.tampc_mppi_state_costs.argtypes = [vp, dp, i32, dp, dp]
     lib.tampc_mppi_kernel_name.restype = C.c_char_p
     lib.tampc_mppi_kernel_name.argtypes = [vp]
     lib.tampc_mppi_device_costs.argtypes = [vp, C.POINTER(vp)]
@@ -270,6 +274,7 @@ def _padded(a, shape):
 def cost_desc(c: S.CostSpec):
     d = CostDesc()
     d.kind, d.nx, d.nu = c.kind, c.nx, c.nu
+    d.apf_max_dist = 1.0
     d.ang_mask, d.usim_mask = _mask(c.ang_dims), _mask(c.usim_dims)
     _fill(d.dist_scale, c.dist_scale)
     if c.kind == S.COST_GOAL_TRAP:
@@ -284,6 +289,18 @@ def cost_desc(c: S.CostSpec):
         d.trap_weight = c.trap_weight
         d.has_terminal = int(c.terminal_multiplier is not None)
         d.terminal_multiplier = c.terminal_multiplier if c.terminal_multiplier is not None else 0.0
+    elif c.kind == S.COST_APF:
+        _fill(d.goal, c.goal)
+        _fill(d.Q, _padded(c.Q, (MAX_NX, MAX_NX)))
+        d.n_traps = len(c.trap_x)
+        if d.n_traps:
+            _fill(d.trap_x, _padded(c.trap_x, (d.n_traps, MAX_NX)))
+        d.apf_use_goal = int(c.apf_use_goal)
+        d.apf_max_dist, d.apf_gain = float(c.apf_max_dist), float(c.apf_gain)
+        if c.apf_helicoid is not None:
+            rxy, oxy, cw = c.apf_helicoid
+            d.apf_helicoid, d.apf_clockwise = 1, int(cw)
+            d.apf_rxy[0], d.apf_rxy[1], d.apf_oxy[0], d.apf_oxy[1] = rxy[0], rxy[1], oxy[0], oxy[1]
     else:
         d.n_sets = len(c.goal_sets)
         sets = np.zeros((MAX_GOAL_SETS, MAX_SET_GOALS, MAX_NX))

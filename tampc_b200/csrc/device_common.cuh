@@ -86,6 +86,10 @@ struct CostS {
   CT trap_weight, terminal_multiplier;
   CT set_weight[TAMPC_MAX_GOAL_SETS];
   CT recovery_scale;
+  // APF program (cost.py:236-289)
+  int apf_use_goal, apf_helicoid, apf_clockwise;
+  CT apf_max_dist, apf_inv_max_dist, apf_gain, apf_orig_angle;
+  ST apf_oxy[2];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -110,6 +114,8 @@ __device__ __forceinline__ float t_sqrt_fast(float a) { return a * rsqrtf(fmaxf(
 __device__ __forceinline__ double t_sqrt_fast(double a) { return sqrt(a); }
 __device__ __forceinline__ float t_floor(float a) { return floorf(a); }
 __device__ __forceinline__ double t_floor(double a) { return floor(a); }
+__device__ __forceinline__ float t_atan2(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double t_atan2(double y, double x) { return atan2(y, x); }
 
 // torch.remainder(a + pi, 2pi) - pi  (math_utils.angle_normalize; scripts/push_main.py:192), computed as
 // y - 2pi*floor(y/2pi) with one correction step instead of the (slow, looping) fmod; agrees with the fmod form
@@ -489,9 +495,38 @@ __device__ __forceinline__ CT quad_form_x(const CT* __restrict__ Q, const CT (&d
 // running cost of (x_next, u)      [controller.py:248-249 -> cost.py:213-235]
 // `part` of `nparts`: lanes that mirror the same sample share the work — the trap-set terms are dealt round-robin,
 // everything else goes to part 0; the caller adds the parts' sums (once, after the horizon loop).
+// APFVO / APFSP potentials of a (next) state (online_controller.py:564,586,639-662; cost.py:236-289): optional goal cost
+// d'Qd (U=None: no action term), artificial repulsion from the trap states, optional helicoid around the active obstacle.
+template <typename ST, typename CT, int NX>
+__device__ __forceinline__ CT apf_cost(const CostS<ST, CT>& c, const ST (&x)[NX]) {
+  CT d[NX];
+  CT cost = (CT)0;
+  if (c.apf_use_goal) {
+    state_diff<ST, CT, NX>(c.ang_mask, x, c.goal, d);
+    cost = quad_form_x<CT, NX>(c.Q, d);
+  }
+  CT rep = (CT)0;
+  for (int p = 0; p < c.n_traps; ++p) {
+    state_diff<ST, CT, NX>(c.ang_mask, x, c.trap_x[p], d);
+    const CT rho = t_sqrt(dist_sq<CT, NX>(c.dist_scale, d));
+    CT v = (CT)1 / rho - c.apf_inv_max_dist;   // rho = 0 -> inf -> clamped, like torch
+    v = t_max(t_min(v * v, (CT)kTrapMaxCost), (CT)0);
+    rep += rho <= c.apf_max_dist ? v : (CT)0;
+  }
+  cost = t_fma(rep, c.apf_gain, cost);
+  if (c.apf_helicoid) {
+    const CT dx = (CT)(c.apf_oxy[0] - x[0]), dy = (CT)(c.apf_oxy[1] - x[1]);
+    const CT ang = angular_wrap_once<CT>(c.apf_orig_angle - t_atan2(dy, dx));
+    const CT hel = ang * t_sqrt(t_fma(dx, dx, dy * dy));
+    cost += c.apf_clockwise ? hel : -hel;
+  }
+  return cost;
+}
+
 template <typename ST, typename CT, int NX, int NU>
 __device__ __forceinline__ CT running_cost(const CostS<ST, CT>& c, const ST (&x)[NX], const ST (&us)[NU], int part = 0, int nparts = 1) {
   CT d[NX];
+  if (c.kind == TAMPC_COST_APF) return part == 0 ? apf_cost<ST, CT, NX>(c, x) : (CT)0;
   if (c.kind == TAMPC_COST_RECOVERY) {
     if (part != 0) return (CT)0;
     CT total = (CT)0;
@@ -572,7 +607,7 @@ struct CostHot {
 template <typename ST, typename CT, int NX, int NU>
 __device__ __forceinline__ CT running_cost_hot(const CostS<ST, CT>& c, const CostHot<ST, CT, NX, NU>& h, const ST (&x)[NX], const ST (&us)[NU],
                                                int part, int nparts) {
-  if (c.kind == TAMPC_COST_RECOVERY) return running_cost<ST, CT, NX, NU>(c, x, us, part, nparts);
+  if (c.kind != TAMPC_COST_GOAL_TRAP) return running_cost<ST, CT, NX, NU>(c, x, us, part, nparts);
   CT d[NX];
   CT u[NU];
 #pragma unroll
@@ -625,7 +660,7 @@ __device__ __forceinline__ CT running_cost_hot(const CostS<ST, CT>& c, const Cos
 // c_u = 0 when terminal (cost.py:177)      [controller.py:251-259]
 template <typename ST, typename CT, int NX>
 __device__ __forceinline__ CT terminal_cost(const CostS<ST, CT>& c, const ST (&x)[NX]) {
-  if (c.kind == TAMPC_COST_RECOVERY || !c.has_terminal) return (CT)0;
+  if (c.kind != TAMPC_COST_GOAL_TRAP || !c.has_terminal) return (CT)0;
   CT d[NX];
   state_diff<ST, CT, NX>(c.ang_mask, x, c.goal, d);
   return c.terminal_multiplier * quad_form_x<CT, NX>(c.Q, d);
@@ -656,6 +691,11 @@ __device__ __forceinline__ void stage_cost(CostS<ST, CT>& dst, const tampc_cost_
     dst.ang_mask = src.ang_mask; dst.usim_mask = src.usim_mask;
     dst.trap_weight = (CT)src.trap_weight; dst.terminal_multiplier = (CT)src.terminal_multiplier;
     dst.recovery_scale = (CT)src.recovery_scale;
+    dst.apf_use_goal = src.apf_use_goal; dst.apf_helicoid = src.apf_helicoid; dst.apf_clockwise = src.apf_clockwise;
+    dst.apf_max_dist = (CT)src.apf_max_dist; dst.apf_inv_max_dist = (CT)(1.0 / src.apf_max_dist); dst.apf_gain = (CT)src.apf_gain;
+    // original_angle = atan2 of (oxy - rxy) (cost.py:277-278), once per program
+    dst.apf_orig_angle = (CT)atan2(src.apf_oxy[1] - src.apf_rxy[1], src.apf_oxy[0] - src.apf_rxy[0]);
+    dst.apf_oxy[0] = (ST)src.apf_oxy[0]; dst.apf_oxy[1] = (ST)src.apf_oxy[1];
   }
   for (int i = tid; i < kMaxNx; i += nthreads) { dst.dist_scale[i] = (CT)src.dist_scale[i]; dst.goal[i] = (ST)src.goal[i]; }
   for (int i = tid; i < kMaxNx * kMaxNx; i += nthreads) dst.Q[i] = (CT)src.Q[i];

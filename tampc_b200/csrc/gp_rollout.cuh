@@ -6,8 +6,12 @@
 //     var_d  = s_d + n_d - | L_d^-1 k_d(g, X) |^2           K_d + n_d I = L_d L_d^T,  k_d(a,b) = s_d exp(-|a-b|^2 / (2 l_d^2))
 // followed by a Normal(mean, sqrt(var)) draw.  The mean function m is the nominal network, which the kernel evaluates
 // anyway; alpha and L^-1 are prepared on the host once per GP update (tampc_mppi_set_gp), staged in shared memory and
-// read with broadcast loads.  The posterior is written with L^-1 (a sum of squares) rather than (K + n I)^-1 so that
-// the variance stays accurate in float32.
+// read with broadcast loads.  The posterior is written with L^-1 (a sum of squares) rather than (K + n I)^-1.
+// The GP part — kernel vector, mean, variance, draw — is evaluated in float64 (type GT) in EVERY precision mode: alpha
+// has large entries of alternating sign (the kernel matrix of <= 50 nearby points is ill-conditioned), so float32
+// rounding of the individual k_j is amplified by |alpha| in the mean, and the variance is a difference of O(s) terms;
+// with float32 here the per-sample costs only reached 5e-5 relative (north star: 1e-5).  The networks around it stay in
+// the mode's arithmetic (float32 FFMA2 / float64 DFMA).
 //
 // A stochastic model makes the reference's M rollout replicas (ExperimentalMPPI._compute_rollout_costs,
 // tampc/controller/controller.py:340-381) genuinely different: one thread per (sample, replica), the replicas of a
@@ -138,21 +142,22 @@ template <typename NT, int NX_, int NU_, int H1, int H2>
 struct GpModel<ModelMlp<NT, NX_, NU_, H1, H2>> {
   using Base = ModelMlp<NT, NX_, NU_, H1, H2>;
   static constexpr int NOUT = NX_;
-  template <typename ST>
+  template <typename ST, typename GT>
   static __device__ __forceinline__ void predict(const NT* __restrict__ w, NT slope, const unsigned char* __restrict__ gp,
-                                                 typename GpVec4<NT>::type* __restrict__ ks, int kstride, const NT (&eps)[NOUT],
+                                                 typename GpVec4<GT>::type* __restrict__ ks, int kstride, const GT (&eps)[NOUT],
                                                  ST (&x)[NX_], const ST (&u)[NU_]) {
     NT in[1][NX_ + NU_];
+    GT gin[NX_ + NU_];
 #pragma unroll
-    for (int i = 0; i < NX_; ++i) in[0][i] = (NT)x[i];
+    for (int i = 0; i < NX_; ++i) { in[0][i] = (NT)x[i]; gin[i] = (GT)x[i]; }
 #pragma unroll
-    for (int i = 0; i < NU_; ++i) in[0][NX_ + i] = (NT)u[i];
+    for (int i = 0; i < NU_; ++i) { in[0][NX_ + i] = (NT)u[i]; gin[NX_ + i] = (GT)u[i]; }
     NT dx[1][NX_];
     Base::Net::template eval<1>(w, in, dx, slope);
-    NT delta[NX_];
-    gp_delta<NT, NX_ + NU_, NX_>(gp, ks, kstride, in[0], eps, delta);
+    GT delta[NX_];
+    gp_delta<GT, NX_ + NU_, NX_>(gp, ks, kstride, gin, eps, delta);
 #pragma unroll
-    for (int i = 0; i < NX_; ++i) x[i] += (ST)(dx[0][i] + delta[i]);
+    for (int i = 0; i < NX_; ++i) x[i] += (ST)((GT)dx[0][i] + delta[i]);
   }
 };
 
@@ -160,28 +165,32 @@ template <typename NT, int NX_, int NU_, int E1, int E2, int NZ, int D1, int D2,
 struct GpModel<ModelRex<NT, NX_, NU_, E1, E2, NZ, D1, D2, NV, C1, C2>> {
   using Base = ModelRex<NT, NX_, NU_, E1, E2, NZ, D1, D2, NV, C1, C2>;
   static constexpr int NOUT = NX_ > NV ? NX_ : NV;
-  template <typename ST>
+  template <typename ST, typename GT>
   static __device__ __forceinline__ void predict(const NT* __restrict__ w, NT slope, const unsigned char* __restrict__ gp,
-                                                 typename GpVec4<NT>::type* __restrict__ ks, int kstride, const NT (&eps)[NOUT],
+                                                 typename GpVec4<GT>::type* __restrict__ ks, int kstride, const GT (&eps)[NOUT],
                                                  ST (&x)[NX_], const ST (&u)[NU_]) {
-    const int space = reinterpret_cast<const GpHeader<NT>*>(gp)->space;
+    const int space = reinterpret_cast<const GpHeader<GT>*>(gp)->space;
     NT in[1][NX_ + NU_];
 #pragma unroll
     for (int i = 0; i < NX_; ++i) in[0][i] = (NT)x[i];
 #pragma unroll
     for (int i = 0; i < NU_; ++i) in[0][NX_ + i] = (NT)u[i];
-    NT v[1][NV];
+    GT v[NV];
     {
-      NT z[1][NZ];
+      NT z[1][NZ], vn[1][NV];
       Base::Enc::template eval<1>(w, in, z, slope);
-      Base::Dyn::template eval<1>(w + Base::kOffDyn, z, v, slope);
+      Base::Dyn::template eval<1>(w + Base::kOffDyn, z, vn, slope);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] = (GT)vn[0][j];
       if (space == TAMPC_GP_AT_NETWORK) {
-        NT e[NV], delta[NV];
+        GT e[NV], delta[NV], zin[NZ];
 #pragma unroll
         for (int j = 0; j < NV; ++j) e[j] = eps[j];
-        gp_delta<NT, NZ, NV>(gp, ks, kstride, z[0], e, delta);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) v[0][j] += delta[j];
+        for (int j = 0; j < NZ; ++j) zin[j] = (GT)z[0][j];
+        gp_delta<GT, NZ, NV>(gp, ks, kstride, zin, e, delta);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] += delta[j];
       }
     }
     NT xin[1][NX_];
@@ -189,19 +198,21 @@ struct GpModel<ModelRex<NT, NX_, NU_, E1, E2, NZ, D1, D2, NV, C1, C2>> {
     for (int i = 0; i < NX_; ++i) xin[0][i] = (NT)x[i];
     NT C[1][NX_ * NV];
     Base::Dec::template eval<1>(w + Base::kOffDec, xin, C, slope);
-    NT dx[NX_];
+    GT dx[NX_];
 #pragma unroll
     for (int i = 0; i < NX_; ++i) {
-      NT acc = w[Base::kOffD0 + i];
+      GT acc = (GT)w[Base::kOffD0 + i];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) acc = t_fma(C[0][i * NV + j], v[0][j], acc);
+      for (int j = 0; j < NV; ++j) acc = t_fma((GT)C[0][i * NV + j], v[j], acc);
       dx[i] = acc;
     }
     if (space == TAMPC_GP_ORIGINAL) {
-      NT e[NX_], delta[NX_];
+      GT e[NX_], delta[NX_], gin[NX_ + NU_];
 #pragma unroll
-      for (int i = 0; i < NX_; ++i) e[i] = eps[i];
-      gp_delta<NT, NX_ + NU_, NX_>(gp, ks, kstride, in[0], e, delta);
+      for (int i = 0; i < NX_; ++i) { e[i] = eps[i]; gin[i] = (GT)x[i]; }
+#pragma unroll
+      for (int i = 0; i < NU_; ++i) gin[NX_ + i] = (GT)u[i];
+      gp_delta<GT, NX_ + NU_, NX_>(gp, ks, kstride, gin, e, delta);
 #pragma unroll
       for (int i = 0; i < NX_; ++i) dx[i] += delta[i];
     }
@@ -213,7 +224,7 @@ struct GpModel<ModelRex<NT, NX_, NU_, E1, E2, NZ, D1, D2, NV, C1, C2>> {
 // ---- kernel ---------------------------------------------------------------------------------------------
 // One thread per (sample, replica).  A warp holds G = 32 / M samples; lanes G*M..31 mirror the last group and never
 // write.  Shared memory: the FMA-path image | shifted nominal sequence | GP block | per-thread kernel-vector scratch.
-template <class Model, typename NT, typename ST, typename CT>
+template <class Model, typename NT, typename ST, typename CT, typename GT>
 __global__ void __launch_bounds__(128) rollout_gp_kernel(const RolloutArgs a) {
   using GM = GpModel<Model>;
   constexpr int NX = Model::NX, NU = Model::NU, NOUT = GM::NOUT;
@@ -226,7 +237,7 @@ __global__ void __launch_bounds__(128) rollout_gp_kernel(const RolloutArgs a) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
   const int T = a.src.T;
   unsigned char* gp = smem_raw + L::bytes(T);
-  typename GpVec4<NT>::type* ks = reinterpret_cast<typename GpVec4<NT>::type*>(gp + a.gp_bytes) + tid;  // [j/4][thread] scratch
+  typename GpVec4<GT>::type* ks = reinterpret_cast<typename GpVec4<GT>::type*>(gp + a.gp_bytes) + tid;  // [j/4][thread] scratch
   {
     copy_image_async(smem_raw, a.image, (int)L::kU, tid, nthr);
     copy_image_async(gp, a.gp, a.gp_bytes, tid, nthr);
@@ -244,7 +255,7 @@ __global__ void __launch_bounds__(128) rollout_gp_kernel(const RolloutArgs a) {
   const int kk = (blockIdx.x * (nthr >> 5) + (tid >> 5)) * G + grp;
   const bool live = active && kk < a.K_local;
   const int k = min(kk, a.K_local - 1);
-  const int ny = reinterpret_cast<const GpHeader<NT>*>(gp)->n_out;
+  const int ny = reinterpret_cast<const GpHeader<GT>*>(gp)->n_out;
 
   ST x[NX];
 #pragma unroll
@@ -271,20 +282,20 @@ __global__ void __launch_bounds__(128) rollout_gp_kernel(const RolloutArgs a) {
         for (int i = 0; i < NU; ++i) u[i] = (ST)0;
       }
     }
-    NT eps[NOUT];
+    GT eps[NOUT];
     if (a.gp_eps != nullptr) {  // injected standard normals (K_local, M, T, n_out)
       const double* p = a.gp_eps + (((size_t)k * M + m) * T + t) * ny;
 #pragma unroll
-      for (int i = 0; i < NOUT; ++i) eps[i] = i < ny ? (NT)p[i] : (NT)0;
+      for (int i = 0; i < NOUT; ++i) eps[i] = i < ny ? (GT)p[i] : (GT)0;
     } else {  // Philox stream of (global sample, replica, t): counter word 1 = 128 * (1 + 2 m + block) + t
       float z[8];
       const uint32_t s = (uint32_t)(a.src.sample_offset + k);
       philox_normal4(a.src.seed, a.src.call, s, 128u * (1u + 2u * (uint32_t)m) + (uint32_t)t, *reinterpret_cast<float(*)[4]>(z));
       if (NOUT > 4) philox_normal4(a.src.seed, a.src.call, s, 128u * (2u + 2u * (uint32_t)m) + (uint32_t)t, *reinterpret_cast<float(*)[4]>(z + 4));
 #pragma unroll
-      for (int i = 0; i < NOUT; ++i) eps[i] = (NT)z[i];
+      for (int i = 0; i < NOUT; ++i) eps[i] = (GT)z[i];
     }
-    GM::template predict<ST>(w, slope, gp, ks, nthr, eps, x, u);
+    GM::template predict<ST, GT>(w, slope, gp, ks, nthr, eps, x, u);
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       if ((a.wrap_mask >> i) & 1u) x[i] = angle_normalize<ST>(x[i]);
@@ -319,12 +330,12 @@ __global__ void __launch_bounds__(128) rollout_gp_kernel(const RolloutArgs a) {
   if (live && m == 0) a.cost_out[k] = total;
 }
 
-template <class Model, typename NT, typename ST, typename CT>
+template <class Model, typename NT, typename ST, typename CT, typename GT>
 cudaError_t launch_rollout_gp(const RolloutArgs& a, int block, cudaStream_t stream) {
-  auto kern = rollout_gp_kernel<Model, NT, ST, CT>;
+  auto kern = rollout_gp_kernel<Model, NT, ST, CT, GT>;
   const size_t fixed = RolloutSmem<Model, NT, ST, CT>::bytes(a.src.T) + (size_t)a.gp_bytes;
-  while (block > 32 && fixed + gp_scratch_bytes<NT>(block) > 227 * 1024) block >>= 1;  // float64 with many points: smaller CTAs
-  const size_t smem = fixed + gp_scratch_bytes<NT>(block);
+  while (block > 32 && fixed + gp_scratch_bytes<GT>(block) > 227 * 1024) block >>= 1;  // many points: smaller CTAs
+  const size_t smem = fixed + gp_scratch_bytes<GT>(block);
   if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   static size_t configured = 0;
   if (smem > configured) {
@@ -344,9 +355,9 @@ struct GpLaunchers {
 template <class MF, class MD>
 GpLaunchers make_gp_launchers() {
   GpLaunchers g;
-  g.f64 = &launch_rollout_gp<MD, double, double, double>;
-  g.mixed = &launch_rollout_gp<MF, float, double, float>;
-  g.f32 = &launch_rollout_gp<MF, float, float, float>;
+  g.f64 = &launch_rollout_gp<MD, double, double, double, double>;
+  g.mixed = &launch_rollout_gp<MF, float, double, float, double>;
+  g.f32 = &launch_rollout_gp<MF, float, float, float, double>;
   return g;
 }
 

@@ -62,6 +62,7 @@ struct tampc_mppi {
   double* d_states = nullptr;   // optional trajectories (K_local, Tmax, nx)
   double* d_scratch = nullptr;  // perturbed-action readback
   double* d_predict = nullptr;  // action + cost scratch of tampc_mppi_predict
+  double* d_select = nullptr;   // index, cost, next state of tampc_mppi_select_action
   tampc_partial* d_partials = nullptr;
   int n_partial_slots = 0;
   // peer-memory exchange (multi-GPU): [parity][source rank][kPartialWords values][2 tagged words] (reduce_kernels.cuh)
@@ -1137,7 +1138,7 @@ TAMPC_API void tampc_mppi_destroy(tampc_mppi* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_sampler); cudaFree(h->d_cost); cudaFree(h->d_U[0]); cudaFree(h->d_U[1]); cudaFree(h->d_state);
-  cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_predict); cudaFree(h->d_partials); cudaFree(h->d_partials2); cudaFree(h->d_ticket); cudaFree(h->d_phdr); cudaFree(h->d_pwsum);
+  cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_predict); cudaFree(h->d_select); cudaFree(h->d_partials); cudaFree(h->d_partials2); cudaFree(h->d_ticket); cudaFree(h->d_phdr); cudaFree(h->d_pwsum);
   cudaFree(h->d_rank_partial); cudaFree(h->d_action); cudaFree(h->d_stats); cudaFree(h->d_weights);
   for (int p = 0; p < h->comm_world; ++p)
     if (p != h->comm_rank && h->comm_peer[p] && h->comm_peer[p] != h->comm_local) cudaIpcCloseMemHandle(h->comm_peer[p]);
@@ -1383,8 +1384,7 @@ TAMPC_API int tampc_mppi_set_gp(tampc_mppi* h, const tampc_gp_desc* g, const dou
       for (int i = j; i < n; ++i) alpha[d][j] += Li[(size_t)i * n + j] * w[i];
   }
   std::vector<unsigned char> blob;
-  if (h->cfg.precision == TAMPC_PREC_F64) pack_gp<double>(blob, *g, in_scale, in_off, out_mul, X, alpha, Linv);
-  else pack_gp<float>(blob, *g, in_scale, in_off, out_mul, X, alpha, Linv);
+  pack_gp<double>(blob, *g, in_scale, in_off, out_mul, X, alpha, Linv);  // the GP part is float64 in every precision mode (gp_rollout.cuh)
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   if (blob.size() > h->gp_capacity) {
     cudaFree(h->d_gp);
@@ -1434,6 +1434,9 @@ TAMPC_API int tampc_mppi_set_cost(tampc_mppi* h, const tampc_cost_desc* d) {
     if (d->n_sets < 1 || d->n_sets > TAMPC_MAX_GOAL_SETS) { h->err = "n_sets out of range"; return TAMPC_ERR_INVALID; }
     for (int j = 0; j < d->n_sets; ++j)
       if (d->set_size[j] < 1 || d->set_size[j] > TAMPC_MAX_SET_GOALS) { h->err = "goal set size out of range"; return TAMPC_ERR_INVALID; }
+  } else if (d->kind == TAMPC_COST_APF) {
+    if (d->n_traps < 0 || d->n_traps > TAMPC_MAX_TRAPS) { h->err = "n_traps out of range"; return TAMPC_ERR_INVALID; }
+    if (!(d->apf_max_dist > 0.0)) { h->err = "apf_max_dist must be positive"; return TAMPC_ERR_INVALID; }
   } else {
     h->err = "unknown cost kind";
     return TAMPC_ERR_INVALID;
@@ -1797,6 +1800,57 @@ TAMPC_API int tampc_mppi_query(tampc_mppi* h, int32_t what, double* out, size_t 
     }
     default: h->err = "unknown query"; return TAMPC_ERR_INVALID;
   }
+}
+
+TAMPC_API int tampc_mppi_select_action(tampc_mppi* h, const double* state, const double* actions, int32_t n, int64_t* index_out, double* cost_out,
+                                       double* next_state_out) {
+  if (!h || !state || !actions || !index_out) return TAMPC_ERR_INVALID;
+  if (!h->has_model || !h->has_cost) { h->err = "set_model / set_cost first"; return TAMPC_ERR_STATE; }
+  if (n < 1 || n > h->cfg.num_local) { h->err = "select_action: need 1 <= n <= num_local candidate actions"; return TAMPC_ERR_INVALID; }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  int rc;
+  if ((rc = upload_state(h, state))) return rc;
+  if ((rc = ensure_noise(h)) || (rc = ensure_states(h))) return rc;
+  const int nx = h->cfg.nx, nu = h->cfg.nu;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_noise, actions, sizeof(double) * (size_t)n * nu, cudaMemcpyHostToDevice, h->stream));
+  // a one-step rollout of the n given actions with the states kept; only the first n rows exist for the kernels
+  const int saved_local = h->cfg.num_local;
+  h->cfg.num_local = n;
+  rc = launch_rollout_for(h, kModeActions, 0, h->d_U[h->cur], 1, 0, /*keep_states=*/true);
+  h->cfg.num_local = saved_local;
+  if (rc) return rc;
+  if (!h->d_select) CUDA_TRY(h, cudaMalloc(&h->d_select, sizeof(double) * (2 + kMaxNx)));
+  argmin_select_kernel<<<1, 1024, 0, h->stream>>>(h->d_costs, h->d_states, n, nx, h->d_select);
+  CUDA_TRY(h, cudaGetLastError());
+  h->launches++;
+  double out[2 + kMaxNx];
+  CUDA_TRY(h, cudaMemcpyAsync(out, h->d_select, sizeof(double) * (2 + nx), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  *index_out = (int64_t)out[0];
+  if (cost_out) *cost_out = out[1];
+  if (next_state_out) memcpy(next_state_out, out + 2, sizeof(double) * nx);
+  h->last_valid = false;
+  h->states_valid = false;
+  return TAMPC_OK;
+}
+
+TAMPC_API int tampc_mppi_state_costs(tampc_mppi* h, const double* states, int32_t n, double* goal_cost_out, double* trap_cost_out) {
+  if (!h || !states || !goal_cost_out || !trap_cost_out || n < 1) return TAMPC_ERR_INVALID;
+  if (!h->has_cost) { h->err = "set_cost first"; return TAMPC_ERR_STATE; }
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  const int nx = h->cfg.nx;
+  double* buf = nullptr;
+  CUDA_TRY(h, cudaMallocAsync(&buf, sizeof(double) * (size_t)n * (nx + 2), h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(buf, states, sizeof(double) * (size_t)n * nx, cudaMemcpyHostToDevice, h->stream));
+  state_costs_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_cost, buf, n, buf + (size_t)n * nx, buf + (size_t)n * (nx + 1));
+  cudaError_t le = cudaGetLastError();
+  if (le == cudaSuccess) le = cudaMemcpyAsync(goal_cost_out, buf + (size_t)n * nx, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+  if (le == cudaSuccess) le = cudaMemcpyAsync(trap_cost_out, buf + (size_t)n * (nx + 1), sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+  cudaFreeAsync(buf, h->stream);
+  CUDA_TRY(h, le);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->launches++;
+  return TAMPC_OK;
 }
 
 TAMPC_API const char* tampc_mppi_kernel_name(tampc_mppi* h) {

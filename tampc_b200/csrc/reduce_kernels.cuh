@@ -383,4 +383,57 @@ __global__ void perturbed_kernel(const PerturbedArgs a) {
   for (int d = 0; d < NU; ++d) a.out[i * NU + d] = a.post_clamp_noise ? npost[d] : u[d];
 }
 
+// ---- one-step samplers of the APF baselines (online_controller.py:583-590, 657-664): argmin over the candidates' costs ----
+// Single CTA (n <= a few thousand candidates): lowest index wins ties, like torch.argmin.  out[0] = index, out[1] = cost,
+// out[2 .. 2+nx) = the next state of the winner (row `index` of states (n, 1, nx)).
+__global__ void __launch_bounds__(1024) argmin_select_kernel(const double* __restrict__ cost, const double* __restrict__ states, int n, int nx,
+                                                             double* __restrict__ out) {
+  __shared__ double s_b[32];
+  __shared__ long long s_i[32];
+  const int tid = threadIdx.x;
+  double b = __longlong_as_double(0x7ff0000000000000ll);
+  long long bi = 0x7fffffffffffffffll;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const double c = cost[i];
+    if (c < b || (c == b && i < bi)) { b = c; bi = i; }
+  }
+  block_min_arg(b, bi, s_b, s_i, tid, blockDim.x);
+  if (tid == 0) { out[0] = (double)bi; out[1] = b; }
+  if (tid < nx && bi < n) out[2 + tid] = states[(size_t)bi * nx + tid];
+}
+
+// goal_cost(x) and the raw trap-set cost with c_u = 1 (U=None) for n states, float64
+// (OnlineMPPI.normalize_trapset_cost_to_state, online_controller.py:517-530; cost.py:11-18,154-189).
+__global__ void state_costs_kernel(const tampc_cost_desc* __restrict__ c, const double* __restrict__ states, int n, double* __restrict__ goal_out,
+                                   double* __restrict__ trap_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int nx = c->nx;
+  double x[kMaxNx], d[kMaxNx];
+  for (int k = 0; k < nx; ++k) x[k] = states[(size_t)i * nx + k];
+  auto diff = [&](const double* g) {
+    for (int k = 0; k < nx; ++k) {
+      double v = x[k] - g[k];
+      if ((c->ang_mask >> k) & 1u) v = angular_wrap_once(v);
+      d[k] = v;
+    }
+  };
+  diff(c->goal);
+  double q = 0.0;
+  for (int j = 0; j < nx; ++j) {
+    double col = 0.0;
+    for (int k = 0; k < nx; ++k) col = __fma_rn(d[k], c->Q[k * kMaxNx + j], col);
+    q = __fma_rn(col, d[j], q);
+  }
+  goal_out[i] = q;
+  double t = 0.0;
+  for (int p = 0; p < c->n_traps; ++p) {
+    diff(c->trap_x[p]);
+    double s = 0.0;
+    for (int k = 0; k < nx; ++k) { const double v = d[k] * c->dist_scale[k]; s = __fma_rn(v, v, s); }
+    t += fmax(fmin(1.0 / s, kTrapMaxCost), 0.0);
+  }
+  trap_out[i] = t;
+}
+
 }  // namespace tampc

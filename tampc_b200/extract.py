@@ -417,6 +417,51 @@ def cost_from_controller(ctrl, running_cost=None, terminal_state_cost='unset') -
                       use_trap_cost=use_trap, usim_dims=usim, terminal_multiplier=tm)
 
 
+def apf_cost_from_controller(ctrl, this_cost=None) -> S.CostSpec:
+    """Cost program of the APF baselines' one-step action selection (online_controller.py:554-664).
+
+    `this_cost` is the potential the controller is about to evaluate on the next states: APFVO's `ctrl.cost` =
+    ComposeCost([goal_cost, ArtificialRepulsionCost]) (default when the controller has one), or APFSP's `ctrl.goal_cost` /
+    a fresh APFHelicoid2D(xy, active_obstacle).  Anything else raises UnsupportedSpec."""
+    nx, nu = int(ctrl.nx), int(ctrl.nu)
+    if this_cost is None:
+        this_cost = getattr(ctrl, 'cost', None) or ctrl.goal_cost
+    ang = probe_ang_dims(ctrl.compare_to_goal, nx)
+    dist_scale = probe_dist_scale(ctrl.state_dist, nx)
+    gc = ctrl.goal_cost
+    if gc.goal is None:
+        raise UnsupportedSpec("controller has no goal; call set_goal first")
+    common = dict(kind=S.COST_APF, nx=nx, nu=nu, ang_dims=ang, dist_scale=dist_scale, Q=_np(gc.Q), goal=_np(gc.goal).reshape(nx))
+    terms = list(this_cost.fn) if hasattr(this_cost, 'fn') else [this_cost]
+    if hasattr(this_cost, 'fn') and getattr(this_cost, 'weights', None) is not None:
+        raise UnsupportedSpec("weighted ComposeCost is not an APF configuration")
+    use_goal, rep, hel = False, None, None
+    for t in terms:
+        if t is gc:
+            use_goal = True
+        elif hasattr(t, 'state_set') and hasattr(t, 'max_dist_influence'):
+            if t.compare_to_goal is not ctrl.compare_to_goal and not _same_method(t.compare_to_goal, ctrl.compare_to_goal):
+                raise UnsupportedSpec("ArtificialRepulsionCost uses another state difference than the controller")
+            rep = t
+        elif hasattr(t, 'rxy') and hasattr(t, 'oxy'):
+            hel = (_np(t.rxy).reshape(2), _np(t.oxy).reshape(2), bool(getattr(t, 'clockwise', False)))
+        else:
+            raise UnsupportedSpec("APF potential term {} has no fused implementation".format(type(t).__name__))
+    trap_x = None
+    max_dist, gain = 1.0, 1.0
+    if rep is not None:
+        states = list(rep.state_set)
+        if len(states) > S.MAX_TRAPS:
+            import warnings
+            warnings.warn("repulsive set of {} exceeds TAMPC_MAX_TRAPS={}: the most recent ones are used".format(len(states), S.MAX_TRAPS),
+                          RuntimeWarning, stacklevel=2)
+            states = states[-S.MAX_TRAPS:]
+        if states:
+            trap_x = np.stack([_np(x).reshape(nx) for x in states])
+        max_dist, gain = float(rep.max_dist_influence), float(rep.gain)
+    return S.CostSpec(trap_x=trap_x, apf_use_goal=use_goal, apf_max_dist=max_dist, apf_gain=gain, apf_helicoid=hel, **common)
+
+
 def sampler_from_mppi(mpc) -> S.SamplerSpec:
     """Sampler constants from a pytorch_mppi.MPPI-like object."""
     return S.SamplerSpec(K=int(mpc.K), T=int(mpc.T), nu=int(mpc.nu), lambda_=float(mpc.lambda_),

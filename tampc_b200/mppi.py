@@ -110,7 +110,12 @@ class B200MPPI:
         self._gather = None
         self._p2p = False
         if world_size > 1 and exchange in ('auto', 'p2p'):
-            self._connect_peers(required=exchange == 'p2p')
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self._connect_peers(required=exchange == 'p2p')
+            elif exchange == 'p2p':
+                raise RuntimeError("exchange='p2p' needs an initialised torch.distributed process group to trade the IPC handles")
+            # 'auto' without a process group: the caller drives command_begin / command_finish with its own transport
         self._last_noise = None
         self._cost_fp = None
         self._cost_cache = None
@@ -134,19 +139,32 @@ class B200MPPI:
         return cls(S.load_spec(path), **kwargs)
 
     @classmethod
-    def for_one_step(cls, ctrl, samples, **kwargs):
+    def for_one_step(cls, ctrl, samples, this_cost='none', **kwargs):
         """A handle for the one-step action samplers of the APF baselines (APFVO / APFSP, online_controller.py:554-664)
         and anything else that pushes `samples` candidate actions through `ctrl._apply_dynamics` from one state: the
-        dynamics of `ctrl`, K = samples, horizon 1.  Use `apply_dynamics`."""
+        dynamics of `ctrl`, K = samples, horizon 1.
+
+        this_cost='none': dynamics only (use `apply_dynamics`).  this_cost=None / a cost object of the controller: also the
+        APF potential (extract.apf_cost_from_controller), so that `select_action` runs dynamics + cost + argmin on the
+        device; `set_apf_cost` re-reads it (APFVO's trap set grows, APFSP switches between goal and helicoid potential)."""
         dyn = extract.dynamics_from_controller(ctrl)
         nx, nu = dyn.nx, dyn.nu
-        cost = S.CostSpec(kind=S.COST_GOAL_TRAP, nx=nx, nu=nu, Q=np.zeros((nx, nx)), R=np.zeros((nu, nu)), goal=np.zeros(nx),
-                          use_trap_cost=False)
+        if isinstance(this_cost, str) and this_cost == 'none':
+            cost = S.CostSpec(kind=S.COST_GOAL_TRAP, nx=nx, nu=nu, Q=np.zeros((nx, nx)), R=np.zeros((nu, nu)), goal=np.zeros(nx),
+                              use_trap_cost=False)
+        else:
+            cost = extract.apf_cost_from_controller(ctrl, this_cost)
         u_min = None if getattr(ctrl, 'u_min', None) is None else extract._np(ctrl.u_min)
         u_max = None if getattr(ctrl, 'u_max', None) is None else extract._np(ctrl.u_max)
         sampler = S.SamplerSpec(K=int(samples), T=1, nu=nu, lambda_=1.0, noise_mu=np.zeros(nu), noise_sigma=np.eye(nu),
                                 u_min=u_min, u_max=u_max)
-        return cls(S.RolloutSpec(dyn, cost, sampler, name='one_step'), U_init=torch.zeros(1, nu, dtype=torch.double), **kwargs)
+        obj = cls(S.RolloutSpec(dyn, cost, sampler, name='one_step'), U_init=torch.zeros(1, nu, dtype=torch.double), **kwargs)
+        obj._apf_ctrl = ctrl
+        return obj
+
+    def set_apf_cost(self, this_cost=None):
+        """Re-read the APF potential from the controller this one-step handle was built for."""
+        self.set_cost(extract.apf_cost_from_controller(self._apf_ctrl, this_cost))
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc):
@@ -489,6 +507,37 @@ class B200MPPI:
             out[lo:lo + len(chunk)] = states[:len(chunk), 0]
         return torch.from_numpy(out)
 
+    def select_action(self, state, actions):
+        """The APF baselines' action selection (online_controller.py:583-590, 657-664) in one device call: candidate
+        `actions` (n, nu) through `_apply_dynamics` from `state`, the installed potential on the next states, argmin on the
+        device.  Returns (index, actions[index] as a float64 tensor, cost, next_state (nx,))."""
+        a = np.ascontiguousarray(torch.as_tensor(actions).detach().to('cpu', torch.double).numpy().reshape(-1, self.nu))
+        if a.shape[0] > self.K_local:
+            raise ValueError("{} candidate actions exceed the handle's {} samples".format(a.shape[0], self.K_local))
+        x = self._state_array(state)
+        idx, cost = C.c_int64(), C.c_double()
+        nxt = np.empty(self.nx)
+        self._check(self._lib.tampc_mppi_select_action(self._h, L.dptr(x), L.dptr(a), a.shape[0], C.byref(idx),
+                                                       C.cast(C.byref(cost), C.POINTER(C.c_double)), L.dptr(nxt)))
+        return int(idx.value), torch.from_numpy(a[idx.value].copy()), float(cost.value), torch.from_numpy(nxt)
+
+    def state_costs(self, states):
+        """(goal_cost(x), raw trap_cost(x) with U=None) of the installed GOAL_TRAP program for (n, nx) states."""
+        xs = np.ascontiguousarray(torch.as_tensor(states).detach().to('cpu', torch.double).numpy().reshape(-1, self.nx))
+        g, t = np.empty(len(xs)), np.empty(len(xs))
+        self._check(self._lib.tampc_mppi_state_costs(self._h, L.dptr(xs), len(xs), L.dptr(g), L.dptr(t)))
+        return torch.from_numpy(g), torch.from_numpy(t)
+
+    def normalize_trapset_cost_to_state(self, x):
+        """OnlineMPPI.normalize_trapset_cost_to_state (online_controller.py:517-530): goal_cost(x) / trap_cost(x), None
+        without a trap cost or traps — evaluated by the device from the cost program of the bound controller."""
+        self._refresh_from_controller()
+        c = self._cost_spec
+        if c.kind != S.COST_GOAL_TRAP or not c.use_trap_cost or len(c.trap_x) == 0:
+            return None
+        g, t = self.state_costs(torch.as_tensor(x).reshape(1, -1))
+        return g / t
+
     def _compute_rollout_costs(self, perturbed_actions, state=None):
         """ExperimentalMPPI._compute_rollout_costs (controller.py:340-381): (cost_total (K,), states (M,K,T,nx),
         actions (M,K,T,nu)) for caller-given actions.  M replicas of a deterministic model are identical, so M=1
@@ -553,4 +602,6 @@ def install(ctrl, predict_on_device=True, **kwargs):
                 ctrl.predict_next_state = lambda state, control: mpc.predict_next_state(state, control, nominal_only=True)
         else:
             ctrl.predict_next_state = mpc.predict_next_state
+    if predict_on_device and hasattr(ctrl, 'normalize_trapset_cost_to_state'):
+        ctrl.normalize_trapset_cost_to_state = mpc.normalize_trapset_cost_to_state  # online_controller.py:471,517-530
     return mpc

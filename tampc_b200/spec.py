@@ -197,6 +197,7 @@ class DynamicsSpec:
 
 COST_GOAL_TRAP = 0  # ComposeCost([CostQROnlineTorch, TrapSetCost]) or CostQROnlineTorch alone
 COST_RECOVERY = 1  # GoalSetCost / ComposeCost([GoalSetCost, GoalSetCost], weights=MAB arm)
+COST_APF = 2  # APFVO: ComposeCost([goal_cost, ArtificialRepulsionCost]); APFSP: goal_cost | APFHelicoid2D (online_controller.py:554-664)
 
 
 @dataclass
@@ -224,6 +225,11 @@ class CostSpec:
     goal_sets: Sequence[np.ndarray] = ()  # each (n_j, nx)
     set_weights: Sequence[float] = ()
     recovery_scale: float = 1.0
+    # --- COST_APF (potentials of the NEXT state, U=None): Q / goal as above, repulsive states in trap_x ---
+    apf_use_goal: bool = True
+    apf_max_dist: float = 1.0   # ArtificialRepulsionCost.max_dist_influence (cost.py:239-243)
+    apf_gain: float = 1.0
+    apf_helicoid: Optional[tuple] = None  # (rxy (2,), oxy (2,), clockwise) of APFHelicoid2D (cost.py:268-289)
 
     def __post_init__(self):
         self.ang_dims = tuple(int(d) for d in self.ang_dims)
@@ -249,6 +255,18 @@ class CostSpec:
             if len(self.trap_x) > MAX_TRAPS:
                 raise ValueError("trap set of {} exceeds TAMPC_MAX_TRAPS={}".format(len(self.trap_x), MAX_TRAPS))
             self.trap_weight = float(self.trap_weight)
+        elif self.kind == COST_APF:
+            self.Q = _f64(self.Q)
+            self.goal = _f64(self.goal).reshape(-1)
+            assert self.Q.shape == (self.nx, self.nx) and self.goal.shape == (self.nx,)
+            self.R = np.zeros((self.nu, self.nu))
+            self.trap_x = np.zeros((0, self.nx)) if self.trap_x is None or len(self.trap_x) == 0 else _f64(self.trap_x).reshape(-1, self.nx)
+            self.trap_u = np.zeros((len(self.trap_x), self.nu))
+            if len(self.trap_x) > MAX_TRAPS:
+                raise ValueError("repulsive set of {} exceeds TAMPC_MAX_TRAPS={}".format(len(self.trap_x), MAX_TRAPS))
+            if self.apf_helicoid is not None:
+                rxy, oxy, cw = self.apf_helicoid
+                self.apf_helicoid = (_f64(rxy).reshape(2), _f64(oxy).reshape(2), bool(cw))
         elif self.kind == COST_RECOVERY:
             self.goal_sets = [_f64(g).reshape(-1, self.nx) for g in self.goal_sets]
             self.set_weights = [float(w) for w in self.set_weights]

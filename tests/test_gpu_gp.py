@@ -8,10 +8,10 @@ from conftest import GP_CASES, load_golden
 
 pytestmark = pytest.mark.gpu
 
-# float64 runs the reference's arithmetic.  The float32 modes evaluate the GP posterior in float32: the variance is a
-# difference of O(s) terms and the rollout feeds draws of that stddev back through the dynamics for T steps, so the
-# per-sample cost tolerance is the measured float32 level for these fixtures, not the 1e-5 of the deterministic path.
-COST_RTOL = {'f64': 1e-9, 'tf32x3': 2e-4, 'mixed': 2e-4, 'f32': 2e-4}
+# float64 runs the reference's arithmetic.  The float32 modes keep the NETWORKS in float32 but evaluate the GP posterior
+# (kernel vector, mean, variance, draw) in float64 (gp_rollout.cuh), so they are held to the north-star gate of the
+# deterministic path: per-sample cost 1e-5 relative.
+COST_RTOL = {'f64': 1e-9, 'tf32x3': 1e-5, 'mixed': 1e-5, 'f32': 1e-5}
 ACTION_ATOL = {'f64': 1e-8, 'tf32x3': 1e-4, 'mixed': 1e-4, 'f32': 1e-4}
 
 

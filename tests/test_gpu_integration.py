@@ -182,3 +182,83 @@ def test_one_step_sampler_of_the_apf_baselines(cuda_lib, case, precision):
         bad = m.apply_dynamics(torch.full((spec.dynamics.nx,), 1e6, dtype=torch.double), u[:3])
         assert torch.all(bad == 0)
     m.close()
+
+
+@pytest.mark.parametrize('case,precision', [('push_nominal', 'f64'), ('push_nominal', 'tf32x3'), ('peg_nominal', 'mixed')])
+def test_apf_action_selection_on_the_device(cuda_lib, case, precision):
+    """APFVO / APFSP (online_controller.py:583-590, 657-664) — dynamics, potential and argmin in one
+    device call — against the oracle (which tests/test_reference_live.py pins to the reference's cost classes)."""
+    import types
+    from oracle import mppi_oracle as O
+    from tampc_b200 import spec as S
+    from tampc_b200.mppi import B200MPPI
+    z, spec = load_golden(case)
+    ctrl = fake_tampc.make_controller(spec, z['in.U'])
+    ctrl.u_min, ctrl.u_max = torch.from_numpy(spec.sampler.u_min), torch.from_numpy(spec.sampler.u_max)
+    nx, nu = spec.dynamics.nx, spec.dynamics.nu
+    g = torch.Generator().manual_seed(2)
+    x = torch.from_numpy(z['in.state'])
+    u = torch.rand(5000, nu, dtype=torch.double, generator=g) * (ctrl.u_max - ctrl.u_min) + ctrl.u_min
+    nxt0, _ = O.apply_dynamics(spec.dynamics, x.view(1, -1).repeat(16, 1), u[:16])
+    # APFVO: goal + artificial repulsion; repulsive states where the model thinks some actions lead (online_controller.py:578-581)
+    rep = types.SimpleNamespace(state_set=[nxt0[3].clone(), nxt0[11].clone() + 0.05, x.clone() + 0.2], max_dist_influence=1.0, gain=1.0,
+                                compare_to_goal=ctrl.compare_to_goal)
+    ctrl.cost = types.SimpleNamespace(fn=[ctrl.goal_cost, rep], weights=None)
+    m = B200MPPI.for_one_step(ctrl, samples=5000, this_cost=None, precision=precision)
+    tol = 1e-9 if precision == 'f64' else 1e-5
+
+    def check(n):
+        cost_spec = m._cost_spec
+        idx, a, c, nxt = m.select_action(x, u[:n])
+        wi, wc, wn = O.select_action(S.RolloutSpec(spec.dynamics, cost_spec, m.spec.sampler), x, u[:n])
+        s = torch.sort(wc).values
+        gap = float((s[1] - s[0]) / s[0].abs().clamp_min(1e-300)) if n > 1 else 1.0
+        print(case, precision, 'n', n, 'top-2 gap', gap, 'cost err', abs(c - float(wc[idx])) / abs(float(wc[idx])))
+        assert abs(c - float(wc[idx])) <= tol * max(1.0, abs(float(wc[idx])))  # the cost of the row it picked
+        if gap > 10 * tol:
+            assert idx == wi and torch.equal(a, u[idx])
+        np.testing.assert_allclose(nxt.numpy(), wn[idx].numpy(), rtol=1e-4 if precision != 'f64' else 1e-10, atol=1e-4 if precision != 'f64' else 1e-10)
+
+    check(5000)
+    check(37)
+    check(1)
+    # the trap set grows, then APFSP's switched potentials: helicoid around an obstacle / plain goal potential
+    rep.state_set.append(nxt0[5].clone())
+    m.set_apf_cost()
+    assert len(m._cost_spec.trap_x) == 4
+    check(5000)
+    hel = types.SimpleNamespace(rxy=x[:2].clone(), oxy=x[:2].clone() + torch.tensor([0.15, -0.1], dtype=torch.double), clockwise=False)
+    m.set_apf_cost(hel)
+    check(5000)
+    hel.clockwise = True
+    m.set_apf_cost(hel)
+    check(4999)
+    m.set_apf_cost(ctrl.goal_cost)
+    check(5000)
+    m.close()
+
+
+def test_trapset_cost_normalisation_on_the_device(cuda_lib):
+    """OnlineMPPI.normalize_trapset_cost_to_state (online_controller.py:517-530) served from the installed cost program."""
+    from oracle import mppi_oracle as O
+    from tampc_b200.mppi import install
+    z, spec = load_golden('push_nominal')
+    ctrl = fake_tampc.make_controller(spec, z['in.U'])
+    ctrl.normalize_trapset_cost_to_state = lambda x: None
+    mpc = install(ctrl, precision='tf32x3')
+    assert ctrl.normalize_trapset_cost_to_state == mpc.normalize_trapset_cost_to_state
+    g = torch.Generator().manual_seed(9)
+    for i in range(4):
+        x = torch.randn(5, dtype=torch.double, generator=g) * 0.5
+        want, _, _ = O.normalize_trapset_cost_to_state(spec.cost, x)
+        got = ctrl.normalize_trapset_cost_to_state(x)
+        assert got.shape == (1,) and abs(float(got) - float(want)) <= 1e-12 * abs(float(want))
+    # the trap set changed since the last command: the device program follows; no traps -> None like the reference
+    ctrl.trap_set.append((torch.tensor([0.3, -0.1, 0.4, 0., 0.], dtype=torch.double), torch.tensor([0.1, 0.9, 0.2], dtype=torch.double)))
+    spec.cost.trap_x = np.vstack([spec.cost.trap_x, [0.3, -0.1, 0.4, 0., 0.]])
+    x = torch.tensor([0.2, 0.1, -0.3, 1., 2.], dtype=torch.double)
+    want, _, _ = O.normalize_trapset_cost_to_state(spec.cost, x)
+    assert abs(float(ctrl.normalize_trapset_cost_to_state(x)) - float(want)) <= 1e-12 * abs(float(want))
+    ctrl.trap_set.clear()
+    assert ctrl.normalize_trapset_cost_to_state(x) is None
+    mpc.close()

@@ -150,3 +150,45 @@ def test_device_fitted_gp_class_is_recognised_by_the_reference():
     assert issubclass(cls, ref.online_model.OnlineDynamicsModel)
     assert cls.update is ref.online_model.OnlineDynamicsModel.update
     assert not getattr(cls, '__abstractmethods__', None)
+
+
+def test_apf_potentials_and_trapset_normalisation_match_the_reference_classes(push_ctrl):
+    """the oracle's restatement of the APF baselines' potentials (ArtificialRepulsionCost, APFHelicoid2D,
+    goal cost with U=None; cost.py:11-18,236-289 as used at online_controller.py:561-590,639-664) and of
+    OnlineMPPI.normalize_trapset_cost_to_state (online_controller.py:517-530) against the reference's own classes, through
+    the extraction the device path uses (extract.apf_cost_from_controller)."""
+    import types
+    ref = rh.load_reference()
+    ctrl = push_ctrl
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(257, 5, dtype=torch.double, generator=g) * torch.tensor([0.6, 0.6, 2.5, 3., 3.])
+    traps = [torch.randn(5, dtype=torch.double, generator=g) * 0.4 for _ in range(4)]
+    traps.append(X[7].clone() + 1e-9)  # a candidate sitting on a repulsive state: clamped at TRAP_MAX_COST
+    rep = ref.cost.ArtificialRepulsionCost(traps, ctrl.compare_to_goal, ctrl.state_dist, 0.7, gain=2.5)
+    apfvo = types.SimpleNamespace(nx=5, nu=3, compare_to_goal=ctrl.compare_to_goal, state_dist=ctrl.state_dist, goal_cost=ctrl.goal_cost,
+                                  cost=ref.cost.ComposeCost([ctrl.goal_cost, rep]))
+    c = extract.apf_cost_from_controller(apfvo)
+    assert c.kind == S.COST_APF and c.apf_use_goal and len(c.trap_x) == 5 and c.apf_max_dist == 0.7 and c.apf_gain == 2.5
+    want = apfvo.cost(X.clone())
+    got = O.apf_cost(c, X.clone())
+    assert torch.allclose(got, want, rtol=1e-12, atol=1e-12) and int(got.argmin()) == int(want.argmin())
+    # APFSP: the helicoid around the active obstacle, both senses, and the plain goal potential
+    for cw in (False, True):
+        hel = ref.cost.APFHelicoid2D(torch.tensor([0.1, -0.2], dtype=torch.double), torch.tensor([0.4, 0.3], dtype=torch.double), clockwise=cw)
+        ch = extract.apf_cost_from_controller(apfvo, hel)
+        assert not ch.apf_use_goal and len(ch.trap_x) == 0
+        assert torch.allclose(O.apf_cost(ch, X.clone()), hel(X.clone()), rtol=1e-12, atol=1e-12)
+    cg = extract.apf_cost_from_controller(apfvo, ctrl.goal_cost)
+    assert torch.allclose(O.apf_cost(cg, X.clone()), ctrl.goal_cost(X.clone()), rtol=1e-12, atol=1e-12)
+    with pytest.raises(extract.UnsupportedSpec):
+        extract.apf_cost_from_controller(apfvo, ref.cost.CostLeaveState(X[0], 1., 1., ctrl.compare_to_goal, 100.))
+    # normalize_trapset_cost_to_state on the live OnlineMPPI
+    ctrl.trap_set.clear()
+    assert ctrl.normalize_trapset_cost_to_state(X[0]) is None
+    for k in range(3):
+        ctrl.trap_set.append((torch.randn(5, dtype=torch.double, generator=g) * 0.5, torch.randn(3, dtype=torch.double, generator=g)))
+    spec = extract.spec_from_controller(ctrl)
+    for i in range(5):
+        want = ctrl.normalize_trapset_cost_to_state(X[i].clone())
+        got, _, _ = O.normalize_trapset_cost_to_state(spec.cost, X[i])
+        assert abs(float(got) - float(want)) <= 1e-12 * abs(float(want))
