@@ -271,8 +271,9 @@ def select_action(spec: S.RolloutSpec, state, actions):
 
 
 def normalize_trapset_cost_to_state(c: S.CostSpec, x):
-    """OnlineMPPI.normalize_trapset_cost_to_state (online_controller.py:517-530): goal_cost(x) / trap_cost(x) with the raw
-    (unweighted, U=None -> c_u = 1) TrapSetCost summed over the traps (controller.py:245-246, cost.py:154-189)."""
+    """OnlineMPPI.normalize_trapset_cost_to_state (online_controller.py:517-530): goal_cost(x) / trap_cost(x); trap_cost is
+    the TrapSetCost with U=None (c_u = 1, cost.py:177) reduced by MPC._trap_cost_reduce = sum * the CURRENT trap_set_weight
+    (controller.py:245-246)."""
     x = _t(x).view(1, -1)
     d = compare_to_goal(c, x, _t(c.goal))
     goal = torch.einsum('ni,ij,nj->n', d, _t(c.Q), d)
@@ -280,6 +281,7 @@ def normalize_trapset_cost_to_state(c: S.CostSpec, x):
     for tx in c.trap_x:
         cx = state_dist(c, compare_to_goal(c, x, _t(tx))).square()
         trap = trap + torch.clamp(1 / cx, 0, S.TRAP_MAX_COST)
+    trap = trap * c.trap_weight
     return goal / trap, goal, trap
 
 

@@ -529,14 +529,15 @@ class B200MPPI:
         return torch.from_numpy(g), torch.from_numpy(t)
 
     def normalize_trapset_cost_to_state(self, x):
-        """OnlineMPPI.normalize_trapset_cost_to_state (online_controller.py:517-530): goal_cost(x) / trap_cost(x), None
-        without a trap cost or traps — evaluated by the device from the cost program of the bound controller."""
+        """OnlineMPPI.normalize_trapset_cost_to_state (online_controller.py:517-530): goal_cost(x) / trap_cost(x) (the trap
+        cost with U=None, summed and scaled by the current trap_set_weight, controller.py:245-246), None without a trap cost
+        or traps — evaluated by the device from the cost program of the bound controller."""
         self._refresh_from_controller()
         c = self._cost_spec
         if c.kind != S.COST_GOAL_TRAP or not c.use_trap_cost or len(c.trap_x) == 0:
             return None
         g, t = self.state_costs(torch.as_tensor(x).reshape(1, -1))
-        return g / t
+        return g / (t * c.trap_weight)  # MPC._trap_cost_reduce: sum over the traps * the current trap_set_weight (controller.py:245-246)
 
     def _compute_rollout_costs(self, perturbed_actions, state=None):
         """ExperimentalMPPI._compute_rollout_costs (controller.py:340-381): (cost_total (K,), states (M,K,T,nx),
