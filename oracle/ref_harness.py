@@ -126,7 +126,7 @@ def _fake_env(cls):
     return object.__new__(cls)
 
 
-def build_task(task, num_samples=None, rollout_samples=None, horizon=None, nominal_adapt='NONE'):
+def build_task(task, num_samples=None, rollout_samples=None, horizon=None, nominal_adapt='NONE', controller_class=None):
     """Build the reference's real OnlineMPPI controller for 'push' or 'peg' exactly as
     run_controller does (push_main.py:796-892 / peg_main.py:221-367), REX_EXTRACT transform,
     AlwaysSelectNominal gating.  nominal_adapt: name of a hybrid_model.OnlineAdapt member ('NONE' is the scripts'
@@ -174,7 +174,7 @@ def build_task(task, num_samples=None, rollout_samples=None, horizon=None, nomin
             mpc['rollout_samples'] = rollout_samples
         if horizon is not None:
             mpc['horizon'] = horizon
-        ctrl = ref.online_controller.OnlineMPPI(ds, hybrid, ds.original_config(),
+        ctrl = (controller_class or ref.online_controller.OnlineMPPI)(ds, hybrid, ds.original_config(),
                                                 gating=ref.gating_function.AlwaysSelectNominal(),
                                                 autonomous_recovery=ref.online_controller.AutonomousRecovery.MAB,
                                                 constrain_state=constrain, mpc_opts=mpc, **common)

