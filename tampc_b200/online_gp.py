@@ -1,12 +1,10 @@
 """Drop-in for `tampc.dynamics.online_model.OnlineGPMixing` (independent outputs) whose hyper-parameter fit runs on the
 device: the reference refits its GP with 15 Adam iterations of autograd through gpytorch on every
 control step spent in non-nominal dynamics (online_model.py:386-430; 150 at a reset) — the other heavy per-step cost
-next to the rollout.  Here the data bookkeeping of `OnlineGPMixing` is kept verbatim in spirit (roll / append, the three
-refit strategies, optimiser state carried across updates) and `_fit_params` becomes one call of `tampc_gp_fit`.
-
-The class is built against the reference's own `OnlineDynamicsModel` base, so `update()` (state difference,
-preprocessor transform; online_model.py:33-44) is the reference's code and `HybridDynamicsModel._uses_local_model_api`
-recognises instances:
+next to the rollout.  The class here SUBCLASSES the reference's own `OnlineGPMixing`: its constructor, `reset`, `update`
+/ `_update` (roll / append of the data window, the three refit strategies) run unchanged; only the gpytorch objects
+become plain raw-parameter holders and `_fit_params` becomes one call of `tampc_gp_fit` (optimiser state carried across
+updates like the reference's Adam instance).  `HybridDynamicsModel._uses_local_model_api` recognises instances:
 
     from tampc.dynamics import online_model
     from tampc_b200.online_gp import install_gp
@@ -72,46 +70,33 @@ class _GPView:
     def forward(self, xu):
         return types.SimpleNamespace(mean=self._o._mean_function(xu))
 
+    def set_train_data(self, inputs=None, targets=None, strict=True):
+        """gpytorch ExactGP.set_train_data as the reference's `_update` calls it (online_model.py:401): the data live on
+        the owner (`xu`, `y`), which `_fit_params` reads."""
+
 
 def make_online_gp_class(online_model):
-    """`online_model`: the reference module `tampc.dynamics.online_model` (anything exposing `OnlineDynamicsModel`)."""
-    Base = online_model.OnlineDynamicsModel
-    strategies = getattr(online_model, 'RefitGPStrategy', types.SimpleNamespace(RESET_DATA=0, RECREATE_GP=1, RECREATE_ALL=2))
+    """`online_model`: the reference module `tampc.dynamics.online_model`.  The returned class SUBCLASSES its
+    `OnlineGPMixing`: construction, `reset`, `update` / `_update` (data window, refit strategies) stay the reference's own
+    code; only what touches gpytorch is replaced — the likelihood / GP objects (plain raw-parameter holders here) and
+    `_fit_params` (one `tampc_gp_fit` call)."""
+    Base = online_model.OnlineGPMixing
 
     class B200OnlineGP(Base):
-        """OnlineGPMixing (online_model.py:324-457) with `_fit_params` on the device."""
-
-        def __init__(self, prior, ds, state_difference, max_data_points=50, training_iter=100, slice_to_use=None,
-                     refit_strategy=strategies.RESET_DATA, use_independent_outputs=True, allow_update=True, sample=True,
-                     cuda_device=0, **kwargs):
-            if not use_independent_outputs:
+        def __init__(self, prior, ds, state_difference, *args, cuda_device=0, **kwargs):
+            kwargs.setdefault('use_independent_outputs', True)  # OnlineAdapt.GP_KERNEL_INDEP_OUT (push_main.py:1789)
+            if not kwargs['use_independent_outputs']:
                 raise NotImplementedError("only the independent-output GP (OnlineAdapt.GP_KERNEL_INDEP_OUT) is fused")
-            if max_data_points > L.GP_FIT_MAX_POINTS:
-                raise ValueError("max_data_points {} exceeds TAMPC_GP_FIT_MAX_POINTS={}".format(max_data_points, L.GP_FIT_MAX_POINTS))
-            super().__init__(ds, state_difference, **kwargs)
+            max_points = kwargs.get('max_data_points', args[0] if args else 50)
+            if max_points > L.GP_FIT_MAX_POINTS:
+                raise ValueError("max_data_points {} exceeds TAMPC_GP_FIT_MAX_POINTS={}".format(max_points, L.GP_FIT_MAX_POINTS))
+            # needed by the overrides below, which the reference constructor reaches through reset()
             self._lib = L.load()
             self.cuda_device = cuda_device
-            self.prior = prior
-            self.max_data_points = max_data_points
-            self.xu = None
-            self.y = None
-            self.last_loss = 0
-            self.last_loss_diff = 0
-            self.training_iter = training_iter
-            self.refit_strategy = refit_strategy
-            self.use_independent_outputs = True
-            self.allow_update = allow_update
-            self.sample_dynamics = sample
-            self.last_prediction = None
-            if slice_to_use is None:
-                slice_to_use = slice(max_data_points)
-            xu, y, _ = self.ds.training_set()
-            self.init_xu = xu[slice_to_use]
-            self.init_y = y[slice_to_use]
-            self.ny = int(self.ds.config.ny)
-            self.reset()
+            self.ny = int(ds.config.ny)
+            super().__init__(prior, ds, state_difference, *args, **kwargs)
 
-        # ---- the pieces of gpytorch state the reference keeps (online_model.py:363-384)
+        # ---- the gpytorch objects of online_model.py:363-384 as raw-parameter holders
         def _recreate_all(self):
             self.raw_task_noises = np.zeros(self.ny)   # MultitaskGaussianLikelihood: fresh raw parameters are 0
             self.raw_noise = np.zeros(1)
@@ -122,6 +107,7 @@ def make_online_gp_class(online_model):
             self.raw_lengthscale = np.zeros(self.ny)   # ScaleKernel(RBFKernel(batch_shape=[ny]))
             self.raw_outputscale = np.zeros(self.ny)
             self.gp = _GPView(self)
+            self.optimizer = None
             # MixingBatchGP.__init__ (online_model.py:289-295): is the nominal model evaluated in the original space?
             try:
                 self.ds.preprocessor.invert_x(self.xu)
@@ -131,13 +117,6 @@ def make_online_gp_class(online_model):
             n = 3 * self.ny + 1                           # a new torch.optim.Adam: zero moments, step 0
             self._adam_m, self._adam_v, self._adam_step = np.zeros(n), np.zeros(n), C.c_int64(0)
 
-        def reset(self):
-            self.xu = self.init_xu.clone()
-            self.y = self.init_y.clone()
-            self._recreate_all()
-            if len(self.xu):
-                self._fit_params(self.training_iter)
-
         def _mean_function(self, xu):
             """MixingBatchGP.forward's mean (online_model.py:304-311): the nominal model at the GP's inputs, (N, ny)."""
             pre = self.ds.preprocessor
@@ -146,30 +125,6 @@ def make_online_gp_class(online_model):
                     pred = self.prior.get_batch_predictions(pre.invert_x(xu), all_in_transformed_space=False)
                     return pre.transform_y(pred)
                 return self.prior.get_batch_predictions(xu, all_in_transformed_space=True)
-
-        def _update(self, px, pu, y):
-            # online_model.py:386-410
-            self.last_prediction = None
-            if not self.allow_update:
-                return
-            xu = torch.cat((px.view(1, -1), pu.view(1, -1)), dim=1)
-            y = y.view(1, -1)
-            if self.xu.shape[0] < self.max_data_points:
-                self.xu = torch.cat((self.xu, xu), dim=0)
-                self.y = torch.cat((self.y, y), dim=0)
-            else:
-                self.xu = torch.roll(self.xu, -1, dims=0)
-                self.xu[-1] = xu
-                self.y = torch.roll(self.y, -1, dims=0)
-                self.y[-1] = y
-            if self.refit_strategy is strategies.RESET_DATA or self.refit_strategy == strategies.RESET_DATA:
-                self._fit_params(self.training_iter // 10)
-            elif self.refit_strategy == strategies.RECREATE_GP:
-                self._recreate_gp()
-                self._fit_params(self.training_iter // 3)
-            else:
-                self._recreate_all()
-                self._fit_params(self.training_iter)
 
         def _fit_params(self, training_iter):
             """online_model.py:412-430 as one device call."""
@@ -193,12 +148,12 @@ def make_online_gp_class(online_model):
                 self.last_loss = float(loss[0])
             self.gp.training = False
 
-        def _dynamics_in_transformed_space(self, px, pu, cx, cu):
+        def _make_prediction(self, cx, cu):
             raise RuntimeError("B200OnlineGP predicts inside the rollout kernels only (tampc_mppi_set_gp): use the installed "
                                "B200MPPI's command / predict_next_state / apply_dynamics; there is no host prediction path")
 
         def predict(self, px, pu, cx, cu, already_transformed=False):
-            return self._dynamics_in_transformed_space(px, pu, cx, cu)
+            return self._make_prediction(cx, cu)
 
     return B200OnlineGP
 

@@ -203,10 +203,61 @@ def identity_preprocessor():
 
 
 def fake_online_model_module():
-    """Stand-in for the module tampc.dynamics.online_model: just the abstract base B200OnlineGP derives from."""
+    """Stand-in for the module tampc.dynamics.online_model on the GPU box (no reference tree there): the abstract base, the
+    refit-strategy enum and the DATA BOOKKEEPING of OnlineGPMixing that B200OnlineGP inherits — constructor attributes,
+    reset, the roll / append window and the refit-strategy dispatch of `_update` (online_model.py:317-410) — behaviourally
+    restated for the test; where the reference exists, tests/test_reference_live.py runs the same subclass over the real
+    class."""
+    import enum
+
+    class RefitGPStrategy(enum.IntEnum):
+        RESET_DATA = 0
+        RECREATE_GP = 1
+        RECREATE_ALL = 2
+
     class OnlineDynamicsModel:
         def __init__(self, ds, state_difference, device=torch.device('cpu')):
             self.ds, self.state_difference, self.d, self.dtype = ds, state_difference, device, torch.double
             self.nx, self.nu = ds.config.nx, ds.config.nu
 
-    return types.SimpleNamespace(OnlineDynamicsModel=OnlineDynamicsModel)
+    class OnlineGPMixing(OnlineDynamicsModel):
+        def __init__(self, prior, ds, state_difference, max_data_points=50, training_iter=100, slice_to_use=None,
+                     refit_strategy=RefitGPStrategy.RESET_DATA, use_independent_outputs=False, allow_update=True, sample=True, **kw):
+            super().__init__(ds, state_difference, **kw)
+            self.prior, self.max_data_points, self.training_iter = prior, max_data_points, training_iter
+            self.refit_strategy, self.use_independent_outputs = refit_strategy, use_independent_outputs
+            self.allow_update, self.sample_dynamics = allow_update, sample
+            self.xu = self.y = self.likelihood = self.gp = self.optimizer = self.last_prediction = None
+            self.last_loss = self.last_loss_diff = 0
+            xu, y, _ = ds.training_set()
+            sl = slice(max_data_points) if slice_to_use is None else slice_to_use
+            self.init_xu, self.init_y = xu[sl], y[sl]
+            self.reset()
+
+        def reset(self):
+            self.xu, self.y = self.init_xu.clone(), self.init_y.clone()
+            self._recreate_all()
+            if len(self.xu):
+                self._fit_params(self.training_iter)
+
+        def _update(self, px, pu, y):
+            self.last_prediction = None
+            if not self.allow_update:
+                return
+            row, y = torch.cat((px.view(1, -1), pu.view(1, -1)), dim=1), y.view(1, -1)
+            if self.xu.shape[0] < self.max_data_points:
+                self.xu, self.y = torch.cat((self.xu, row)), torch.cat((self.y, y))
+            else:
+                self.xu, self.y = torch.roll(self.xu, -1, dims=0), torch.roll(self.y, -1, dims=0)
+                self.xu[-1], self.y[-1] = row, y
+            if self.refit_strategy is RefitGPStrategy.RESET_DATA:
+                self.gp.set_train_data(self.xu, self.y, strict=False)
+                self._fit_params(self.training_iter // 10)
+            elif self.refit_strategy is RefitGPStrategy.RECREATE_GP:
+                self._recreate_gp()
+                self._fit_params(self.training_iter // 3)
+            else:
+                self._recreate_all()
+                self._fit_params(self.training_iter)
+
+    return types.SimpleNamespace(OnlineDynamicsModel=OnlineDynamicsModel, OnlineGPMixing=OnlineGPMixing, RefitGPStrategy=RefitGPStrategy)

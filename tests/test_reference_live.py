@@ -147,8 +147,13 @@ def test_device_fitted_gp_class_is_recognised_by_the_reference():
     ref = rh.load_reference()
     from tampc_b200.online_gp import make_online_gp_class
     cls = make_online_gp_class(ref.online_model)
-    assert issubclass(cls, ref.online_model.OnlineDynamicsModel)
+    assert issubclass(cls, ref.online_model.OnlineGPMixing) and issubclass(cls, ref.online_model.OnlineDynamicsModel)
     assert cls.update is ref.online_model.OnlineDynamicsModel.update
+    # the data bookkeeping is the reference's own code, only the gpytorch-facing pieces are replaced
+    for name in ('reset', '_update'):
+        assert getattr(cls, name) is getattr(ref.online_model.OnlineGPMixing, name)
+    for name in ('_recreate_all', '_recreate_gp', '_fit_params', '_make_prediction'):
+        assert getattr(cls, name) is not getattr(ref.online_model.OnlineGPMixing, name)
     assert not getattr(cls, '__abstractmethods__', None)
 
 
