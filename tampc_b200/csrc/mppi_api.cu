@@ -15,6 +15,7 @@
 
 #include "reduce_kernels.cuh"
 #include "variants.cuh"
+#include "tc_rollout.cuh"
 
 using namespace tampc;
 
@@ -86,6 +87,11 @@ struct tampc_mppi {
   size_t weights_bytes = 0;
   int n_weight_elems = 0;
   bool use_mma = false;  // the staged weights are in the mma-path layout
+  bool use_tc = false;   // tcgen05 plain-MLP kernel (tc_rollout.cuh): image in its slab layout, W2 streamed from d_tc_w2
+  TcMlpDims tc_dims{};
+  rollout_launch_fn tc_fn = nullptr;
+  void* d_tc_w2 = nullptr;
+  size_t tc_w2_bytes = 0;
   int img_cost_off = 0, img_sampler_off = 0, img_sampler_d_off = 0, img_bytes = 0;  // shared-memory image offsets inside d_weights
 
   double* h_pin = nullptr;  // pinned staging: [0..15] in, [16..31] out
@@ -108,6 +114,7 @@ struct tampc_mppi {
   std::vector<double> model_params;  // kept so that the network image can be re-laid-out when the GP toggles
   double net_in_scale[kMaxNx + kMaxNu] = {0}, net_in_off[kMaxNx + kMaxNu] = {0}, net_out_scale[kMaxNx] = {0};  // scalers around `net`
   bool gp_on = false;
+  bool img_f64 = false;  // the installed image holds float64 networks (precision F64, or a GP with the replica-variance penalty)
   tampc_gp_desc gp{};
   void* d_gp = nullptr;
   size_t gp_capacity = 0;
@@ -303,6 +310,17 @@ bool dims_are(const std::vector<HostLayer>& m, std::initializer_list<int> dims) 
   return true;
 }
 
+// placeholder variant of the shape-generic tcgen05 kernel (no per-shape kernels; the launcher lives in the handle)
+const ModelVariant* variant_tc_generic() {
+  static const ModelVariant v = [] {
+    ModelVariant m{};
+    m.name = "mlp_tcgen05_generic";
+    m.kind = TAMPC_DYN_MLP;
+    return m;
+  }();
+  return &v;
+}
+
 struct PackedModel {
   const ModelVariant* variant = nullptr;
   std::vector<float> f32;              // FMA-path layouts
@@ -310,7 +328,76 @@ struct PackedModel {
   std::vector<unsigned char> mma_f64;  // mma-path layouts
   std::vector<unsigned char> mma_tf32;
   std::vector<unsigned char> mma_f16;
+  // tcgen05 plain-MLP kernel
+  bool tc = false;
+  std::vector<unsigned char> tc_image, tc_w2;
+  TcMlpDims tc_dims{};
+  rollout_launch_fn tc_fn = nullptr;
 };
+
+// ---- tcgen05 layout (tc_rollout.cuh): K-major no-swizzle slabs.  One slab = rows [n0, n0 + N) x one K = 8 step:
+// (N/8) groups of 256 bytes = [k half (2)][row in group (8)][k in half (4)] floats — the 8 x 16-byte core matrices the
+// shared-memory descriptor walks with LBO = 128, SBO = 256.
+template <typename F>
+void append_slab(std::vector<unsigned char>& blob, int n0, int N, F value) {
+  for (int g = 0; g < N / 8; ++g)
+    for (int half = 0; half < 2; ++half)
+      for (int r = 0; r < 8; ++r)
+        for (int kk = 0; kk < 4; ++kk) append<float>(blob, value(n0 + g * 8 + r, half * 4 + kk));
+}
+
+// (nx+nu) -> h1 -> h2 -> nx, scalers already folded into `net`.  Image: W1 chunk by chunk [hi slabs | lo slabs | bias slab],
+// layer-2 bias slab, W3 as float [h2][8] and b3 (layer 3 runs on the CUDA cores); W2 separately in K-chunk-major order for TMA.
+void pack_tc_mlp(const std::vector<HostLayer>& net, int nx, int nu, PackedModel& out) {
+  TcMlpDims d{};
+  d.nin = nx + nu;
+  d.k0_steps = (d.nin + 7) / 8;
+  d.h1 = net[0].out;
+  d.h2 = net[1].out;
+  d.nc = (d.h1 % 32 == 0 && d.h2 % 32 == 0) ? 32 : 16;
+  d.n_chunks = d.h1 / d.nc;
+  auto hi = [](double w) { return tf32_rna(w); };
+  auto lo = [](double w) { return tf32_rna(w - (double)tf32_rna(w)); };
+  auto W = [](const HostLayer& L, int o, int i) { return (o < L.out && i < L.in) ? L.W[(size_t)o * L.in + i] : 0.0; };
+  std::vector<unsigned char>& img = out.tc_image;
+  d.off_w1 = 0;
+  for (int c = 0; c < d.n_chunks; ++c) {
+    const size_t before = img.size();
+    for (int ks = 0; ks < d.k0_steps; ++ks) append_slab(img, c * d.nc, d.nc, [&](int n, int k) { return hi(W(net[0], n, ks * 8 + k)); });
+    for (int ks = 0; ks < d.k0_steps; ++ks) append_slab(img, c * d.nc, d.nc, [&](int n, int k) { return lo(W(net[0], n, ks * 8 + k)); });
+    append_slab(img, c * d.nc, d.nc, [&](int n, int k) { return k == 0 ? hi(net[0].b[n]) : (k == 1 ? lo(net[0].b[n]) : 0.f); });
+    d.w1_chunk_bytes = (int)(img.size() - before);
+  }
+  d.off_b2 = (int)img.size();
+  append_slab(img, 0, d.h2, [&](int n, int k) { return k == 0 ? hi(net[1].b[n]) : (k == 1 ? lo(net[1].b[n]) : 0.f); });
+  d.off_w3 = (int)img.size();
+  for (int k = 0; k < d.h2; ++k)
+    for (int j = 0; j < 8; ++j) append<float>(img, (float)W(net[2], j, k));
+  d.off_b3 = (int)img.size();
+  for (int j = 0; j < 8; ++j) append<float>(img, j < nx ? (float)net[2].b[j] : 0.f);
+  std::vector<unsigned char>& w2 = out.tc_w2;
+  for (int c = 0; c < d.n_chunks; ++c) {
+    const size_t before = w2.size();
+    for (int ks = 0; ks < d.nc / 8; ++ks) append_slab(w2, 0, d.h2, [&](int n, int k) { return hi(W(net[1], n, c * d.nc + ks * 8 + k)); });
+    for (int ks = 0; ks < d.nc / 8; ++ks) append_slab(w2, 0, d.h2, [&](int n, int k) { return lo(W(net[1], n, c * d.nc + ks * 8 + k)); });
+    d.w2_chunk_bytes = (int)(w2.size() - before);
+  }
+  out.tc = true;
+  out.tc_dims = d;
+  out.tc_fn = tc_mlp_launcher(nx, nu);
+}
+
+// Does the tcgen05 kernel take this MLP?  TAMPC_TC=0 never, =1 whenever the shape allows; default: shapes without a tuned
+// kernel of their own (any make_sequential_network(h_units=...) widths), and the wide shapes at throughput-bound K.
+bool tc_mlp_wanted(const tampc_mppi* h, const std::vector<HostLayer>& net, int nx, int nu, bool has_tuned_variant) {
+  if (h->cfg.precision != TAMPC_PREC_TF32X3 || net.size() != 3) return false;
+  const int h1 = net[0].out, h2 = net[1].out;
+  if (h1 % 16 || h2 % 16 || h1 < 16 || h2 < 16 || h1 > 256 || h2 > 256 || nx > 8 || nu > kMaxNu || !tc_mlp_launcher(nx, nu)) return false;
+  const int env = env_int("TAMPC_TC", -1);
+  if (env == 0) return false;
+  if (env == 1 || !has_tuned_variant) return true;
+  return (h1 >= 128 || h2 >= 128) && h->cfg.num_local >= env_int("TAMPC_TC_MIN_K", 1 << 30);
+}
 
 int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t n, PackedModel& out) {
   const int nx = d.nx, nu = d.nu;
@@ -349,8 +436,14 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
     for (const ModelVariant* v : all) {
       if (v->kind == TAMPC_DYN_MLP && v->nx == nx && v->nu == nu && net[0].out == v->dims[0] && net[1].out == v->dims[1]) out.variant = v;
     }
+    if (tc_mlp_wanted(h, net, nx, nu, out.variant != nullptr)) {
+      pack_tc_mlp(net, nx, nu, out);
+      out.variant = variant_tc_generic();
+      return TAMPC_OK;
+    }
     if (!out.variant) {
-      snprintf(buf, sizeof buf, "no compiled kernel for MLP dynamics nx=%d nu=%d hidden=%d,%d", nx, nu, net[0].out, net[1].out);
+      snprintf(buf, sizeof buf, "no compiled kernel for MLP dynamics nx=%d nu=%d hidden=%d,%d in this precision (the tcgen05 kernel of "
+               "precision tf32x3 takes any hidden widths that are multiples of 16 up to 256)", nx, nu, net[0].out, net[1].out);
       h->err = buf;
       return TAMPC_ERR_UNSUPPORTED;
     }
@@ -481,12 +574,16 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
   LaunchPlan p;
   const int SM = h->n_sm;  // cudaDeviceProp::multiProcessorCount (148 on B200); the thresholds below are per SM
   const int eb = env_int("TAMPC_BLOCK", 0);
+  if (h->use_tc) {
+    p.fn = h->tc_fn;
+    p.block = tc::kThreads;
+    p.name = "tc_mlp_rollout_kernel 3xTF32 (tcgen05.mma kind::tf32, TMEM operands, TMA weight ring)";
+    return p;
+  }
   if (h->gp_on) {
     // one thread per (sample, replica), FMA-layout networks; float32 networks for every precision but F64
-    switch (h->cfg.precision) {
-      case TAMPC_PREC_F64: p.fn = v->gp.f64; p.name = "rollout_gp_kernel f64 (DFMA)"; break;
-      default: p.fn = v->gp.mixed; p.name = "rollout_gp_kernel f32 networks (FFMA2), f64 state + cost + GP posterior"; break;
-    }
+    if (h->img_f64) { p.fn = v->gp.f64; p.name = "rollout_gp_kernel f64 (DFMA)"; }
+    else { p.fn = v->gp.mixed; p.name = "rollout_gp_kernel f32 networks (FFMA2), f64 state + cost + GP posterior"; }
     p.block = 128;
     return p;
   }
@@ -662,6 +759,8 @@ int launch_rollout_for(tampc_mppi* h, int mode, int shift, const double* d_U, in
   RolloutArgs a{};
   a.image = h->d_weights;
   a.image_bytes = h->img_bytes;
+  a.tc = h->tc_dims;
+  a.tc_w2 = h->d_tc_w2;
   a.slope = h->model.leaky_slope;
   a.cost = h->d_cost;
   a.sampler = h->d_sampler;
@@ -1137,7 +1236,7 @@ TAMPC_API void tampc_mppi_destroy(tampc_mppi* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_sampler); cudaFree(h->d_cost); cudaFree(h->d_U[0]); cudaFree(h->d_U[1]); cudaFree(h->d_state);
-  cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_predict); cudaFree(h->d_select); cudaFree(h->d_partials); cudaFree(h->d_partials2); cudaFree(h->d_ticket); cudaFree(h->d_phdr); cudaFree(h->d_pwsum);
+  cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_predict); cudaFree(h->d_select); cudaFree(h->d_tc_w2); cudaFree(h->d_partials); cudaFree(h->d_partials2); cudaFree(h->d_ticket); cudaFree(h->d_phdr); cudaFree(h->d_pwsum);
   cudaFree(h->d_rank_partial); cudaFree(h->d_action); cudaFree(h->d_stats); cudaFree(h->d_weights);
   for (int p = 0; p < h->comm_world; ++p)
     if (p != h->comm_rank && h->comm_peer[p] && h->comm_peer[p] != h->comm_local) cudaIpcCloseMemHandle(h->comm_peer[p]);
@@ -1154,14 +1253,74 @@ TAMPC_API void tampc_mppi_destroy(tampc_mppi* h) {
 
 // Lay the model out for the kernels the handle will run.  With the GP residual on, the networks are always in the
 // FMA layout (gp_rollout.cuh); otherwise the precision picks the layout.
+// With a sampled GP and rollout_var_cost > 0 the cost holds the VARIANCE over the M replicas of every step's cost
+// (controller.py:364).  The replicas differ only by the GP draws, so that variance is a difference of nearly equal
+// numbers, and the independent float32 rounding of each replica's network pass shows up in it amplified ~1000x
+// (measured: 6.4e-5 on the total cost with float32 networks and everything else in float64; north star 1e-5).  Such
+// a configuration therefore runs the float64 kernel whatever precision was asked for (K is ~500 there: latency-bound).
+static bool gp_needs_f64(const tampc_mppi* h) {
+  return h->gp_on && h->gp.sample && h->gp.rollout_samples > 1 && h->gp.rollout_var_cost != 0.0;
+}
+
 static int install_model(tampc_mppi* h, const tampc_model_desc* desc, const double* params, size_t n_params) {
   PackedModel pm;
   int rc = pack_model(h, *desc, params, n_params, pm);
   if (rc) return rc;
+  h->use_tc = false;
+  if (pm.tc) {
+    if (h->gp_on) { h->err = "the tcgen05 MLP kernel has no GP-residual form"; return TAMPC_ERR_UNSUPPORTED; }
+    // image = slabs | CostS<float,float> | SamplerS<float> | SamplerS<double> (the layout of the other tensor-core kernels)
+    const size_t wbytes = (pm.tc_image.size() + 15) & ~size_t(15);
+    const size_t cost_off = wbytes, samp_off = cost_off + ((sizeof(CostS<float, float>) + 15) & ~size_t(15));
+    const size_t samp_d_off = samp_off + ((sizeof(SamplerS<float>) + 15) & ~size_t(15));
+    const size_t bytes = samp_d_off + ((sizeof(SamplerS<double>) + 15) & ~size_t(15));
+    TcMlpDims d = pm.tc_dims;
+    d.off_cost = (int)cost_off;
+    d.off_sampler = (int)samp_off;
+    // ring stages: what is left of the 227 KB next to the image, the nominal sequence and the control block
+    const int ring_off = tc::smem_ring_off((int)bytes, h->cfg.max_horizon);
+    const int avail = 227 * 1024 - 1024 - ring_off;
+    int stages = avail / d.w2_chunk_bytes;
+    if (stages > tc::kMaxStages) stages = tc::kMaxStages;
+    if (stages >= d.n_chunks) { stages = d.n_chunks; d.resident = 1; }
+    if (stages < 2 && !d.resident) { h->err = "tcgen05 MLP kernel: shared memory cannot hold two K-chunks of layer 2"; return TAMPC_ERR_UNSUPPORTED; }
+    d.stages = stages;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (bytes > h->weights_bytes) {
+      cudaFree(h->d_weights);
+      h->d_weights = nullptr;
+      CUDA_TRY(h, cudaMalloc(&h->d_weights, bytes));
+      h->weights_bytes = bytes;
+    }
+    CUDA_TRY(h, cudaMemset(h->d_weights, 0, h->weights_bytes));
+    CUDA_TRY(h, cudaMemcpy(h->d_weights, pm.tc_image.data(), pm.tc_image.size(), cudaMemcpyHostToDevice));
+    if (pm.tc_w2.size() > h->tc_w2_bytes) {
+      cudaFree(h->d_tc_w2);
+      h->d_tc_w2 = nullptr;
+      CUDA_TRY(h, cudaMalloc(&h->d_tc_w2, pm.tc_w2.size()));
+      h->tc_w2_bytes = pm.tc_w2.size();
+    }
+    CUDA_TRY(h, cudaMemcpy(h->d_tc_w2, pm.tc_w2.data(), pm.tc_w2.size(), cudaMemcpyHostToDevice));
+    h->use_tc = true;
+    h->use_mma = true;  // CostS / SamplerS in the float32 tensor-kernel types
+    h->img_f64 = false;
+    h->tc_dims = d;
+    h->tc_fn = pm.tc_fn;
+    h->img_cost_off = (int)cost_off;
+    h->img_sampler_off = (int)samp_off;
+    h->img_sampler_d_off = (int)samp_d_off;
+    h->img_bytes = (int)bytes;
+    h->n_weight_elems = (int)(wbytes / 4);
+    h->variant = pm.variant;
+    h->model = *desc;
+    h->has_model = true;
+    return prep_image(h);
+  }
   // arithmetic -> layout:  F64 = DMMA layout (FMA layout if the shape has no mma kernel or TAMPC_F64_IMPL=fma),
   // TF32X3 = mma layout, MIXED / F32 = float32 FMA layout
   const int prec = h->cfg.precision;
-  const bool f64 = prec == TAMPC_PREC_F64;
+  const bool f64 = prec == TAMPC_PREC_F64 || gp_needs_f64(h);
   const char* f64_impl = getenv("TAMPC_F64_IMPL");
   bool use_mma = false;
   if (h->gp_on) {
@@ -1224,6 +1383,7 @@ static int install_model(tampc_mppi* h, const tampc_model_desc* desc, const doub
   CUDA_TRY(h, cudaMemcpy(h->d_weights, src, raw_bytes, cudaMemcpyHostToDevice));
   h->n_weight_elems = (int)(wbytes / (f64 ? 8 : 4));
   h->use_mma = use_mma;
+  h->img_f64 = f64;
   h->img_cost_off = (int)cost_off;
   h->img_sampler_off = (int)samp_off;
   h->img_sampler_d_off = (int)samp_d_off;
@@ -1395,10 +1555,11 @@ TAMPC_API int tampc_mppi_set_gp(tampc_mppi* h, const tampc_gp_desc* g, const dou
   CUDA_TRY(h, cudaMemcpy(h->d_gp, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   h->gp_bytes = (int)blob.size();
   h->gp = *g;
-  if (!h->gp_on) {
-    h->gp_on = true;
+  const bool was_on = h->gp_on;
+  h->gp_on = true;
+  if (!was_on || (h->img_f64 != (h->cfg.precision == TAMPC_PREC_F64 || gp_needs_f64(h)))) {
     int rc = install_model(h, &h->model, h->model_params.data(), h->model_params.size());
-    if (rc) { h->gp_on = false; return rc; }
+    if (rc) { h->gp_on = was_on; return rc; }
   }
   return TAMPC_OK;
 }
@@ -1650,6 +1811,8 @@ TAMPC_API int tampc_mppi_get_rollouts(tampc_mppi* h, const double* state, double
   RolloutArgs a{};
   a.image = h->d_weights;
   a.image_bytes = h->img_bytes;
+  a.tc = h->tc_dims;
+  a.tc_w2 = h->d_tc_w2;
   a.slope = h->model.leaky_slope;
   a.cost = h->d_cost;
   a.sampler = h->d_sampler;
@@ -1691,6 +1854,8 @@ static int predict_impl(tampc_mppi* h, const double* state, const double* action
   RolloutArgs a{};
   a.image = h->d_weights;
   a.image_bytes = h->img_bytes;
+  a.tc = h->tc_dims;
+  a.tc_w2 = h->d_tc_w2;
   a.slope = h->model.leaky_slope;
   a.cost = h->d_cost;
   a.sampler = h->d_sampler;
@@ -1709,7 +1874,7 @@ static int predict_impl(tampc_mppi* h, const double* state, const double* action
     // with a GP installed the image is in the FMA layout of the (sample, replica) kernels: the plain FMA kernels of
     // the same precision read it as it is and know nothing of the residual
     if (h->gp_on) {
-      plan.fn = h->cfg.precision == TAMPC_PREC_F64 ? h->variant->f64_s1 : h->variant->gp.nominal;
+      plan.fn = h->img_f64 ? h->variant->f64_s1 : h->variant->gp.nominal;
       plan.block = 32;
       plan.name = "rollout_kernel (nominal network only)";
     } else {

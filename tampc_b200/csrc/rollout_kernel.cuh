@@ -9,6 +9,23 @@
 
 namespace tampc {
 
+// Shape and image layout of the tcgen05 plain-MLP kernel (tc_rollout.cuh), filled in by mppi_api.cu pack_tc_mlp.
+struct TcMlpDims {
+  int nin;        // nx + nu
+  int k0_steps;   // K = 8 steps of the input row (1 or 2)
+  int h1, h2;     // hidden widths, multiples of nc, <= 256
+  int nc;         // width of a layer-1 output chunk = K-chunk of layer 2 (32 or 16)
+  int n_chunks;   // h1 / nc
+  int stages;     // ring stages, each holding one K-chunk of W2 (hi + lo pieces)
+  int resident;   // n_chunks <= stages: W2 is loaded once and stays
+  int off_w1;     // image: per chunk [k0 hi slabs | k0 lo slabs | bias slab], slab = (nc/8) * 256 bytes
+  int off_b2;     // image: bias slab of layer 2, (h2/8) * 256 bytes
+  int off_w3;     // image: float [h2][8]
+  int off_b3;     // image: float [8]
+  int off_cost, off_sampler;  // image: CostS<float,float>, SamplerS<float>
+  int w1_chunk_bytes, w2_chunk_bytes;
+};
+
 struct RolloutArgs {
   const void* image;    // shared-memory image: packed networks | CostS | SamplerS in the kernel's types
   int image_bytes;
@@ -44,6 +61,9 @@ struct RolloutArgs {
   int M;
   double var_cost, var_discount;
   const double* gp_eps;
+  // tcgen05 plain-MLP kernel: W2 in K-chunk-major slab order in global memory (streamed by TMA), dims
+  const void* tc_w2;
+  TcMlpDims tc;
 };
 
 template <typename T> __host__ __device__ constexpr size_t align16(size_t n) { return (n + 15) & ~size_t(15); }

@@ -88,5 +88,7 @@ const ModelVariant* variant_mlp_5_3_64(); // 8-64-64-5
 const ModelVariant* variant_mlp_5_3_128(); // 8-128-128-5 (tensor-core kernels only)
 const ModelVariant* variant_mlp_5_3_256(); // 8-256-256-5 (streamed-weight 3xTF32 kernel only)
 const ModelVariant* variant_pendulum();
+// plain MLP (nx+nu) -> H1 -> H2 -> nx of any widths (multiples of 16, <= 256), nx <= 8, nu <= 4: tcgen05 kernel (tc_rollout.cuh)
+rollout_launch_fn tc_mlp_launcher(int nx, int nu);
 
 }  // namespace tampc

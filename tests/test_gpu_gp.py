@@ -127,5 +127,5 @@ def test_gp_toggle_returns_to_the_tensor_core_path(cuda_lib):
     m.set_gp(gp)  # and back on
     m.U = torch.from_numpy(z['in.U'])
     m.command(z['in.state'], noise=z['in.noise'], gp_eps=z['in.gp_eps'])
-    assert _rel(m.cost_total.numpy(), z['ref.cost_total']) < 2e-4
+    assert _rel(m.cost_total.numpy(), z["ref.cost_total"]) < 1e-5
     m.close()
