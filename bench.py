@@ -42,7 +42,7 @@ FP32_PEAK_TFLOPS = 74.1  # tools/peaks/fma_peaks ffma2_reg on this pool's B200 (
 FP64_TENSOR_PEAK_TFLOPS = 37.1  # tools/peaks/mma_peaks dmma (profiles/mma_peaks_r1.jsonl)
 TF32_MMA_PEAK_TFLOPS = 278.0  # tools/peaks/mma_peaks mma.sync m16n8k8 tf32
 F16_MMA_PEAK_TFLOPS = 556.0  # tools/peaks/mma_peaks mma.sync m16n8k16 f16
-TCGEN05_TF32_PEAK_TFLOPS = None  # tools/peaks/tcgen05_peaks (profiles/tcgen05_peaks_r2.jsonl): tcgen05.mma kind::tf32, M=128
+TCGEN05_TF32_PEAK_TFLOPS = 982.7  # tools/peaks/tcgen05_probe (profiles/tcgen05_probe_r2.jsonl): tcgen05.mma kind::tf32, M=128, N=256, A in TMEM
 # DRAM traffic of one rollout launch at K=8192 from the committed ncu capture (the kernel reads its ~45 KB image and
 # the nominal sequence, writes 8*K bytes of costs that stay in L2): compute-bound by four orders of magnitude
 NCU_DRAM_BYTES_PER_LAUNCH = {'tf32x3': 75776, 'f16x3': 70912}
@@ -317,9 +317,14 @@ def strong_scaling_points(args, rank, local_rank, world, dist, torch, B200MPPI, 
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t[0])
         flop = 2.0 * spec.dynamics.macs_per_step
+        tf = K * T * flop / (ms * 1e-3) * 1e-12
+        peak = (TCGEN05_TF32_PEAK_TFLOPS if 'tcgen05' in kname else TF32_MMA_PEAK_TFLOPS) / 3.0 * world
         out[wl] = {"workload": WORKLOADS[wl]['name'], "K_total": int(K), "K_per_gpu": int(-(-K // world)), "T": int(T), "n_gpus": world,
                    "scaling": "strong", "steps": steps, "warmup": 3, "ms_per_step": ms, "value": K * T / (ms * 1e-3), "unit": UNIT,
-                   "tflops_algorithmic": K * T * flop / (ms * 1e-3) * 1e-12, "kernel": kname}
+                   "tflops_algorithmic": tf, "kernel": kname,
+                   "frac_of_tensor_peak": tf / peak,
+                   "peak_note": "whole command (rollout + softmax update) against {} GPU(s) x the measured {} peak / 3 products per MAC".format(
+                       world, "tcgen05 kind::tf32 982.7 TFLOP/s" if 'tcgen05' in kname else "mma.sync tf32 278 TFLOP/s")}
     return out
 
 
@@ -509,7 +514,7 @@ def main():
                 src = "FFMA2 register-operand peak measured (profiles/fma_peaks_r1.jsonl)"
             elif 'tcgen05' in kernel_name:
                 bound, peak = "tensor", TCGEN05_TF32_PEAK_TFLOPS / 3.0
-                src = ("tcgen05.mma kind::tf32 M=128 measured {:.0f} TFLOP/s (profiles/tcgen05_peaks_r2.jsonl) / 3 products per "
+                src = ("tcgen05.mma kind::tf32 M=128 measured {:.0f} TFLOP/s (profiles/tcgen05_probe_r2.jsonl) / 3 products per "
                        "algorithmic MAC (error-compensated 3xTF32 split)").format(TCGEN05_TF32_PEAK_TFLOPS)
             elif '3xTF32' in kernel_name:
                 bound, peak = "tensor", TF32_MMA_PEAK_TFLOPS / 3.0

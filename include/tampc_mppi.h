@@ -312,6 +312,9 @@ TAMPC_API int tampc_mppi_query(tampc_mppi* h, int32_t what, double* out, size_t 
 /* which rollout kernel family and arithmetic a command of this handle runs (static string; "none" before set_model):
  * the precision asked for in the config is a request, e.g. TF32X3 on the analytic pendulum runs the FMA kernel */
 TAMPC_API const char* tampc_mppi_kernel_name(tampc_mppi* h);
+/* development aid: 64 SM-clock stamps left by the roles of the tcgen05 kernel's first CTA at horizon step 2 when the
+ * handle's model was installed with TAMPC_TC_PROF=1 in the environment (tools/tc_timeline.py); zeros otherwise */
+TAMPC_API int tampc_mppi_debug_stamps(tampc_mppi* h, int64_t* out);
 /* device pointer to the per-sample costs of the last rollout (double[num_local]); valid until the next call */
 TAMPC_API int tampc_mppi_device_costs(tampc_mppi* h, void** dev_ptr);
 TAMPC_API int tampc_mppi_synchronize(tampc_mppi* h);

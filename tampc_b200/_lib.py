@@ -23,7 +23,7 @@ EXPORTS = [
     'tampc_mppi_last_error', 'tampc_mppi_abi_version', 'tampc_mppi_create', 'tampc_mppi_destroy',
     'tampc_mppi_set_model', 'tampc_mppi_set_cost', 'tampc_mppi_set_nominal', 'tampc_mppi_get_nominal',
     'tampc_mppi_command', 'tampc_mppi_command_begin', 'tampc_mppi_command_finish', 'tampc_mppi_rollout_costs',
-    'tampc_mppi_get_rollouts', 'tampc_mppi_query', 'tampc_mppi_select_action', 'tampc_mppi_state_costs', 'tampc_mppi_kernel_name', 'tampc_mppi_device_costs', 'tampc_mppi_synchronize',
+    'tampc_mppi_get_rollouts', 'tampc_mppi_query', 'tampc_mppi_select_action', 'tampc_mppi_state_costs', 'tampc_mppi_kernel_name', 'tampc_mppi_debug_stamps', 'tampc_mppi_device_costs', 'tampc_mppi_synchronize',
     'tampc_mppi_command_resident', 'tampc_mppi_set_state_resident', 'tampc_mppi_rollout_resident', 'tampc_mppi_comm_init', 'tampc_mppi_comm_connect', 'tampc_mppi_comm_disconnect', 'tampc_mppi_predict', 'tampc_mppi_predict_nominal',
     'tampc_mppi_set_gp', 'tampc_mppi_set_gp_draws', 'tampc_gp_fit', 'tampc_gp_fit_last_error',
 ]
@@ -129,6 +129,7 @@ def load():
     lib.tampc_mppi_state_costs.argtypes = [vp, dp, i32, dp, dp]
     lib.tampc_mppi_kernel_name.restype = C.c_char_p
     lib.tampc_mppi_kernel_name.argtypes = [vp]
+    lib.tampc_mppi_debug_stamps.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.tampc_mppi_device_costs.argtypes = [vp, C.POINTER(vp)]
     lib.tampc_mppi_synchronize.argtypes = [vp]
     lib.tampc_mppi_command_resident.argtypes = [vp, i32]

@@ -92,6 +92,7 @@ struct tampc_mppi {
   rollout_launch_fn tc_fn = nullptr;
   void* d_tc_w2 = nullptr;
   size_t tc_w2_bytes = 0;
+  long long* d_tc_prof = nullptr;  // development (TAMPC_TC_PROF=1): clock stamps of the tcgen05 kernel's roles
   int img_cost_off = 0, img_sampler_off = 0, img_sampler_d_off = 0, img_bytes = 0;  // shared-memory image offsets inside d_weights
 
   double* h_pin = nullptr;  // pinned staging: [0..15] in, [16..31] out
@@ -371,16 +372,17 @@ void pack_tc_mlp(const std::vector<HostLayer>& net, int nx, int nu, PackedModel&
   d.off_b2 = (int)img.size();
   append_slab(img, 0, d.h2, [&](int n, int k) { return k == 0 ? hi(net[1].b[n]) : (k == 1 ? lo(net[1].b[n]) : 0.f); });
   d.off_w3 = (int)img.size();
-  for (int k = 0; k < d.h2; ++k)
-    for (int j = 0; j < 8; ++j) append<float>(img, (float)W(net[2], j, k));
+  for (int k = 0; k < d.h2; ++k)  // [k][ceil(nx/2)] pairs of outputs (packed FFMA2 operands)
+    for (int j = 0; j < 2 * ((nx + 1) / 2); ++j) append<float>(img, (float)W(net[2], j, k));
+  while (img.size() % 16) append<float>(img, 0.f);
   d.off_b3 = (int)img.size();
   for (int j = 0; j < 8; ++j) append<float>(img, j < nx ? (float)net[2].b[j] : 0.f);
-  std::vector<unsigned char>& w2 = out.tc_w2;
-  for (int c = 0; c < d.n_chunks; ++c) {
+  std::vector<unsigned char>& w2 = out.tc_w2;  // K-step-major: [k-step][hi slab | lo slab], one ring stage each
+  for (int q = 0; q < d.h1 / 8; ++q) {
     const size_t before = w2.size();
-    for (int ks = 0; ks < d.nc / 8; ++ks) append_slab(w2, 0, d.h2, [&](int n, int k) { return hi(W(net[1], n, c * d.nc + ks * 8 + k)); });
-    for (int ks = 0; ks < d.nc / 8; ++ks) append_slab(w2, 0, d.h2, [&](int n, int k) { return lo(W(net[1], n, c * d.nc + ks * 8 + k)); });
-    d.w2_chunk_bytes = (int)(w2.size() - before);
+    append_slab(w2, 0, d.h2, [&](int n, int k) { return hi(W(net[1], n, q * 8 + k)); });
+    append_slab(w2, 0, d.h2, [&](int n, int k) { return lo(W(net[1], n, q * 8 + k)); });
+    d.w2_stage_bytes = (int)(w2.size() - before);
   }
   out.tc = true;
   out.tc_dims = d;
@@ -396,14 +398,17 @@ bool tc_mlp_wanted(const tampc_mppi* h, const std::vector<HostLayer>& net, int n
   const int env = env_int("TAMPC_TC", -1);
   if (env == 0) return false;
   if (env == 1 || !has_tuned_variant) return true;
-  return (h1 >= 128 || h2 >= 128) && h->cfg.num_local >= env_int("TAMPC_TC_MIN_K", 1 << 30);
+  // measured on B200 (profiles/r2_tc_sweep.jsonl): at widths >= 128 the tcgen05 kernel wins at every K (H=256: 0.53 vs 2.03 ms
+  // at K=1024, 29.6 vs 113 ms at K=1M; H=128: 0.22 vs 0.23 ms at K=1024, 12.3 vs 23.7 ms at 1M); at 32 / 64 the register-
+  // chained mma.sync kernels win (tcgen05.mma issue costs ~150 cycles whatever its N)
+  return (h1 >= 128 || h2 >= 128) && h->cfg.num_local >= env_int("TAMPC_TC_MIN_K", 1);
 }
 
 int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t n, PackedModel& out) {
   const int nx = d.nx, nu = d.nu;
   if (nx != h->cfg.nx || nu != h->cfg.nu) { h->err = "model nx/nu differ from the handle's"; return TAMPC_ERR_INVALID; }
   if (!(d.leaky_slope >= 0.0 && d.leaky_slope <= 1.0)) { h->err = "leaky_slope must be in [0,1]"; return TAMPC_ERR_UNSUPPORTED; }
-  const ModelVariant* all[] = {variant_rex_push(), variant_rex_peg(), variant_mlp_5_3_32(), variant_mlp_5_3_64(), variant_mlp_5_3_128(), variant_mlp_5_3_256(),
+  const ModelVariant* all[] = {variant_rex_push(), variant_rex_peg(), variant_mlp_5_3_32(), variant_mlp_5_3_64(), variant_mlp_5_3_128(),
                                variant_pendulum()};
   char buf[256];
   if (d.kind == TAMPC_DYN_PENDULUM) {
@@ -606,7 +611,7 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
     const int warps = (K + (mt << idx) - 1) / (mt << idx);
     p.block = warps <= cap32 ? 32 : (warps <= cap64 ? 64 : 128);
     p.fn = fmma[idx];
-    p.name = f64 ? "rollout_mma_kernel f64 (DMMA m8n8k4)" : (f16 ? "rollout_mma_kernel 3xFP16 (HMMA m16n8k16)" : (big ? "rollout_mma(_stream)_kernel 3xTF32 (HMMA m16n8k8)" : "rollout_mma_kernel 3xTF32 (HMMA m16n8k8)"));
+    p.name = f64 ? "rollout_mma_kernel f64 (DMMA m8n8k4)" : (f16 ? "rollout_mma_kernel 3xFP16 (HMMA m16n8k16)" : "rollout_mma_kernel 3xTF32 (HMMA m16n8k8)");
     if (eb == 32 || eb == 64 || eb == 128) p.block = eb;
     // throughput-bound 3xTF32: eight warps per CTA and two CTAs per SM give 16 resident warps instead of 12.
     // Measured on B200 (push, T=40): a full wave takes 1.18x as long but holds 1.33x the samples (1M: 5.98 -> 5.68 ms),
@@ -761,6 +766,7 @@ int launch_rollout_for(tampc_mppi* h, int mode, int shift, const double* d_U, in
   a.image_bytes = h->img_bytes;
   a.tc = h->tc_dims;
   a.tc_w2 = h->d_tc_w2;
+  a.tc_prof = h->d_tc_prof;
   a.slope = h->model.leaky_slope;
   a.cost = h->d_cost;
   a.sampler = h->d_sampler;
@@ -1236,7 +1242,7 @@ TAMPC_API void tampc_mppi_destroy(tampc_mppi* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_sampler); cudaFree(h->d_cost); cudaFree(h->d_U[0]); cudaFree(h->d_U[1]); cudaFree(h->d_state);
-  cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_predict); cudaFree(h->d_select); cudaFree(h->d_tc_w2); cudaFree(h->d_partials); cudaFree(h->d_partials2); cudaFree(h->d_ticket); cudaFree(h->d_phdr); cudaFree(h->d_pwsum);
+  cudaFree(h->d_costs); cudaFree(h->d_noise); cudaFree(h->d_states); cudaFree(h->d_scratch); cudaFree(h->d_predict); cudaFree(h->d_select); cudaFree(h->d_tc_w2); cudaFree(h->d_tc_prof); cudaFree(h->d_partials); cudaFree(h->d_partials2); cudaFree(h->d_ticket); cudaFree(h->d_phdr); cudaFree(h->d_pwsum);
   cudaFree(h->d_rank_partial); cudaFree(h->d_action); cudaFree(h->d_stats); cudaFree(h->d_weights);
   for (int p = 0; p < h->comm_world; ++p)
     if (p != h->comm_rank && h->comm_peer[p] && h->comm_peer[p] != h->comm_local) cudaIpcCloseMemHandle(h->comm_peer[p]);
@@ -1279,12 +1285,13 @@ static int install_model(tampc_mppi* h, const tampc_model_desc* desc, const doub
     d.off_sampler = (int)samp_off;
     // ring stages: what is left of the 227 KB next to the image, the nominal sequence and the control block
     const int ring_off = tc::smem_ring_off((int)bytes, h->cfg.max_horizon);
-    const int avail = 227 * 1024 - 1024 - ring_off;
-    int stages = avail / d.w2_chunk_bytes;
+    const int avail = 226 * 1024 - ring_off;
+    int stages = avail / d.w2_stage_bytes;
     if (stages > tc::kMaxStages) stages = tc::kMaxStages;
-    if (stages >= d.n_chunks) { stages = d.n_chunks; d.resident = 1; }
-    if (stages < 2 && !d.resident) { h->err = "tcgen05 MLP kernel: shared memory cannot hold two K-chunks of layer 2"; return TAMPC_ERR_UNSUPPORTED; }
+    if (stages >= d.h1 / 8) { stages = d.h1 / 8; d.resident = 1; }
+    if (stages < 2 * (d.nc / 8) && !d.resident) { h->err = "tcgen05 MLP kernel: shared memory cannot hold two K-chunks of layer 2"; return TAMPC_ERR_UNSUPPORTED; }
     d.stages = stages;
+    d.n_issuers = (d.h2 % 32 == 0 && env_int("TAMPC_TC_ISSUERS", 1) == 2) ? 2 : 1;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (bytes > h->weights_bytes) {
@@ -1296,12 +1303,16 @@ static int install_model(tampc_mppi* h, const tampc_model_desc* desc, const doub
     CUDA_TRY(h, cudaMemset(h->d_weights, 0, h->weights_bytes));
     CUDA_TRY(h, cudaMemcpy(h->d_weights, pm.tc_image.data(), pm.tc_image.size(), cudaMemcpyHostToDevice));
     if (pm.tc_w2.size() > h->tc_w2_bytes) {
-      cudaFree(h->d_tc_w2);
+      cudaFree(h->d_tc_w2); cudaFree(h->d_tc_prof);
       h->d_tc_w2 = nullptr;
       CUDA_TRY(h, cudaMalloc(&h->d_tc_w2, pm.tc_w2.size()));
       h->tc_w2_bytes = pm.tc_w2.size();
     }
     CUDA_TRY(h, cudaMemcpy(h->d_tc_w2, pm.tc_w2.data(), pm.tc_w2.size(), cudaMemcpyHostToDevice));
+    if (env_int("TAMPC_TC_PROF", 0) && !h->d_tc_prof) {
+      CUDA_TRY(h, cudaMalloc(&h->d_tc_prof, sizeof(long long) * 64));
+      CUDA_TRY(h, cudaMemset(h->d_tc_prof, 0, sizeof(long long) * 64));
+    }
     h->use_tc = true;
     h->use_mma = true;  // CostS / SamplerS in the float32 tensor-kernel types
     h->img_f64 = false;
@@ -1813,6 +1824,7 @@ TAMPC_API int tampc_mppi_get_rollouts(tampc_mppi* h, const double* state, double
   a.image_bytes = h->img_bytes;
   a.tc = h->tc_dims;
   a.tc_w2 = h->d_tc_w2;
+  a.tc_prof = h->d_tc_prof;
   a.slope = h->model.leaky_slope;
   a.cost = h->d_cost;
   a.sampler = h->d_sampler;
@@ -1856,6 +1868,7 @@ static int predict_impl(tampc_mppi* h, const double* state, const double* action
   a.image_bytes = h->img_bytes;
   a.tc = h->tc_dims;
   a.tc_w2 = h->d_tc_w2;
+  a.tc_prof = h->d_tc_prof;
   a.slope = h->model.leaky_slope;
   a.cost = h->d_cost;
   a.sampler = h->d_sampler;
@@ -2017,6 +2030,17 @@ TAMPC_API int tampc_mppi_state_costs(tampc_mppi* h, const double* states, int32_
   CUDA_TRY(h, le);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->launches++;
+  return TAMPC_OK;
+}
+
+// development: the 64 clock stamps the tcgen05 kernel left (TAMPC_TC_PROF=1 at set_model time); zeros otherwise
+TAMPC_API int tampc_mppi_debug_stamps(tampc_mppi* h, int64_t* out) {
+  if (!h || !out) return TAMPC_ERR_INVALID;
+  memset(out, 0, sizeof(int64_t) * 64);
+  if (!h->d_tc_prof) return TAMPC_OK;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaMemcpy(out, h->d_tc_prof, sizeof(int64_t) * 64, cudaMemcpyDeviceToHost));
   return TAMPC_OK;
 }
 

@@ -16,14 +16,15 @@ struct TcMlpDims {
   int h1, h2;     // hidden widths, multiples of nc, <= 256
   int nc;         // width of a layer-1 output chunk = K-chunk of layer 2 (32 or 16)
   int n_chunks;   // h1 / nc
-  int stages;     // ring stages, each holding one K-chunk of W2 (hi + lo pieces)
-  int resident;   // n_chunks <= stages: W2 is loaded once and stays
+  int stages;     // ring stages, each holding one K = 8 step of W2 (hi slab + lo slab)
+  int resident;   // h1 / 8 <= stages: W2 is loaded once and stays
+  int n_issuers;  // threads issuing layer 2 (1, or 2: each half of the output columns)
   int off_w1;     // image: per chunk [k0 hi slabs | k0 lo slabs | bias slab], slab = (nc/8) * 256 bytes
   int off_b2;     // image: bias slab of layer 2, (h2/8) * 256 bytes
-  int off_w3;     // image: float [h2][8]
+  int off_w3;     // image: float [h2][2 * ceil(nx/2)] (output pairs for packed FFMA2)
   int off_b3;     // image: float [8]
   int off_cost, off_sampler;  // image: CostS<float,float>, SamplerS<float>
-  int w1_chunk_bytes, w2_chunk_bytes;
+  int w1_chunk_bytes, w2_stage_bytes;
 };
 
 struct RolloutArgs {
@@ -64,6 +65,7 @@ struct RolloutArgs {
   // tcgen05 plain-MLP kernel: W2 in K-chunk-major slab order in global memory (streamed by TMA), dims
   const void* tc_w2;
   TcMlpDims tc;
+  long long* tc_prof;  // development: per-role clock64() stamps of CTA 0 at step 2 (TAMPC_TC_PROF=1), else null
 };
 
 template <typename T> __host__ __device__ constexpr size_t align16(size_t n) { return (n + 15) & ~size_t(15); }

@@ -13,18 +13,18 @@
 //   epilogue  tcgen05.ld D1 -> LeakyReLU -> hi/lo split -> tcgen05.st: the chunk becomes a K-chunk of layer 2's A operand
 //   layer 2   D2[128 x H2] += A1chunk W2chunk^T    N = H2 (up to 256) per instruction, accumulating over the K-chunks;
 //                                                  W2 (up to 512 KB of hi/lo pieces) is STREAMED from L2 by the TMA unit
-//                                                  (cp.async.bulk + mbarrier complete_tx) through a shared-memory ring,
-//                                                  or loaded once if it fits
+//                                                  (cp.async.bulk + mbarrier complete_tx) through a shared-memory ring of
+//                                                  one-K-step stages (16 KB at H2 = 256), or loaded once if it fits
 //   layer 3   dx = h2 W3^T + b3                    on the CUDA cores inside the D2 epilogue (nx <= 8 outputs: an N=8 MMA
 //                                                  costs as much to issue as an N=256 one; measured ~150 cycles per
 //                                                  tcgen05.mma from one thread, tools/peaks/tcgen05_issue.cu)
 // 3xTF32: every product is A_lo B_hi + A_hi B_lo + A_hi B_hi with fp32 accumulation in TMEM (the error-compensated split
 // of the mma.sync kernels, mma_rollout.cuh); biases enter through a constant ones column of A.
 //
-// Warp roles (352 threads): warps 0-3 own the samples (state, sampling, cost) and post-process the EVEN layer-1 chunks,
+// Warp roles (384 threads): warps 0-3 own the samples (state, sampling, cost) and post-process the EVEN layer-1 chunks,
 // warps 4-7 post-process the ODD chunks and half of D2 (a warp can only touch the TMEM lanes of its quadrant, warp % 4,
 // so two warps share a quadrant); warp 8 issues layer 1, warp 9 issues layer 2 (two issuing threads run in parallel,
-// tcgen05_issue.cu), warp 10 feeds the weight ring.  Hand-offs are mbarriers (tcgen05.commit on the MMA side).
+// tcgen05_issue.cu; optionally a second one, warp 11, for the other half of its columns), warp 10 feeds the weight ring.  Hand-offs are mbarriers (tcgen05.commit on the MMA side).
 // Every wait is bounded: on a timeout the CTA raises an abort flag, all roles leave their loops, TMEM is released and
 // the tile's costs come back as NaN.
 #pragma once
@@ -79,6 +79,10 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
     }
   }
 }
+// hi piece of the 3xTF32 split ROUNDED to nearest (the mma.sync kernels truncate): |lo| = |f - hi| <= 2^-12 |f|, so the
+// tensor core's own truncation of lo to TF32 loses at most 2^-23 |f| — float32 accuracy without a bias towards zero, which
+// is what carried a 256-wide network through a horizon of 100 steps at 2e-5 instead of the gate's 1e-5
+__device__ __forceinline__ uint32_t split_hi(float f) { return (__float_as_uint(f) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\t.reg .b32 R;\n\telect.sync R|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
@@ -102,18 +106,22 @@ __device__ __forceinline__ bool elect_one() {
                : "memory")
 
 // mbarrier slots
+constexpr int kMaxStages = 32;
 enum : int {
   kBarInFull = 0,   // count 256: A_in of the step written (sample owners) and D2 of the previous step read (everybody)
   kBarD1Full = 1,   // [2] count 1 (commit): a layer-1 chunk landed in D1[b]
   kBarA1Full = 3,   // [2] count 128: the group wrote the hi/lo pieces of the chunk into A1[b] (and is done reading D1[b])
-  kBarA1Free = 5,   // [2] count 1 (commit): layer 2 consumed A1[b]
+  kBarA1Free = 5,   // [2] count 1 (commit): layer 2 consumed the chunk in A1[b] — and the ring stages of its K-steps
+                    //     (one commit per chunk serves the epilogue group AND the ring producer: every tcgen05.commit
+                    //     costs the tensor pipe ~140 cycles, measured with one commit per K-step)
   kBarD2Full = 7,   // count 1 (commit): layer 2 complete
-  kBarWFull = 8,    // [kMaxStages] count 1 + tx bytes: a W2 K-chunk landed in ring stage s
-  kBarWFree = 16,   // [kMaxStages] count 1 (commit): layer 2 consumed ring stage s
-  kNumBars = 24
+  kBarWFull = 8,    // [4] count 1 + tx bytes: the K-steps of one K-chunk of W2 landed in the ring (chunk counter % 4; at
+                    //     most three chunks are ever in flight).  The ring itself is handed out one K = 8 step at a time
+                    //     (hi slab + lo slab, 16 KB at H2 = 256), so that ~2.75 chunks can be on their way instead of one.
+  kNumBars = 12
 };
-constexpr int kMaxStages = 8;
-constexpr int kThreads = 352;
+constexpr int kCtrlBytes = ((kNumBars * 8 + 16) + 127) & ~127;
+constexpr int kThreads = 384;
 
 // tensor-memory columns (512 allocated: one CTA per SM)
 constexpr uint32_t kColD2 = 0, kColD1 = 256, kColA1 = 320, kColAin = 448, kColOnes = 480;
@@ -121,7 +129,7 @@ constexpr uint32_t kColD2 = 0, kColD1 = 256, kColA1 = 320, kColAin = 448, kColOn
 // shared-memory layout behind the image
 __host__ __device__ inline int smem_u_off(int image_bytes) { return (image_bytes + 127) & ~127; }
 __host__ __device__ inline int smem_ctrl_off(int image_bytes, int T) { return smem_u_off(image_bytes) + (((int)sizeof(float) * T * kMaxNu + 15) & ~15); }
-__host__ __device__ inline int smem_dx_off(int image_bytes, int T) { return smem_ctrl_off(image_bytes, T) + 256; }
+__host__ __device__ inline int smem_dx_off(int image_bytes, int T) { return smem_ctrl_off(image_bytes, T) + kCtrlBytes; }
 __host__ __device__ inline int smem_ring_off(int image_bytes, int T) { return (smem_dx_off(image_bytes, T) + 128 * 8 * (int)sizeof(float) + 127) & ~127; }
 
 }  // namespace tc
@@ -144,6 +152,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
   float* dx_x = reinterpret_cast<float*>(smem + smem_dx_off(a.image_bytes, T));
   unsigned char* ring = smem + smem_ring_off(a.image_bytes, T);
   auto bar = [&](int i) { return smem_u32(bars + i); };
+  const bool prof_cta = a.tc_prof != nullptr && blockIdx.x == 0;
+#define TC_STAMP(cond, slot) do { if (prof_cta && (cond)) a.tc_prof[slot] = clock64(); } while (0)
 
   // ---- prologue: image, nominal sequence, barriers, tensor memory
   grid_dep_launch();
@@ -157,13 +167,10 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(kBarD1Full + b), 1);
       mbar_init(bar(kBarA1Full + b), 128);
-      mbar_init(bar(kBarA1Free + b), 1);
+      mbar_init(bar(kBarA1Free + b), D.n_issuers);
     }
-    mbar_init(bar(kBarD2Full), 1);
-    for (int s = 0; s < kMaxStages; ++s) {
-      mbar_init(bar(kBarWFull + s), 1);
-      mbar_init(bar(kBarWFree + s), 1);
-    }
+    mbar_init(bar(kBarD2Full), D.n_issuers);
+    for (int s = 0; s < 4; ++s) mbar_init(bar(kBarWFull + s), 1);
     *abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
     const bool live = kbase + row < a.K_local;
     const int k = live ? kbase + row : a.K_local - 1;
     const float slope = (float)a.slope;
-    const float* w3 = reinterpret_cast<const float*>(smem + D.off_w3);  // [h2][8]
+    const float* w3 = reinterpret_cast<const float*>(smem + D.off_w3);  // [h2][2 * ceil(nx/2)]: output pairs of every k
     const float* b3 = reinterpret_cast<const float*>(smem + D.off_b3);
     float x[NX], u[NU];
 #pragma unroll
@@ -207,20 +214,28 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
     // another role aborted; a step is always walked to its two named barriers, and the second one is a reduction that
     // hands every thread the same stop decision.
     auto wait_all = [&](int b, uint32_t parity) { return __all_sync(0xffffffffu, mbar_wait(bar(b), parity, abort_flag) ? 1 : 0) != 0; };
+    // The recurrence x_{t+1} = f(x_t, u_t) is the only thing that must sit between two steps' tensor work, so the sample
+    // owners keep everything else off that path: the action of step t+1 is drawn while layer 2 of step t runs, and the
+    // running cost of the state reached by step t is evaluated after the input row of step t+1 is on its way.
+    float u_next[NU], u_prev[NU], pert_next = 0.f;
+    if (grp == 0) {
+      float npost[NU];
+      pert_next = sample_action<float, NU>(a.src, sp, Ush, k, 0, u_next, npost);
+    }
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
       bool bad = false;
+      const bool st0 = t == 2 && tid == 0, st1 = t == 2 && tid == 128;
+      TC_STAMP(st0, 0);
       if (grp == 0) {
-        float npost[NU];
-        pert += sample_action<float, NU>(a.src, sp, Ush + t * kMaxNu, k, t, u, npost);
-        if (a.has_guard) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) u[i] = u_next[i];
+        if (a.has_guard) {  // online_controller.py:62-66: the networks (and the cost of this step) see zeros
           float n2 = 0.f;
 #pragma unroll
           for (int i = 0; i < NX; ++i) n2 = __fmaf_rn(x[i], x[i], n2);
           bad = n2 > bad2;
           if (bad) {
-#pragma unroll
-            for (int i = 0; i < NX; ++i) x[i] = 0.f;
 #pragma unroll
             for (int i = 0; i < NU; ++i) u[i] = 0.f;
           }
@@ -236,7 +251,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
             for (int i = 0; i < NX; ++i) v = f == i ? x[i] : v;
 #pragma unroll
             for (int i = 0; i < NU; ++i) v = f == NX + i ? u[i] : v;
-            hi[j] = __float_as_uint(v) & 0xffffe000u;
+            v = bad ? 0.f : v;
+            hi[j] = split_hi(v);
             lo[j] = __float_as_uint(v - __uint_as_float(hi[j]));
           }
           TC_ST8(tb + kColAin + 8 * ks + lane_off, hi);
@@ -245,11 +261,31 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
         wait_st();
         fence_before();
         mbar_arrive(bar(kBarInFull));
+        TC_STAMP(st0, 1);
+        pert += pert_next;
       }
+      // the running cost of the state reached by the previous step: evaluated in the gap after this group's first chunk
+      // (measured: done here, before the chunk, it delayed layer 2 of every step by ~1300 cycles)
+      bool cost_pending = grp == 0;
+      auto deferred_cost = [&]() {
+        if (t > 0) {  // x is the state reached by step t-1 (zero if that step was guarded); its action is u_prev
+          cost += (double)running_cost<float, float, NX, NU>(cs, x, u_prev);
+          if (a.states_out != nullptr && live) {
+            double* so = a.states_out + ((size_t)k * T + (t - 1)) * NX;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) so[i] = (double)x[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i) u_prev[i] = u[i];
+        cost_pending = false;
+      };
       // ---- layer-1 chunks of this group: D1[grp] -> LeakyReLU -> hi/lo -> A1[grp]
       for (int c = grp; c < n_chunks && alive; c += 2) {
         alive = wait_all(kBarD1Full + grp, n_d1 & 1);
         if (!alive) break;
+        TC_STAMP(st0 && c == 0, 2);
+        TC_STAMP(st1 && c == 1, 48);
         fence_after();
         uint32_t v[NC];
         TC_LD16(v, tb + kColD1 + 32 * grp + lane_off);
@@ -264,7 +300,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
         for (int j = 0; j < NC; ++j) {
           float f = __uint_as_float(v[j]);
           f = fmaxf(f, slope * f);
-          const uint32_t h = __float_as_uint(f) & 0xffffe000u;
+          const uint32_t h = split_hi(f);
           lo[j] = __float_as_uint(f - __uint_as_float(h));
           v[j] = h;
         }
@@ -276,14 +312,30 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
         wait_st();
         fence_before();
         mbar_arrive(bar(kBarA1Full + grp));
+        TC_STAMP(st0 && c == 0, 3);
+        TC_STAMP(st1 && c == 1, 49);
         ++n_d1;
+        if (cost_pending) deferred_cost();
       }
+      if (cost_pending) deferred_cost();
+      TC_STAMP(st0, 4);
+      if (grp == 0 && t + 1 < T) {  // the next step's perturbed action, while layer 2 runs
+        float npost[NU];
+        pert_next = sample_action<float, NU>(a.src, sp, Ush + (t + 1) * kMaxNu, k, t + 1, u_next, npost);
+      }
+      TC_STAMP(st0, 5);
       // ---- D2 -> LeakyReLU -> layer 3 on the CUDA cores; the two groups take alternate NC-column chunks
       if (alive) alive = wait_all(kBarD2Full, n_d2 & 1);
       ++n_d2;
-      float dx[8];
+      TC_STAMP(st0, 6);
+      TC_STAMP(st1, 50);
+      // layer 3 with packed FFMA2: outputs paired in 64-bit accumulators; W3 lies in shared memory as [k][NXP] float pairs, so
+      // two consecutive k are NXP broadcast LDS.128 (the shared-memory pipe, one wavefront per LDS, was half of this phase
+      // with one LDS.128 pair per k)
+      constexpr int NXP = (NX + 1) / 2;
+      uint64_t dxp[NXP];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dx[i] = grp == 0 ? b3[i] : 0.f;
+      for (int i = 0; i < NXP; ++i) dxp[i] = grp == 0 ? pack2(b3[2 * i], b3[2 * i + 1]) : pack2(0.f, 0.f);
       if (alive) {
         fence_after();
         for (int c = grp; c < h2 / NC; c += 2) {
@@ -291,26 +343,31 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
           TC_LD16(v, tb + kColD2 + NC * c + lane_off);
           if (NC == 32) TC_LD16((v + 16), tb + kColD2 + NC * c + 16 + lane_off);
           wait_ld();
-          const float4* wrow = reinterpret_cast<const float4*>(w3 + (size_t)c * NC * 8);
+          const ulonglong2* wrow = reinterpret_cast<const ulonglong2*>(w3 + (size_t)c * NC * 2 * NXP);
 #pragma unroll
-          for (int j = 0; j < NC; ++j) {
-            float f = __uint_as_float(v[j]);
-            f = fmaxf(f, slope * f);
-            const float4 wa = wrow[2 * j];
-            dx[0] = __fmaf_rn(f, wa.x, dx[0]);
-            dx[1] = __fmaf_rn(f, wa.y, dx[1]);
-            dx[2] = __fmaf_rn(f, wa.z, dx[2]);
-            dx[3] = __fmaf_rn(f, wa.w, dx[3]);
-            if (NX > 4) {
-              const float4 wb = wrow[2 * j + 1];
-              dx[4] = __fmaf_rn(f, wb.x, dx[4]);
-              if (NX > 5) dx[5] = __fmaf_rn(f, wb.y, dx[5]);
-              if (NX > 6) dx[6] = __fmaf_rn(f, wb.z, dx[6]);
-              if (NX > 7) dx[7] = __fmaf_rn(f, wb.w, dx[7]);
+          for (int j = 0; j < NC; j += 2) {
+            float f0 = __uint_as_float(v[j]), f1 = __uint_as_float(v[j + 1]);
+            f0 = fmaxf(f0, slope * f0);
+            f1 = fmaxf(f1, slope * f1);
+            const uint64_t ff[2] = {pack2(f0, f0), pack2(f1, f1)};
+            ulonglong2 q[NXP];
+#pragma unroll
+            for (int i = 0; i < NXP; ++i) q[i] = wrow[(j / 2) * NXP + i];
+#pragma unroll
+            for (int p = 0; p < 2 * NXP; ++p) {  // pair p: output pair p % NXP of element j + p / NXP
+              const uint64_t w = (p & 1) ? q[p / 2].y : q[p / 2].x;
+              dxp[p % NXP] = ffma2(ff[p / NXP], w, dxp[p % NXP]);
             }
           }
         }
       }
+      float dx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dx[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NXP; ++i) unpack2(dxp[i], dx[2 * i], dx[2 * i + 1]);
+      TC_STAMP(st0, 7);
+      TC_STAMP(st1, 51);
       if (grp == 1) {
         fence_before();
         mbar_arrive(bar(kBarInFull));  // this thread is done with D2: layer 2 of the next step may overwrite it
@@ -319,6 +376,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
         p[1] = make_float4(dx[4], dx[5], dx[6], dx[7]);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      TC_STAMP(st0, 8);
       if (grp == 0) {
         const float4* p = reinterpret_cast<const float4*>(dx_x + row * 8);
         const float4 pa = p[0], pb = p[1];
@@ -327,20 +385,23 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
         for (int i = 0; i < NX; ++i) {
           float xn = x[i] + (dx[i] + other[i]);
           if ((a.wrap_mask >> i) & 1u) xn = angle_normalize<float>(xn);
-          x[i] = bad ? 0.f : xn;
-        }
-        cost += (double)running_cost<float, float, NX, NU>(cs, x, u);
-        if (a.states_out != nullptr && live) {
-          double* so = a.states_out + ((size_t)k * T + t) * NX;
-#pragma unroll
-          for (int i = 0; i < NX; ++i) so[i] = (double)x[i];
+          x[i] = bad ? 0.f : xn;  // next_state[bad] = state[bad] (= 0), online_controller.py:77
         }
       }
+      TC_STAMP(st0, 9);
       // the exchange rows are free again before anybody writes the next step's; the barrier also reduces the stop decision
       uint32_t stop;
       const uint32_t mine = alive ? 0u : 1u;
       asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, 2, 256, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(stop) : "r"(mine) : "memory");
       if (stop) break;
+    }
+    if (grp == 0) {  // the running cost of the last step's state
+      cost += (double)running_cost<float, float, NX, NU>(cs, x, u_prev);
+      if (a.states_out != nullptr && live && T > 0) {
+        double* so = a.states_out + ((size_t)k * T + (T - 1)) * NX;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) so[i] = (double)x[i];
+      }
     }
     if (grp == 0 && live) {
       double total = cost + (double)terminal_cost<float, float, NX>(cs, x) + (double)pert;
@@ -357,6 +418,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
       bool alive = true;
       for (int t = 0; t < T && alive; ++t) {
         if (!(alive = mbar_wait(bar(kBarInFull), t & 1, abort_flag))) break;
+        TC_STAMP(t == 2, 32);
         fence_after();
         for (int c = 0; c < n_chunks; ++c) {
           const int b = c & 1;
@@ -374,45 +436,57 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
             mma_ts(d1, ahi, bhi, idesc, 1);
           }
           commit(bar(kBarD1Full + b));
+          TC_STAMP(t == 2 && c < 8, 33 + c);
           ++use[b];
         }
       }
     }
-  } else if (warp == 9) {
-    // =================================================================== layer-2 issuer
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc((uint32_t)h2);
+  } else if (warp == 9 || warp == 11) {
+    // =================================================================== layer-2 issuer(s)
+    // With two issuers each takes one half of the output columns (its own half of D2, of the bias slab and of every
+    // weight slab): two threads feed the tensor pipe in parallel (tools/peaks/tcgen05_issue.cu).
+    const int qi = warp == 9 ? 0 : 1;
+    if (qi < D.n_issuers && elect_one()) {
+      const uint32_t n_mine = (uint32_t)(h2 / D.n_issuers);
+      const uint32_t idesc = make_idesc(n_mine);
       const uint32_t slab2 = (uint32_t)(h2 / 8) * 256;
+      const uint32_t half_off = (uint32_t)qi * (n_mine / 8) * 256;   // this issuer's rows inside a slab
+      const uint32_t d2 = tb + kColD2 + (uint32_t)qi * n_mine;
       const uint32_t ring_u = smem_u32(ring);
+      const uint32_t stages = (uint32_t)D.stages;
       uint32_t use[2] = {0, 0};
-      uint32_t g = 0;  // K-chunks consumed so far
+      uint32_t g = 0, gc = 0;  // K = 8 steps / K-chunks consumed so far
       bool alive = true;
       for (int t = 0; t < T && alive; ++t) {
         if (!(alive = mbar_wait(bar(kBarInFull), t & 1, abort_flag))) break;
+        TC_STAMP(t == 2 && qi == 0, 16);
         fence_after();
-        mma_ts(tb + kColD2, tb + kColOnes, make_desc(smem_u32(smem + D.off_b2)), idesc, 0);  // D2 = bias
-        for (int c = 0; c < n_chunks; ++c, ++g) {
+        for (int c = 0; c < n_chunks && alive; ++c, ++gc) {
           const int b = c & 1;
-          const int s = D.resident ? c : (int)(g % (uint32_t)D.stages);
           if (!D.resident || t == 0) {
-            if (!(alive = mbar_wait(bar(kBarWFull + s), D.resident ? 0u : (g / (uint32_t)D.stages) & 1u, abort_flag))) break;
+            if (!(alive = mbar_wait(bar(kBarWFull + (D.resident ? 0 : (gc & 3))), D.resident ? 0u : (gc >> 2) & 1u, abort_flag))) break;
           }
           if (!(alive = mbar_wait(bar(kBarA1Full + b), use[b] & 1, abort_flag))) break;
           fence_after();
-          const uint32_t wbase = ring_u + (uint32_t)s * (uint32_t)D.w2_chunk_bytes;
+          // D2 = bias (through the ones column) right in front of the first chunk: issued at the top of the step it would
+          // sit in the tensor pipe ahead of layer 1's first chunk, which everything else of the step waits for
+          if (c == 0) mma_ts(d2, tb + kColOnes, make_desc(smem_u32(smem + D.off_b2) + half_off), idesc, 0);
           const uint32_t a1 = tb + kColA1 + 64 * b;
 #pragma unroll
-          for (int ks = 0; ks < NC / 8; ++ks) {
-            const uint64_t bhi = make_desc(wbase + ks * slab2), blo = make_desc(wbase + (NC / 8 + ks) * slab2);
-            mma_ts(tb + kColD2, a1 + NC + 8 * ks, bhi, idesc, 1);
-            mma_ts(tb + kColD2, a1 + 8 * ks, blo, idesc, 1);
-            mma_ts(tb + kColD2, a1 + 8 * ks, bhi, idesc, 1);
+          for (int ks = 0; ks < NC / 8; ++ks, ++g) {
+            const uint32_t s = D.resident ? (uint32_t)(c * (NC / 8) + ks) : g % stages;
+            const uint32_t wbase = ring_u + s * 2 * slab2 + half_off;
+            const uint64_t bhi = make_desc(wbase), blo = make_desc(wbase + slab2);
+            mma_ts(d2, a1 + NC + 8 * ks, bhi, idesc, 1);
+            mma_ts(d2, a1 + 8 * ks, blo, idesc, 1);
+            mma_ts(d2, a1 + 8 * ks, bhi, idesc, 1);
           }
           commit(bar(kBarA1Free + b));
-          if (!D.resident) commit(bar(kBarWFree + s));
+          TC_STAMP(t == 2 && qi == 0 && c < 8, 17 + c);
           ++use[b];
         }
         if (alive) commit(bar(kBarD2Full));
+        TC_STAMP(t == 2 && qi == 0, 26);
       }
     }
   } else {
@@ -420,21 +494,32 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
     if (elect_one()) {
       const unsigned char* w2 = reinterpret_cast<const unsigned char*>(a.tc_w2);
       const uint32_t ring_u = smem_u32(ring);
-      const uint32_t bytes = (uint32_t)D.w2_chunk_bytes;
+      const uint32_t bytes = (uint32_t)D.w2_stage_bytes;  // one K = 8 step: hi slab + lo slab
+      const uint32_t n_ksteps = (uint32_t)(D.h1 / 8), stages = (uint32_t)D.stages;
+      const uint32_t per_chunk = NC / 8;
       if (D.resident) {
-        for (int c = 0; c < n_chunks; ++c) {
-          mbar_expect_tx(bar(kBarWFull + c), bytes);
-          tma_load(ring_u + (uint32_t)c * bytes, w2 + (size_t)c * bytes, bytes, bar(kBarWFull + c));
-        }
+        mbar_expect_tx(bar(kBarWFull), bytes * n_ksteps);
+        for (uint32_t q = 0; q < n_ksteps; ++q) tma_load(ring_u + q * bytes, w2 + (size_t)q * bytes, bytes, bar(kBarWFull));
       } else {
-        uint32_t g = 0;
+        // circular ring of one-K-step stages; stages come back a chunk at a time (kBarA1Free)
+        uint32_t g = 0, gc = 0, freed = 0, use[2] = {0, 0};
+        int cc = 0;  // next chunk (within its step) whose completion has not been observed yet
         bool alive = true;
         for (int t = 0; t < T && alive; ++t)
-          for (int c = 0; c < n_chunks; ++c, ++g) {
-            const uint32_t s = g % (uint32_t)D.stages;
-            if (g >= (uint32_t)D.stages && !(alive = mbar_wait(bar(kBarWFree + s), (g / (uint32_t)D.stages - 1) & 1u, abort_flag))) break;
-            mbar_expect_tx(bar(kBarWFull + s), bytes);
-            tma_load(ring_u + s * bytes, w2 + (size_t)c * bytes, bytes, bar(kBarWFull + s));
+          for (int c = 0; c < n_chunks && alive; ++c, ++gc) {
+            const uint32_t full = bar(kBarWFull + (gc & 3));
+            for (uint32_t ks = 0; ks < per_chunk; ++ks, ++g) {
+              while (g >= freed + stages) {
+                const int b = cc & 1;
+                if (!(alive = mbar_wait(bar(kBarA1Free + b), use[b] & 1, abort_flag))) break;
+                ++use[b];
+                freed += per_chunk;
+                if (++cc == n_chunks) cc = 0;
+              }
+              if (!alive) break;
+              if (ks == 0) mbar_expect_tx(full, bytes * per_chunk);
+              tma_load(ring_u + (g % stages) * bytes, w2 + (size_t)(c * per_chunk + ks) * bytes, bytes, full);
+            }
           }
       }
     }
@@ -448,24 +533,24 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
 template <int NX, int NU>
 cudaError_t launch_tc_mlp(const RolloutArgs& a, int /*block*/, cudaStream_t stream) {
   const int T = a.src.T;
-  const size_t smem = (size_t)tc::smem_ring_off(a.image_bytes, T) + (size_t)a.tc.stages * a.tc.w2_chunk_bytes;
-  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  const size_t smem = (size_t)tc::smem_ring_off(a.image_bytes, T) + (size_t)a.tc.stages * a.tc.w2_stage_bytes;
+  if (smem > 226 * 1024) return cudaErrorInvalidConfiguration;  // (the kernel also has a little static shared memory)
   const int grid = (a.K_local + 127) / 128;
   cudaError_t e;
   if (a.tc.nc == 32) {
     auto kern = tc_mlp_rollout_kernel<NX, NU, 32>;
     static size_t configured = 0;
     if (smem > configured) {
-      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-      configured = 227 * 1024;
+      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return e;
+      configured = 226 * 1024;
     }
     kern<<<grid, tc::kThreads, smem, stream>>>(a);
   } else {
     auto kern = tc_mlp_rollout_kernel<NX, NU, 16>;
     static size_t configured = 0;
     if (smem > configured) {
-      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
-      configured = 227 * 1024;
+      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)) != cudaSuccess) return e;
+      configured = 226 * 1024;
     }
     kern<<<grid, tc::kThreads, smem, stream>>>(a);
   }

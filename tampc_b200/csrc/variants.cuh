@@ -86,7 +86,6 @@ const ModelVariant* variant_rex_peg();    // nx5 nu2, enc 7-16-32-5, ...
 const ModelVariant* variant_mlp_5_3_32(); // 8-32-32-5
 const ModelVariant* variant_mlp_5_3_64(); // 8-64-64-5
 const ModelVariant* variant_mlp_5_3_128(); // 8-128-128-5 (tensor-core kernels only)
-const ModelVariant* variant_mlp_5_3_256(); // 8-256-256-5 (streamed-weight 3xTF32 kernel only)
 const ModelVariant* variant_pendulum();
 // plain MLP (nx+nu) -> H1 -> H2 -> nx of any widths (multiples of 16, <= 256), nx <= 8, nu <= 4: tcgen05 kernel (tc_rollout.cuh)
 rollout_launch_fn tc_mlp_launcher(int nx, int nu);

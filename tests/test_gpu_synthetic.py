@@ -1,6 +1,7 @@
 """GPU: the synthetic sweep of BASELINE.json configs[3] (random-init MLP, hidden width 32 / 64 / 128 / 256, horizon
-10-100) against the CPU oracle on injected noise.  Width 256 runs on the streamed-weight 3xTF32 kernel only; other
-widths and precisions without a kernel must be refused loudly."""
+10-100) against the CPU oracle on injected noise.  In 3xTF32 the widths 128 and 256 run on the tcgen05 kernel
+(tc_rollout.cuh, also tests/test_gpu_tc.py), 32 and 64 on the register-chained mma.sync kernels; widths and precisions
+without a kernel must be refused loudly."""
 import numpy as np
 import pytest
 import torch
@@ -32,6 +33,21 @@ def test_synthetic_mlp_matches_oracle(cuda_lib, H, K, T, precision):
     m.close()
 
 
+def test_width_128_on_the_warp_level_kernel_too(cuda_lib, monkeypatch):
+    """TAMPC_TC=0 keeps the mma.sync 3xTF32 kernel of width 128 reachable (the default there is tcgen05)."""
+    from tampc_b200.mppi import B200MPPI
+    monkeypatch.setenv('TAMPC_TC', '0')
+    spec, x0 = make_synthetic_spec(H=128, K=1500, T=20, seed=11)
+    noise = O.sample_noise(spec, 5)
+    U0 = torch.zeros(20, 3, dtype=torch.double)
+    want = O.command(spec, torch.from_numpy(x0), U0, noise)
+    m = B200MPPI(spec, precision='tf32x3', U_init=U0)
+    assert 'HMMA' in m.kernel_name
+    m.command(x0, noise=noise.numpy())
+    assert float(((m.cost_total - want['cost_total']).abs() / want['cost_total'].abs()).max()) < 1e-5
+    m.close()
+
+
 @pytest.mark.parametrize('precision', ['mixed', 'f32'])
 def test_fma_modes_cover_widths_32_and_64(cuda_lib, precision):
     from tampc_b200.mppi import B200MPPI
@@ -48,25 +64,27 @@ def test_fma_modes_cover_widths_32_and_64(cuda_lib, precision):
 
 
 @pytest.mark.parametrize('K,T', [(2048, 40), (1000, 10), (130, 100)])
-def test_width_256_streamed_weights_matches_oracle(cuda_lib, K, T):
-    """8 -> 256 -> 256 -> 5 (mma_stream.cuh): the 256 x 256 layer is streamed from L2 piece by piece and fused with the
-    output layer; ragged K (not a multiple of the 128 samples of a CTA, idle warps and rows)."""
+def test_width_256_matches_oracle(cuda_lib, K, T):
+    """8 -> 256 -> 256 -> 5 on the tcgen05 kernel (tc_rollout.cuh; W2 streamed by TMA): ragged K, and the 1e-5 gate also at
+    a horizon of 100 steps (tests/test_gpu_tc.py covers the other widths)."""
     from tampc_b200.mppi import B200MPPI
     spec, x0 = make_synthetic_spec(H=256, K=K, T=T, seed=256 + T)
     noise = O.sample_noise(spec, 5)
     U0 = torch.zeros(T, 3, dtype=torch.double)
     want = O.command(spec, torch.from_numpy(x0), U0, noise)
     m = B200MPPI(spec, precision='tf32x3', U_init=U0, max_horizon=T)
+    assert 'tcgen05' in m.kernel_name
     a = m.command(x0, noise=noise.numpy())
     cost = m.cost_total
     rel = float(((cost - want['cost_total']).abs() / want['cost_total'].abs()).max())
-    # 1e-5 is the gate at the task horizons (T <= 40); a float32 state carried through 100 steps of a 256-wide network
-    # measures 2.3e-5 (the narrower widths stay below 1e-5 at T = 100)
-    assert rel < (1e-5 if T <= 40 else 5e-5), rel
+    assert rel < 1e-5, rel
     s = torch.sort(want['cost_total']).values
-    if float(s[1] - s[0]) > 1e-4 * float(s[0].abs()):
+    gap = float(s[1] - s[0]) / float(s[0].abs())
+    if gap > 1e-4:
         assert int(cost.argmin()) == want['argmin']
         assert float((a - want['action']).abs().max()) < 1e-4
+    else:
+        print('argmin / action assert skipped: top-2 cost gap', gap)
     # get_rollouts / predict go through the same kernel with one live sample
     roll = m.get_rollouts(x0)[0]
     ref = O.get_rollouts(spec, torch.from_numpy(x0), m.U)
