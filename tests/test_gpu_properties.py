@@ -44,9 +44,12 @@ def test_oracle_parity_at_benchmark_sizes(cuda_lib, case, K, precision):
     assert rel < RTOL[precision]
     # identical argmin is meaningful when the two best samples are further apart than the numeric error
     s = torch.sort(want['cost_total']).values
-    if float(s[1] - s[0]) > 10 * RTOL[precision] * float(s[0].abs()):
+    gap = float(s[1] - s[0]) / float(s[0].abs())
+    if gap > 10 * RTOL[precision]:
         assert int(cost.argmin()) == want['argmin'] == m.stats['argmin']
         assert float((a - want['action']).abs().max()) < 1e-4
+    else:
+        print('argmin / action assert skipped: top-2 cost gap', gap, case, K, precision)
     m.close()
 
 
@@ -268,9 +271,13 @@ def test_ragged_and_maximum_sizes(cuda_lib, precision, K, T, P):
     # the 1e-5 gate is for the task horizons; 128 steps of float32 state drift further (f64 stays at 1e-9)
     assert rel < (RTOL[precision] if T <= 40 or precision == 'f64' else 1e-4), rel
     s = torch.sort(want['cost_total']).values
-    if K == 1 or float(s[1] - s[0]) > 1e-3 * float(s[0].abs()):
+    gap = 1.0 if K == 1 else float(s[1] - s[0]) / float(s[0].abs())
+    print('K', K, 'T', T, 'P', P, precision, 'cost rel', rel, 'top-2 cost gap', gap)
+    if gap > 1e-3:
         assert m.stats['argmin'] == want['argmin']
         assert float((a - want['action']).abs().max()) < 1e-4
+    else:
+        print('argmin / action assert skipped: top-2 cost gap', gap)
     m.close()
 
 

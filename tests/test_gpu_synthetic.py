@@ -27,9 +27,12 @@ def test_synthetic_mlp_matches_oracle(cuda_lib, H, K, T, precision):
     rel = float(((cost - want['cost_total']).abs() / want['cost_total'].abs()).max())
     assert rel < (1e-9 if precision == 'f64' else 1e-5), rel
     s = torch.sort(want['cost_total']).values
-    if float(s[1] - s[0]) > 1e-4 * float(s[0].abs()):
+    gap = float(s[1] - s[0]) / float(s[0].abs())
+    if gap > 1e-4:
         assert int(cost.argmin()) == want['argmin']
         assert float((a - want['action']).abs().max()) < 1e-4
+    else:
+        print('argmin / action assert skipped: top-2 cost gap', gap, H, K, T, precision)
     m.close()
 
 
