@@ -1288,6 +1288,7 @@ static int install_model(tampc_mppi* h, const tampc_model_desc* desc, const doub
     const int avail = 226 * 1024 - ring_off;
     int stages = avail / d.w2_stage_bytes;
     if (stages > tc::kMaxStages) stages = tc::kMaxStages;
+    if (stages > (tc::kWFullBars - 1) * (d.nc / 8) && stages < d.h1 / 8) stages = (tc::kWFullBars - 1) * (d.nc / 8);  // chunks in flight < barriers
     if (stages >= d.h1 / 8) { stages = d.h1 / 8; d.resident = 1; }
     if (stages < 2 * (d.nc / 8) && !d.resident) { h->err = "tcgen05 MLP kernel: shared memory cannot hold two K-chunks of layer 2"; return TAMPC_ERR_UNSUPPORTED; }
     d.stages = stages;

@@ -115,11 +115,13 @@ enum : int {
                     //     (one commit per chunk serves the epilogue group AND the ring producer: every tcgen05.commit
                     //     costs the tensor pipe ~140 cycles, measured with one commit per K-step)
   kBarD2Full = 7,   // count 1 (commit): layer 2 complete
-  kBarWFull = 8,    // [4] count 1 + tx bytes: the K-steps of one K-chunk of W2 landed in the ring (chunk counter % 4; at
-                    //     most three chunks are ever in flight).  The ring itself is handed out one K = 8 step at a time
-                    //     (hi slab + lo slab, 16 KB at H2 = 256), so that ~2.75 chunks can be on their way instead of one.
-  kNumBars = 12
+  kBarWFull = 8,    // [8] count 1 + tx bytes: the K-steps of one K-chunk of W2 landed in the ring (chunk counter % 8; the host
+                    //     caps the ring at 7 chunks, so a barrier is never re-armed before its previous phase was consumed).
+                    //     The ring itself is handed out one K = 8 step at a time (hi slab + lo slab, 16 KB at H2 = 256), so
+                    //     that ~2.75 chunks can be on their way at H2 = 256 instead of one.
+  kNumBars = 16
 };
+constexpr int kWFullBars = 8;
 constexpr int kCtrlBytes = ((kNumBars * 8 + 16) + 127) & ~127;
 constexpr int kThreads = 384;
 
@@ -130,7 +132,8 @@ constexpr uint32_t kColD2 = 0, kColD1 = 256, kColA1 = 320, kColAin = 448, kColOn
 __host__ __device__ inline int smem_u_off(int image_bytes) { return (image_bytes + 127) & ~127; }
 __host__ __device__ inline int smem_ctrl_off(int image_bytes, int T) { return smem_u_off(image_bytes) + (((int)sizeof(float) * T * kMaxNu + 15) & ~15); }
 __host__ __device__ inline int smem_dx_off(int image_bytes, int T) { return smem_ctrl_off(image_bytes, T) + kCtrlBytes; }
-__host__ __device__ inline int smem_ring_off(int image_bytes, int T) { return (smem_dx_off(image_bytes, T) + 128 * 8 * (int)sizeof(float) + 127) & ~127; }
+__host__ __device__ inline int smem_xs_off(int image_bytes, int T) { return smem_dx_off(image_bytes, T) + 128 * 8 * (int)sizeof(float); }
+__host__ __device__ inline int smem_ring_off(int image_bytes, int T) { return (smem_xs_off(image_bytes, T) + 128 * 12 * (int)sizeof(float) + 127) & ~127; }
 
 }  // namespace tc
 
@@ -149,7 +152,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
   unsigned char* ctrl = smem + smem_ctrl_off(a.image_bytes, T);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(ctrl);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(ctrl + kNumBars * 8);
-  float* dx_x = reinterpret_cast<float*>(smem + smem_dx_off(a.image_bytes, T));
+  float* dx_x = reinterpret_cast<float*>(smem + smem_dx_off(a.image_bytes, T));  // [128][8] group 1 -> owners: partial dx
+  float* xs_x = reinterpret_cast<float*>(smem + smem_xs_off(a.image_bytes, T));  // [128][12] owners -> group 1: state reached, action seen
   unsigned char* ring = smem + smem_ring_off(a.image_bytes, T);
   auto bar = [&](int i) { return smem_u32(bars + i); };
   const bool prof_cta = a.tc_prof != nullptr && blockIdx.x == 0;
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
       mbar_init(bar(kBarA1Free + b), D.n_issuers);
     }
     mbar_init(bar(kBarD2Full), D.n_issuers);
-    for (int s = 0; s < 4; ++s) mbar_init(bar(kBarWFull + s), 1);
+    for (int s = 0; s < kWFullBars; ++s) mbar_init(bar(kBarWFull + s), 1);
     *abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
     // The recurrence x_{t+1} = f(x_t, u_t) is the only thing that must sit between two steps' tensor work, so the sample
     // owners keep everything else off that path: the action of step t+1 is drawn while layer 2 of step t runs, and the
     // running cost of the state reached by step t is evaluated after the input row of step t+1 is on its way.
-    float u_next[NU], u_prev[NU], pert_next = 0.f;
+    float u_next[NU], pert_next = 0.f;
     if (grp == 0) {
       float npost[NU];
       pert_next = sample_action<float, NU>(a.src, sp, Ush, k, 0, u_next, npost);
@@ -264,22 +268,23 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
         TC_STAMP(st0, 1);
         pert += pert_next;
       }
-      // the running cost of the state reached by the previous step: evaluated in the gap after this group's first chunk
-      // (measured: done here, before the chunk, it delayed layer 2 of every step by ~1300 cycles)
-      bool cost_pending = grp == 0;
-      auto deferred_cost = [&]() {
-        if (t > 0) {  // x is the state reached by step t-1 (zero if that step was guarded); its action is u_prev
-          cost += (double)running_cost<float, float, NX, NU>(cs, x, u_prev);
-          if (a.states_out != nullptr && live) {
-            double* so = a.states_out + ((size_t)k * T + (t - 1)) * NX;
+      // The running cost of the state reached by the previous step is group 1's job (it neither samples nor updates): the
+      // owners publish (x_{t}, action seen by step t-1) in shared memory at the end of a step, group 1 evaluates the cost at
+      // the top of the next one.  (Measured: on the owners it delayed their own layer-1 chunks, i.e. layer 2.)
+      if (grp == 1 && t > 0) {
+        const float* r = xs_x + row * 12;
+        float xr[NX], ur[NU];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) so[i] = (double)x[i];
-          }
+        for (int i = 0; i < NX; ++i) xr[i] = r[i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) ur[i] = r[8 + i];
+        cost += (double)running_cost<float, float, NX, NU>(cs, xr, ur);
+        if (a.states_out != nullptr && live) {
+          double* so = a.states_out + ((size_t)k * T + (t - 1)) * NX;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) so[i] = (double)xr[i];
         }
-#pragma unroll
-        for (int i = 0; i < NU; ++i) u_prev[i] = u[i];
-        cost_pending = false;
-      };
+      }
       // ---- layer-1 chunks of this group: D1[grp] -> LeakyReLU -> hi/lo -> A1[grp]
       for (int c = grp; c < n_chunks && alive; c += 2) {
         alive = wait_all(kBarD1Full + grp, n_d1 & 1);
@@ -315,9 +320,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
         TC_STAMP(st0 && c == 0, 3);
         TC_STAMP(st1 && c == 1, 49);
         ++n_d1;
-        if (cost_pending) deferred_cost();
       }
-      if (cost_pending) deferred_cost();
       TC_STAMP(st0, 4);
       if (grp == 0 && t + 1 < T) {  // the next step's perturbed action, while layer 2 runs
         float npost[NU];
@@ -387,6 +390,11 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
           if ((a.wrap_mask >> i) & 1u) xn = angle_normalize<float>(xn);
           x[i] = bad ? 0.f : xn;  // next_state[bad] = state[bad] (= 0), online_controller.py:77
         }
+        float* r = xs_x + row * 12;  // for the cost of this step (group 1, next iteration)
+#pragma unroll
+        for (int i = 0; i < NX; ++i) r[i] = x[i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) r[8 + i] = u[i];
       }
       TC_STAMP(st0, 9);
       // the exchange rows are free again before anybody writes the next step's; the barrier also reduces the stop decision
@@ -395,16 +403,27 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
       asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, 2, 256, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(stop) : "r"(mine) : "memory");
       if (stop) break;
     }
-    if (grp == 0) {  // the running cost of the last step's state
-      cost += (double)running_cost<float, float, NX, NU>(cs, x, u_prev);
-      if (a.states_out != nullptr && live && T > 0) {
-        double* so = a.states_out + ((size_t)k * T + (T - 1)) * NX;
+    // the running cost of the last step's state (group 1), then the total through the exchange rows
+    if (grp == 1) {
+      if (T > 0) {
+        const float* r = xs_x + row * 12;
+        float xr[NX], ur[NU];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) so[i] = (double)x[i];
+        for (int i = 0; i < NX; ++i) xr[i] = r[i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) ur[i] = r[8 + i];
+        cost += (double)running_cost<float, float, NX, NU>(cs, xr, ur);
+        if (a.states_out != nullptr && live) {
+          double* so = a.states_out + ((size_t)k * T + (T - 1)) * NX;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) so[i] = (double)xr[i];
+        }
       }
+      *reinterpret_cast<double*>(dx_x + row * 8) = cost;
     }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (grp == 0 && live) {
-      double total = cost + (double)terminal_cost<float, float, NX>(cs, x) + (double)pert;
+      double total = *reinterpret_cast<const double*>(dx_x + row * 8) + (double)terminal_cost<float, float, NX>(cs, x) + (double)pert;
       if (*abort_flag) total = __longlong_as_double(0x7ff8000000000000ll);
       a.cost_out[k] = total;
     }
@@ -464,7 +483,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
         for (int c = 0; c < n_chunks && alive; ++c, ++gc) {
           const int b = c & 1;
           if (!D.resident || t == 0) {
-            if (!(alive = mbar_wait(bar(kBarWFull + (D.resident ? 0 : (gc & 3))), D.resident ? 0u : (gc >> 2) & 1u, abort_flag))) break;
+            if (!(alive = mbar_wait(bar(kBarWFull + (D.resident ? 0 : (gc & 7))), D.resident ? 0u : (gc >> 3) & 1u, abort_flag))) break;
           }
           if (!(alive = mbar_wait(bar(kBarA1Full + b), use[b] & 1, abort_flag))) break;
           fence_after();
@@ -507,7 +526,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) tc_mlp_rollout_kernel(const R
         bool alive = true;
         for (int t = 0; t < T && alive; ++t)
           for (int c = 0; c < n_chunks && alive; ++c, ++gc) {
-            const uint32_t full = bar(kBarWFull + (gc & 3));
+            const uint32_t full = bar(kBarWFull + (gc & 7));
             for (uint32_t ks = 0; ks < per_chunk; ++ks, ++g) {
               while (g >= freed + stages) {
                 const int b = cc & 1;
