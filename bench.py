@@ -45,7 +45,7 @@ F16_MMA_PEAK_TFLOPS = 556.0  # tools/peaks/mma_peaks mma.sync m16n8k16 f16
 TCGEN05_TF32_PEAK_TFLOPS = 982.7  # tools/peaks/tcgen05_probe (profiles/tcgen05_probe_r2.jsonl): tcgen05.mma kind::tf32, M=128, N=256, A in TMEM
 # DRAM traffic of one rollout launch at K=8192 from the committed ncu capture (the kernel reads its ~45 KB image and
 # the nominal sequence, writes 8*K bytes of costs that stay in L2): compute-bound by four orders of magnitude
-NCU_DRAM_BYTES_PER_LAUNCH = {'tf32x3': 75776, 'f16x3': 70912}
+NCU_DRAM_BYTES_PER_LAUNCH = {'tf32x3': 91648, 'f16x3': 70912}
 
 
 # The driver's line is the default workload (BASELINE.json configs[1]).  The others exist to put the remaining configs
@@ -536,7 +536,7 @@ def main():
                         "frac_tcgen05_tf32x3": achieved / (TCGEN05_TF32_PEAK_TFLOPS / 3.0) if TCGEN05_TF32_PEAK_TFLOPS else None,
                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.precision) if args.workload == 'push' else None,
                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this size, one "
-                                          "ncu --set full capture (profiles/r1h_rollout_split3_tf32x3_k8192_ncu_summary.txt; f16x3: r1e_rollout_split_f16x3_k8192_ncu_summary.txt)",
+                                          "ncu --set full capture (profiles/r2z_split3_k8192_ncu_summary.txt; f16x3: r1e_rollout_split_f16x3_k8192_ncu_summary.txt)",
                         "kernel": "rollout (fused K x T): " + kernel_name,
                         "kernel_ms": roll_ms, "algorithmic_flop_per_launch": K * T * flop_per_step,
                         "peak_source": src,
