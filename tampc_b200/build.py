@@ -16,7 +16,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 BUILD = os.path.join(CSRC, 'build')
 LIB = os.path.join(CSRC, 'libtampc_mppi.so')
 
-SOURCES = ['mppi_api.cu', 'gp_fit.cu', 'variant_tc.cu', 'variant_rex_push.cu', 'variant_rex_peg.cu', 'variant_mlp.cu', 'variant_mlp64.cu', 'variant_mlp128.cu', 'variant_gp.cu']
+SOURCES = ['mppi_api.cu', 'gp_fit.cu', 'variant_tc.cu', 'variant_generic.cu', 'variant_rex_push.cu', 'variant_rex_peg.cu', 'variant_mlp.cu', 'variant_mlp64.cu', 'variant_mlp128.cu', 'variant_gp.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
 

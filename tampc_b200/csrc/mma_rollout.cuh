@@ -559,6 +559,31 @@ __global__ void __launch_bounds__(512, 1) rollout_mma_mix_kernel(const RolloutAr
   else rollout_mma_warp<Model, ST, CT, 2, false>(a, smem_raw, wbase, kbase, lane, wi, wn);
 }
 
+// Several balanced waves (K > one wave of the wide kernel; 3xTF32 / 3xFP16): one CTA of sixteen warps per SM, every warp
+// walks the list of two-tile units (32 samples) with a stride of all warps.  The list is dealt SLOT-major — unit
+// u of a pass goes to slot u / (4 SMs) of sub-partition u % (4 SMs) — so the units of the last, partial pass spread
+// evenly over the sub-partitions instead of filling whole CTAs: a launch lasts ceil(units / (4 SMs)) unit times instead
+// of 4 ceil(units / (16 SMs)).  K = 131 072 per GPU (the K = 1M problem sharded over 8 GPUs): 7 instead of 8 units per
+// sub-partition; K = 262 144: 14 instead of 16; K = 1M: 56 either way.
+template <class Model, typename ST, typename CT>
+__global__ void __launch_bounds__(512, 1) rollout_mma_persist_kernel(const RolloutArgs a) {
+  static_assert(sizeof(typename Model::T) == 4, "16-row policies");
+  constexpr int SW = 2 * PolicyTF32x3::MT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using L = MmaSmem<Model, ST, CT>;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  rollout_mma_stage<Model, ST, CT>(a, smem_raw, tid, 512);
+  unsigned char* wbase = smem_raw + L::stage_off(a.src.T) + (size_t)warp * L::warp_bytes(a.src.T, SW, false);
+  const int q = warp & 3, j = warp >> 2;  // sub-partition, slot on it
+  const int lanes = gridDim.x * 4, stride = lanes * 4;
+  const int units = (a.K_local + SW - 1) / SW;
+#pragma unroll 1
+  for (int u = j * lanes + blockIdx.x * 4 + q; u < units; u += stride) {
+    rollout_mma_warp<Model, ST, CT, 2, false>(a, smem_raw, wbase, u * SW, lane, 0, 0);
+    __syncwarp();  // the warp's staging rows are reused by its next unit
+  }
+}
+
 // ---- two-warp pipelined variant for small K (latency-bound) ----------------------------------------------
 // One CTA = one m-tile of 16 samples and two warps:
 //   warp 0 ("dynamics")  guard -> network chain -> state update -> wrap, and publishes x_{t+1} into a small ring;
@@ -1069,6 +1094,27 @@ cudaError_t launch_rollout_mma_mix(const RolloutArgs& a, int /*block*/, cudaStre
   }
   constexpr int per_block = 4 * 7 * PolicyTF32x3::MT;
   kern<<<(a.K_local + per_block - 1) / per_block, 512, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <class Model, typename ST, typename CT>
+cudaError_t launch_rollout_mma_persist(const RolloutArgs& a, int /*block*/, cudaStream_t stream) {
+  auto kern = rollout_mma_persist_kernel<Model, ST, CT>;
+  if (a.fuse) return cudaErrorInvalidValue;
+  const size_t smem = MmaSmem<Model, ST, CT>::bytes(a.src.T, 16, 2 * PolicyTF32x3::MT, false);
+  static size_t configured = 0;
+  static int n_sm = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  if (n_sm == 0) {
+    int dev = 0;
+    n_sm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  kern<<<n_sm, 512, smem, stream>>>(a);
   return cudaGetLastError();
 }
 

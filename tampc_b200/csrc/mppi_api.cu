@@ -16,6 +16,7 @@
 #include "reduce_kernels.cuh"
 #include "variants.cuh"
 #include "tc_rollout.cuh"
+#include "generic_rollout.cuh"
 
 using namespace tampc;
 
@@ -88,6 +89,10 @@ struct tampc_mppi {
   int n_weight_elems = 0;
   bool use_mma = false;  // the staged weights are in the mma-path layout
   bool use_tc = false;   // tcgen05 plain-MLP kernel (tc_rollout.cuh): image in its slab layout, W2 streamed from d_tc_w2
+  bool use_generic = false;  // runtime-shaped networks (generic_rollout.cuh): FMA layout read from global memory
+  GenDims gen{};
+  rollout_launch_fn gen_fn = nullptr;
+  const char* gen_name = "";
   TcMlpDims tc_dims{};
   rollout_launch_fn tc_fn = nullptr;
   void* d_tc_w2 = nullptr;
@@ -334,6 +339,9 @@ struct PackedModel {
   std::vector<unsigned char> tc_image, tc_w2;
   TcMlpDims tc_dims{};
   rollout_launch_fn tc_fn = nullptr;
+  // runtime-shaped networks (generic_rollout.cuh): f32 / f64 above hold the FMA-layout blobs, these their layer tables
+  bool generic = false;
+  GenDims gen_f32{}, gen_f64{};
 };
 
 // ---- tcgen05 layout (tc_rollout.cuh): K-major no-swizzle slabs.  One slab = rows [n0, n0 + N) x one K = 8 step:
@@ -404,6 +412,45 @@ bool tc_mlp_wanted(const tampc_mppi* h, const std::vector<HostLayer>& net, int n
   return (h1 >= 128 || h2 >= 128) && h->cfg.num_local >= env_int("TAMPC_TC_MIN_K", 1);
 }
 
+// placeholder variants of the runtime-shaped kernel (generic_rollout.cuh)
+const ModelVariant* variant_generic(int kind) {
+  static const ModelVariant mlp = [] { ModelVariant m{}; m.name = "mlp_generic"; m.kind = TAMPC_DYN_MLP; return m; }();
+  static const ModelVariant rex = [] { ModelVariant m{}; m.name = "rex_generic"; m.kind = TAMPC_DYN_REX; return m; }();
+  return kind == TAMPC_DYN_REX ? &rex : &mlp;
+}
+
+template <typename NT>
+void pack_gen_net(std::vector<NT>& blob, const std::vector<HostLayer>& m, GenNet& g) {
+  g.n = (int)m.size();
+  g.dims[0] = m[0].in;
+  for (size_t l = 0; l < m.size(); ++l) {
+    g.off[l] = (int)blob.size();
+    g.dims[l + 1] = m[l].out;
+    pack_layer<NT>(blob, m[l]);
+  }
+}
+
+bool gen_widths_ok(const std::vector<HostLayer>& m) {
+  for (const HostLayer& L : m)
+    if (L.in > kGenMaxWidth || L.out > kGenMaxWidth) return false;
+  return true;
+}
+
+// TAMPC_GENERIC=1: the runtime-shaped kernel even where a tuned one exists (tests compare the two bit for bit)
+bool generic_forced() { return env_int("TAMPC_GENERIC", 0) != 0; }
+
+// does the tuned variant have a kernel for the handle's precision?  (if not, the runtime-shaped kernel takes the model;
+// a GP residual needs the variant's own (sample, replica) kernels, so there the variant stays and install_model decides)
+bool variant_serves(const tampc_mppi* h, const ModelVariant* v) {
+  if (h->gp_on) return true;
+  switch (h->cfg.precision) {
+    case TAMPC_PREC_F64: return v->bytes_mma_f64 != 0 || v->f64_s1 != nullptr;
+    case TAMPC_PREC_TF32X3: return v->bytes_mma_tf32 != 0;
+    case TAMPC_PREC_F16X3: return v->bytes_mma_f16 != 0;
+    default: return v->f64_s1 != nullptr;
+  }
+}
+
 int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t n, PackedModel& out) {
   const int nx = d.nx, nu = d.nu;
   if (nx != h->cfg.nx || nu != h->cfg.nu) { h->err = "model nx/nu differ from the handle's"; return TAMPC_ERR_INVALID; }
@@ -423,8 +470,8 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
     std::vector<HostLayer> net;
     int rc = read_mlp(h, d.net, p, n, net);
     if (rc) return rc;
-    if (net.size() != 3 || net[0].in != nx + nu || net[2].out != nx) {
-      h->err = "MLP dynamics must be (nx+nu) -> h1 -> h2 -> nx";
+    if (net[0].in != nx + nu || net.back().out != nx) {
+      h->err = "MLP dynamics must map (nx+nu) -> ... -> nx";
       return TAMPC_ERR_UNSUPPORTED;
     }
     std::vector<double> s, o;
@@ -436,21 +483,30 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
     {  // dx = (y - o)/s
       std::vector<double> si(nx), oi(nx);
       for (int i = 0; i < nx; ++i) { si[i] = 1.0 / s[i]; oi[i] = -o[i] / s[i]; }
-      fold_output_affine(net[2], si, oi);
+      fold_output_affine(net.back(), si, oi);
     }
     for (const ModelVariant* v : all) {
-      if (v->kind == TAMPC_DYN_MLP && v->nx == nx && v->nu == nu && net[0].out == v->dims[0] && net[1].out == v->dims[1]) out.variant = v;
+      if (net.size() == 3 && v->kind == TAMPC_DYN_MLP && v->nx == nx && v->nu == nu && net[0].out == v->dims[0] && net[1].out == v->dims[1]) out.variant = v;
     }
-    if (tc_mlp_wanted(h, net, nx, nu, out.variant != nullptr)) {
+    if (out.variant && (generic_forced() || !variant_serves(h, out.variant))) out.variant = nullptr;
+    if (!generic_forced() && tc_mlp_wanted(h, net, nx, nu, out.variant != nullptr)) {
       pack_tc_mlp(net, nx, nu, out);
       out.variant = variant_tc_generic();
       return TAMPC_OK;
     }
     if (!out.variant) {
-      snprintf(buf, sizeof buf, "no compiled kernel for MLP dynamics nx=%d nu=%d hidden=%d,%d in this precision (the tcgen05 kernel of "
-               "precision tf32x3 takes any hidden widths that are multiples of 16 up to 256)", nx, nu, net[0].out, net[1].out);
-      h->err = buf;
-      return TAMPC_ERR_UNSUPPORTED;
+      // any other depth / widths / precision: the runtime-shaped kernel
+      if (!gen_widths_ok(net)) {
+        snprintf(buf, sizeof buf, "MLP dynamics with a layer wider than %d", kGenMaxWidth);
+        h->err = buf;
+        return TAMPC_ERR_UNSUPPORTED;
+      }
+      out.generic = true;
+      out.gen_f32.kind = out.gen_f64.kind = TAMPC_DYN_MLP;
+      pack_gen_net<float>(out.f32, net, out.gen_f32.net);
+      pack_gen_net<double>(out.f64, net, out.gen_f64.net);
+      out.variant = variant_generic(TAMPC_DYN_MLP);
+      return TAMPC_OK;
     }
     if (out.variant->f64_s1) {  // shapes with FMA-path kernels
       pack_mlp<float>(out.f32, net);
@@ -466,16 +522,15 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
   int rc;
   if ((rc = read_mlp(h, d.encoder, p, n, enc)) || (rc = read_mlp(h, d.net, p, n, dyn)) || (rc = read_mlp(h, d.decoder, p, n, dec))) return rc;
   const int nv = d.nv, ne = d.ne;
-  if (enc.size() != 3 || dyn.size() != 3 || dec.size() != 3 || enc[0].in != nx + nu || dyn[0].in != enc[2].out || dyn[2].out != nv ||
-      dec[0].in != ne || dec[2].out != nx * nv) {
-    h->err = "REX dynamics must be three 3-layer MLPs: (nx+nu)->..->nz, nz->..->nv, ne->..->nx*nv";
+  if (enc[0].in != nx + nu || dyn[0].in != enc.back().out || dyn.back().out != nv || dec[0].in != ne || dec.back().out != nx * nv) {
+    h->err = "REX dynamics must be three MLPs: (nx+nu)->..->nz, nz->..->nv, ne->..->nx*nv";
     return TAMPC_ERR_UNSUPPORTED;
   }
-  const int nz = enc[2].out;
+  const int nz = enc.back().out;
   std::vector<double> s, o;
   // z' = z*s + o  after the encoder
   if ((rc = read_affine(h, d.aff_in, p, n, nz, s, o))) return rc;
-  fold_output_affine(enc[2], s, o);
+  fold_output_affine(enc.back(), s, o);
   // v = (v' - o)/s after the latent dynamics
   if ((rc = read_affine(h, d.aff_out, p, n, nv, s, o))) return rc;
   if (nv > kMaxNx) { h->err = "latent output wider than TAMPC_MAX_NX"; return TAMPC_ERR_UNSUPPORTED; }
@@ -483,7 +538,7 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
   {
     std::vector<double> si(nv), oi(nv);
     for (int i = 0; i < nv; ++i) { si[i] = 1.0 / s[i]; oi[i] = -o[i] / s[i]; }
-    fold_output_affine(dyn[2], si, oi);
+    fold_output_affine(dyn.back(), si, oi);
   }
   // e = Wx x + bx feeds the decoder's first Linear with no activation in between: compose them
   if (d.ext_w_off < 0 || d.ext_b_off < 0 || (size_t)d.ext_w_off + (size_t)ne * nx > n || (size_t)d.ext_b_off + ne > n) {
@@ -516,18 +571,46 @@ int pack_model(tampc_mppi* h, const tampc_model_desc& d, const double* p, size_t
       d0[i] = -o[i] / s[i];
       for (int j = 0; j < nv; ++j) si[(size_t)i * nv + j] = 1.0 / s[i];
     }
-    fold_output_affine(dec[2], si, oi);
+    fold_output_affine(dec.back(), si, oi);
   }
   for (const ModelVariant* v : all) {
-    if (v->kind == TAMPC_DYN_REX && v->nx == nx && v->nu == nu && enc[0].out == v->dims[0] && enc[1].out == v->dims[1] && nz == v->dims[2] &&
-        dyn[0].out == v->dims[3] && dyn[1].out == v->dims[4] && nv == v->dims[5] && dec[0].out == v->dims[6] && dec[1].out == v->dims[7])
+    if (enc.size() == 3 && dyn.size() == 3 && dec.size() == 3 && v->kind == TAMPC_DYN_REX && v->nx == nx && v->nu == nu && enc[0].out == v->dims[0] &&
+        enc[1].out == v->dims[1] && nz == v->dims[2] && dyn[0].out == v->dims[3] && dyn[1].out == v->dims[4] && nv == v->dims[5] &&
+        dec[0].out == v->dims[6] && dec[1].out == v->dims[7])
       out.variant = v;
   }
+  if (out.variant && (generic_forced() || !variant_serves(h, out.variant))) out.variant = nullptr;
   if (!out.variant) {
-    snprintf(buf, sizeof buf, "no compiled kernel for REX dynamics nx=%d nu=%d enc=%d,%d,%d dyn=%d,%d,%d dec=%d,%d", nx, nu, enc[0].out,
-             enc[1].out, nz, dyn[0].out, dyn[1].out, nv, dec[0].out, dec[1].out);
-    h->err = buf;
-    return TAMPC_ERR_UNSUPPORTED;
+    // other depths / widths: the runtime-shaped kernel
+    if (!gen_widths_ok(enc) || !gen_widths_ok(dyn) || !gen_widths_ok(dec)) {
+      snprintf(buf, sizeof buf, "REX dynamics with a layer wider than %d", kGenMaxWidth);
+      h->err = buf;
+      return TAMPC_ERR_UNSUPPORTED;
+    }
+    out.generic = true;
+    for (int dbl = 0; dbl < 2; ++dbl) {
+      GenDims& g = dbl ? out.gen_f64 : out.gen_f32;
+      g.kind = TAMPC_DYN_REX;
+      g.nv = nv;
+      if (dbl) {
+        pack_gen_net<double>(out.f64, enc, g.enc);
+        pack_gen_net<double>(out.f64, dyn, g.net);
+        pack_gen_net<double>(out.f64, dec, g.dec);
+        g.off_d0 = (int)out.f64.size();
+      } else {
+        pack_gen_net<float>(out.f32, enc, g.enc);
+        pack_gen_net<float>(out.f32, dyn, g.net);
+        pack_gen_net<float>(out.f32, dec, g.dec);
+        g.off_d0 = (int)out.f32.size();
+      }
+    }
+    const int d0g = (nx + 3) & ~3;
+    for (int i = 0; i < d0g; ++i) {
+      out.f32.push_back(i < nx ? (float)d0[i] : 0.f);
+      out.f64.push_back(i < nx ? d0[i] : 0.0);
+    }
+    out.variant = variant_generic(TAMPC_DYN_REX);
+    return TAMPC_OK;
   }
   pack_mlp<float>(out.f32, enc);
   pack_mlp<float>(out.f32, dyn);
@@ -579,6 +662,13 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
   LaunchPlan p;
   const int SM = h->n_sm;  // cudaDeviceProp::multiProcessorCount (148 on B200); the thresholds below are per SM
   const int eb = env_int("TAMPC_BLOCK", 0);
+  if (h->use_generic) {
+    p.fn = h->gen_fn;
+    p.name = h->gen_name;
+    p.block = K >= 2 * SM * 128 ? 128 : (K >= 2 * SM * 64 ? 64 : 32);
+    if (eb == 32 || eb == 64 || eb == 128) p.block = eb;
+    return p;
+  }
   if (h->use_tc) {
     p.fn = h->tc_fn;
     p.block = tc::kThreads;
@@ -633,6 +723,20 @@ LaunchPlan choose_launch(const tampc_mppi* h, int K) {
       p.fn = fsm;
       p.block = 32 * ((warps + SM - 1) / SM);
       return p;
+    }
+    // more than one wave of sixteen warps per SM: one persistent 16-warp CTA per SM that walks the 32-sample units
+    // slot-major, so that a partial last pass spreads over all sub-partitions.  Measured on B200 against the grid launches
+    // below (profiles/r2o_persist_*.jsonl, rollout kernel, T=40): push K=131 072 0.782 -> 0.723 ms, 262 144 1.527 -> 1.444,
+    // 1M 5.57 -> 5.59; synthetic H=32 K=131 072 0.462 -> 0.348 ms, 262 144 0.799 -> 0.690, 1M 2.63 -> 2.60.  TAMPC_PERSIST=0/1.
+    const rollout_launch_fn fpersist = f16 ? v->f16_mma_persist : v->tf32_mma_persist;
+    if (!f64 && idx == 1 && !big && fpersist && eb == 0 && warps > SM * 16) {
+      const int pe = env_int("TAMPC_PERSIST", -1);
+      if (pe != 0) {
+        p.fn = fpersist;
+        p.name = f16 ? "rollout_mma_persist_kernel 3xFP16 (HMMA m16n8k16)" : "rollout_mma_persist_kernel 3xTF32 (HMMA m16n8k8)";
+        p.block = 512;
+        return p;
+      }
     }
     if (!f64 && idx == 1 && !big && fwide && eb == 0) {
       const int wide_env = env_int("TAMPC_WIDE", -1);
@@ -765,6 +869,7 @@ int launch_rollout_for(tampc_mppi* h, int mode, int shift, const double* d_U, in
   a.image = h->d_weights;
   a.image_bytes = h->img_bytes;
   a.tc = h->tc_dims;
+  a.gen = h->gen;
   a.tc_w2 = h->d_tc_w2;
   a.tc_prof = h->d_tc_prof;
   a.slope = h->model.leaky_slope;
@@ -1329,6 +1434,54 @@ static int install_model(tampc_mppi* h, const tampc_model_desc* desc, const doub
     h->has_model = true;
     return prep_image(h);
   }
+  h->use_generic = false;
+  if (pm.generic) {
+    if (h->gp_on) { h->err = "the runtime-shaped kernel has no GP-residual form (GP residuals need one of the compiled network shapes)"; return TAMPC_ERR_UNSUPPORTED; }
+    // precision -> types: F64 = float64 everywhere; F32 = float32 everywhere; MIXED and the tensor precisions (which have no
+    // kernel for an arbitrary shape) = float32 networks, float64 state and cost sum
+    const int prec = h->cfg.precision;
+    const int types = prec == TAMPC_PREC_F64 ? 0 : (prec == TAMPC_PREC_F32 ? 2 : 1);
+    const rollout_launch_fn fn = generic_launcher(h->cfg.nx, h->cfg.nu, types);
+    if (!fn) { h->err = "internal: no runtime-shaped kernel for this nx / nu"; return TAMPC_ERR_UNSUPPORTED; }
+    const bool f64 = types == 0;
+    const void* src = f64 ? (const void*)pm.f64.data() : (const void*)pm.f32.data();
+    const size_t raw_bytes = f64 ? 8 * pm.f64.size() : 4 * pm.f32.size();
+    const size_t wbytes = (raw_bytes + 15) & ~size_t(15);
+    size_t cost_sz, samp_sz;
+    if (types == 0) { cost_sz = sizeof(CostS<double, double>); samp_sz = sizeof(SamplerS<double>); }
+    else if (types == 1) { cost_sz = sizeof(CostS<double, float>); samp_sz = sizeof(SamplerS<double>); }
+    else { cost_sz = sizeof(CostS<float, float>); samp_sz = sizeof(SamplerS<float>); }
+    const size_t cost_off = wbytes, samp_off = cost_off + ((cost_sz + 15) & ~size_t(15));
+    const size_t bytes = samp_off + ((samp_sz + 15) & ~size_t(15));
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (bytes > h->weights_bytes) {
+      cudaFree(h->d_weights);
+      h->d_weights = nullptr;
+      CUDA_TRY(h, cudaMalloc(&h->d_weights, bytes));
+      h->weights_bytes = bytes;
+    }
+    CUDA_TRY(h, cudaMemset(h->d_weights, 0, h->weights_bytes));
+    CUDA_TRY(h, cudaMemcpy(h->d_weights, src, raw_bytes, cudaMemcpyHostToDevice));
+    h->gen = f64 ? pm.gen_f64 : pm.gen_f32;
+    h->gen.off_cost = (int)cost_off;
+    h->gen_fn = fn;
+    h->gen_name = types == 0 ? "rollout_generic_kernel f64 (DFMA), run-time layer widths"
+                             : (types == 1 ? "rollout_generic_kernel f32 networks (FFMA), f64 state + cost sum, run-time layer widths"
+                                           : "rollout_generic_kernel f32 (FFMA), run-time layer widths");
+    h->use_generic = true;
+    h->use_mma = false;
+    h->img_f64 = f64;
+    h->n_weight_elems = (int)(wbytes / (f64 ? 8 : 4));
+    h->img_cost_off = (int)cost_off;
+    h->img_sampler_off = (int)samp_off;
+    h->img_sampler_d_off = -1;
+    h->img_bytes = (int)bytes;
+    h->variant = pm.variant;
+    h->model = *desc;
+    h->has_model = true;
+    return prep_image(h);
+  }
   // arithmetic -> layout:  F64 = DMMA layout (FMA layout if the shape has no mma kernel or TAMPC_F64_IMPL=fma),
   // TF32X3 = mma layout, MIXED / F32 = float32 FMA layout
   const int prec = h->cfg.precision;
@@ -1824,6 +1977,7 @@ TAMPC_API int tampc_mppi_get_rollouts(tampc_mppi* h, const double* state, double
   a.image = h->d_weights;
   a.image_bytes = h->img_bytes;
   a.tc = h->tc_dims;
+  a.gen = h->gen;
   a.tc_w2 = h->d_tc_w2;
   a.tc_prof = h->d_tc_prof;
   a.slope = h->model.leaky_slope;
@@ -1868,6 +2022,7 @@ static int predict_impl(tampc_mppi* h, const double* state, const double* action
   a.image = h->d_weights;
   a.image_bytes = h->img_bytes;
   a.tc = h->tc_dims;
+  a.gen = h->gen;
   a.tc_w2 = h->d_tc_w2;
   a.tc_prof = h->d_tc_prof;
   a.slope = h->model.leaky_slope;

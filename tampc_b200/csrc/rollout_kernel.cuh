@@ -27,6 +27,23 @@ struct TcMlpDims {
   int w1_chunk_bytes, w2_stage_bytes;
 };
 
+// runtime-shaped networks (generic_rollout.cuh): Sequential(Linear, LeakyReLU, ..., Linear) of n Linear layers
+// dims[0] -> ... -> dims[n]; off[l] = element offset of layer l's packed block (layer_elems layout) in the image
+constexpr int kGenMaxWidth = 256;
+struct GenNet {
+  int n;
+  int dims[TAMPC_MAX_LAYERS + 1];
+  int off[TAMPC_MAX_LAYERS];
+};
+struct GenDims {
+  int kind;      // TAMPC_DYN_MLP: `net` is (x,u) -> dx;  TAMPC_DYN_REX: enc (x,u) -> z, net z -> v, dec x -> C (nx*nv)
+  int nv;        // REX: latent output width
+  int off_d0;    // REX: element offset of d0 (nx values)
+  int off_cost;  // byte offset of CostS in the image (SamplerS and nothing else follow)
+  int stage_w;   // set by the launcher: the weights ([0, off_cost) of the image) are staged in shared memory
+  GenNet enc, net, dec;
+};
+
 struct RolloutArgs {
   const void* image;    // shared-memory image: packed networks | CostS | SamplerS in the kernel's types
   int image_bytes;
@@ -62,6 +79,8 @@ struct RolloutArgs {
   int M;
   double var_cost, var_discount;
   const double* gp_eps;
+  // runtime-shaped networks (generic_rollout.cuh)
+  GenDims gen;
   // tcgen05 plain-MLP kernel: W2 in K-chunk-major slab order in global memory (streamed by TMA), dims
   const void* tc_w2;
   TcMlpDims tc;

@@ -25,6 +25,7 @@ struct ModelVariant {
   rollout_launch_fn tf32_split3, f16_split3;  // three warps per tile (chain | decoder | cost): latency-bound K
   rollout_launch_fn tf32_mma_sm, f16_mma_sm;  // NM = 2, ONE CTA per SM of up to 16 warps: a single balanced wave (K just above 56k)
   rollout_launch_fn tf32_mma_mix, f16_mma_mix;  // one CTA per SM, seven tiles per sub-partition (56 832 < K <= 66 304)
+  rollout_launch_fn tf32_mma_persist, f16_mma_persist;  // one 16-warp CTA per SM walking the unit list slot-major (several balanced waves)
   rollout_launch_fn tf32_split;   // two warps per 16-sample tile, split by role (RexExtract shapes, latency-bound K)
   rollout_launch_fn tf32_pipe;    // two-warp pipelined 3xTF32 kernel for small K (16 samples per CTA)
 };
@@ -63,6 +64,7 @@ void add_mma(ModelVariant& v) {
   v.tf32_mma_wide = &launch_rollout_mma<MM32, float, float, 2, false, 256>;
   v.tf32_mma_sm = &launch_rollout_mma<MM32, float, float, 2, false, 512>;
   if constexpr (MM32::kBytes <= 100 * 1024) v.tf32_mma_mix = &launch_rollout_mma_mix<MM32, float, float>;
+  if constexpr (MM32::kBytes <= 100 * 1024) v.tf32_mma_persist = &launch_rollout_mma_persist<MM32, float, float>;
   v.tf32_pipe = &launch_rollout_mma_pipe<MM32>;
 }
 
@@ -79,6 +81,7 @@ void add_f16(ModelVariant& v) {
   v.f16_mma_wide = &launch_rollout_mma<MM16, float, float, 2, false, 256>;
   v.f16_mma_sm = &launch_rollout_mma<MM16, float, float, 2, false, 512>;
   if constexpr (MM16::kBytes <= 100 * 1024) v.f16_mma_mix = &launch_rollout_mma_mix<MM16, float, float>;
+  if constexpr (MM16::kBytes <= 100 * 1024) v.f16_mma_persist = &launch_rollout_mma_persist<MM16, float, float>;
 }
 
 const ModelVariant* variant_rex_push();   // nx5 nu3, enc 8-16-32-5, dyn 5-32-32-5, dec 5(2)-16-32-25

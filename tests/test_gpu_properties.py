@@ -202,9 +202,13 @@ def test_unsupported_shapes_and_bad_arguments_raise(cuda_lib):
     rng = np.random.RandomState(0)
     spec.dynamics.net = S.MLPSpec([rng.randn(24, 8), rng.randn(24, 24), rng.randn(5, 24)],
                                   [np.zeros(24), np.zeros(24), np.zeros(5)])
+    m = B200MPPI(spec, precision='tf32x3')  # widths without a compiled kernel: the run-time-shaped one (tests/test_gpu_generic.py)
+    assert 'generic' in m.kernel_name
+    m.close()
+    spec.dynamics.net = S.MLPSpec([rng.randn(300, 8), rng.randn(5, 300)], [np.zeros(300), np.zeros(5)])
     with pytest.raises(TampcError) as e:
         B200MPPI(spec, precision='tf32x3')
-    assert e.value.code == -2 and 'no compiled kernel' in str(e.value)
+    assert e.value.code == -2 and 'wider than 256' in str(e.value)
     z, spec = _spec('push_nominal', 256)
     m = B200MPPI(spec, precision='tf32x3', U_init=_U(z, spec))
     with pytest.raises(ValueError):
@@ -330,3 +334,20 @@ def test_opt_in_fused_update_matches_the_default_tail(cuda_lib, monkeypatch, pre
     assert st1['argmin'] == st0['argmin']
     assert float((a1 - a0).abs().max()) < 1e-6
     assert float((U_1 - U_0).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize('precision', ['tf32x3', 'f16x3'])
+def test_persistent_multiwave_kernel_same_bits(cuda_lib, monkeypatch, precision):
+    """K beyond one wave: the slot-major persistent launch (rollout_mma_persist_kernel) and the plain grid launch run the
+    same per-sample arithmetic — bitwise-identical costs, ragged last unit included."""
+    from tampc_b200.mppi import B200MPPI
+    z, spec = _spec('push_nominal', 32 * 148 * 16 * 2 + 32 * 148 * 5 + 21, T=4)  # 2 passes + a partial third, ragged last unit
+    costs = []
+    for persist in ('0', '1'):
+        monkeypatch.setenv('TAMPC_PERSIST', persist)
+        m = B200MPPI(spec, precision=precision, U_init=_U(z, spec), seed=3)
+        assert ('persist' in m.kernel_name) == (persist == '1'), m.kernel_name
+        m.command(z['in.state'])
+        costs.append(m.cost_total.clone())
+        m.close()
+    assert torch.equal(costs[0], costs[1])

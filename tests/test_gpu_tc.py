@@ -80,13 +80,19 @@ def test_default_choice_keeps_the_tuned_kernels_for_their_shapes(cuda_lib):
     m.close()
 
 
-def test_widths_outside_the_kernel_are_refused(cuda_lib):
+def test_widths_outside_the_kernel_go_elsewhere_or_are_refused(cuda_lib):
     from tampc_b200.mppi import B200MPPI, TampcError
-    for H1, H2 in [(40, 32), (272, 32), (32, 8)]:
+    for H1, H2 in [(40, 32), (32, 8)]:   # not multiples of 16: the run-time-shaped FMA kernel (tests/test_gpu_generic.py)
         spec, _ = make_synthetic_spec(H=H1, H2=H2, K=256, T=10)
-        with pytest.raises(TampcError) as e:
-            B200MPPI(spec, precision='tf32x3')
-        assert e.value.code == -2
+        m = B200MPPI(spec, precision='tf32x3')
+        assert 'generic' in m.kernel_name
+        m.close()
+    spec, _ = make_synthetic_spec(H=272, H2=32, K=256, T=10)
+    with pytest.raises(TampcError) as e:
+        B200MPPI(spec, precision='tf32x3')
+    assert e.value.code == -2
     spec, _ = make_synthetic_spec(H=48, K=256, T=10)
-    with pytest.raises(TampcError):
-        B200MPPI(spec, precision='f64')  # the shape-generic kernel is 3xTF32 only
+    m = B200MPPI(spec, precision='f64')  # the tcgen05 kernel is 3xTF32 only: float64 of the same widths is the generic kernel
+    assert 'generic' in m.kernel_name and 'f64' in m.kernel_name
+    m.close()
+
