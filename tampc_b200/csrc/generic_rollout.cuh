@@ -24,41 +24,37 @@ namespace tampc {
 // weights and arithmetic of the model's own Linear stacks
 template <typename NT>
 __device__ __forceinline__ void gen_linear(const NT* w, int IN, int OUT, const NT* __restrict__ in, NT* __restrict__ out, bool act, NT slope) {
-  constexpr int V = sizeof(NT) == 4 ? 4 : 2;  // elements per 16-byte load
+  constexpr int V = sizeof(NT) == 4 ? 4 : 2;   // elements per 16-byte load
+  constexpr int NV = sizeof(NT) == 4 ? 2 : 4;  // loads per block of outputs: eight independent accumulators either way
   using Vec = typename std::conditional<sizeof(NT) == 4, float4, double2>::type;
-  const int OP = pad_out<NT>(OUT);            // row length of the packed block (layer_elems): a multiple of V
+  const int OP = pad_out<NT>(OUT);             // row length of the packed block (layer_elems): a multiple of V
 #pragma unroll 1
-  for (int o0 = 0; o0 < OP; o0 += 2 * V) {
-    const bool two = o0 + V < OP;
-    NT acc[2 * V];
-    {
-      const Vec b0 = *reinterpret_cast<const Vec*>(w + o0);
-      const NT* p = reinterpret_cast<const NT*>(&b0);
+  for (int o0 = 0; o0 < OP; o0 += NV * V) {
+    const int nv = min(NV, (OP - o0) / V);     // vectors of this block inside the row (warp-uniform)
+    NT acc[NV * V];
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc[j] = p[j];
-      Vec b1 = b0;
-      if (two) b1 = *reinterpret_cast<const Vec*>(w + o0 + V);
-      const NT* q = reinterpret_cast<const NT*>(&b1);
+    for (int c = 0; c < NV; ++c) {
+      Vec b = *reinterpret_cast<const Vec*>(w + o0 + (c < nv ? c : 0) * V);
+      const NT* p = reinterpret_cast<const NT*>(&b);
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc[V + j] = two ? q[j] : (NT)0;
+      for (int j = 0; j < V; ++j) acc[c * V + j] = c < nv ? p[j] : (NT)0;
     }
     const NT* wr = w + (size_t)OP + o0;
 #pragma unroll 4
     for (int i = 0; i < IN; ++i, wr += OP) {
       const NT x = in[i];
-      const Vec w0 = *reinterpret_cast<const Vec*>(wr);
-      const NT* p = reinterpret_cast<const NT*>(&w0);
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc[j] = t_fma(x, p[j], acc[j]);
-      if (two) {
-        const Vec w1 = *reinterpret_cast<const Vec*>(wr + V);
-        const NT* q = reinterpret_cast<const NT*>(&w1);
+      for (int c = 0; c < NV; ++c) {
+        if (c < nv) {
+          const Vec wv = *reinterpret_cast<const Vec*>(wr + c * V);
+          const NT* p = reinterpret_cast<const NT*>(&wv);
 #pragma unroll
-        for (int j = 0; j < V; ++j) acc[V + j] = t_fma(x, q[j], acc[V + j]);
+          for (int j = 0; j < V; ++j) acc[c * V + j] = t_fma(x, p[j], acc[c * V + j]);
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 2 * V; ++j) {
+    for (int j = 0; j < NV * V; ++j) {
       if (o0 + j < OUT) {
         NT a = acc[j];
         if (act) a = t_max(a, slope * a);
