@@ -26,7 +26,8 @@ int main(int argc, char** argv) {
     unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_prof, z, sizeof z);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0);
     const bool split = argc > 4 && argv[4][0] == 's';
-    cudaError_t e = split ? launch_rollout_mma_split<Model, 2>(a, 128, 0) : (argc > 4 && argv[4][0] == 'p') ? launch_rollout_mma_pipe<Model>(a, 64, 0) : (argc > 4 ? (NM == 1 ? launch_rollout_mma<Model, float, float, 1, true>(a, block, 0) : launch_rollout_mma<Model, float, float, 2, false>(a, block, 0)) : (NM == 1 ? launch_rollout_mma<Model, double, float, 1, true>(a, block, 0) : launch_rollout_mma<Model, double, float, 2, false>(a, block, 0)));
+    const bool split3 = split && argv[4][1] == '3';
+    cudaError_t e = split3 ? launch_rollout_mma_split<Model, 3>(a, 192, 0) : split ? launch_rollout_mma_split<Model, 2>(a, 128, 0) : (argc > 4 && argv[4][0] == 'p') ? launch_rollout_mma_pipe<Model>(a, 64, 0) : (argc > 4 ? (NM == 1 ? launch_rollout_mma<Model, float, float, 1, true>(a, block, 0) : launch_rollout_mma<Model, float, float, 2, false>(a, block, 0)) : (NM == 1 ? launch_rollout_mma<Model, double, float, 1, true>(a, block, 0) : launch_rollout_mma<Model, double, float, 2, false>(a, block, 0)));
     cudaEventRecord(e1); cudaDeviceSynchronize(); float ms; cudaEventElapsedTime(&ms, e0, e1);
     unsigned long long g[16]; cudaMemcpyFromSymbol(g, g_prof, sizeof g);
     const char* names_1[] = {"sample_action", "guard", "stage_in", "enc", "dyn", "dec", "stage_out+dx", "wrap", "cost", "publish"};
