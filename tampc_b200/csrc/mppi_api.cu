@@ -361,24 +361,26 @@ void pack_tc_mlp(const std::vector<HostLayer>& net, int nx, int nu, PackedModel&
   TcMlpDims d{};
   d.nin = nx + nu;
   d.k0_steps = (d.nin + 7) / 8;
-  d.h1 = net[0].out;
-  d.h2 = net[1].out;
+  // hidden widths are padded to multiples of 16 with zero weights and biases: a padded unit is leaky(0) = 0 and feeds zeros
+  d.h1 = (net[0].out + 15) & ~15;
+  d.h2 = (net[1].out + 15) & ~15;
   d.nc = (d.h1 % 32 == 0 && d.h2 % 32 == 0) ? 32 : 16;
   d.n_chunks = d.h1 / d.nc;
   auto hi = [](double w) { return tf32_rna(w); };
   auto lo = [](double w) { return tf32_rna(w - (double)tf32_rna(w)); };
   auto W = [](const HostLayer& L, int o, int i) { return (o < L.out && i < L.in) ? L.W[(size_t)o * L.in + i] : 0.0; };
+  auto Bv = [](const HostLayer& L, int o) { return o < L.out ? L.b[o] : 0.0; };
   std::vector<unsigned char>& img = out.tc_image;
   d.off_w1 = 0;
   for (int c = 0; c < d.n_chunks; ++c) {
     const size_t before = img.size();
     for (int ks = 0; ks < d.k0_steps; ++ks) append_slab(img, c * d.nc, d.nc, [&](int n, int k) { return hi(W(net[0], n, ks * 8 + k)); });
     for (int ks = 0; ks < d.k0_steps; ++ks) append_slab(img, c * d.nc, d.nc, [&](int n, int k) { return lo(W(net[0], n, ks * 8 + k)); });
-    append_slab(img, c * d.nc, d.nc, [&](int n, int k) { return k == 0 ? hi(net[0].b[n]) : (k == 1 ? lo(net[0].b[n]) : 0.f); });
+    append_slab(img, c * d.nc, d.nc, [&](int n, int k) { return k == 0 ? hi(Bv(net[0], n)) : (k == 1 ? lo(Bv(net[0], n)) : 0.f); });
     d.w1_chunk_bytes = (int)(img.size() - before);
   }
   d.off_b2 = (int)img.size();
-  append_slab(img, 0, d.h2, [&](int n, int k) { return k == 0 ? hi(net[1].b[n]) : (k == 1 ? lo(net[1].b[n]) : 0.f); });
+  append_slab(img, 0, d.h2, [&](int n, int k) { return k == 0 ? hi(Bv(net[1], n)) : (k == 1 ? lo(Bv(net[1], n)) : 0.f); });
   d.off_w3 = (int)img.size();
   for (int k = 0; k < d.h2; ++k)  // [k][ceil(nx/2)] pairs of outputs (packed FFMA2 operands)
     for (int j = 0; j < 2 * ((nx + 1) / 2); ++j) append<float>(img, (float)W(net[2], j, k));
@@ -402,7 +404,7 @@ void pack_tc_mlp(const std::vector<HostLayer>& net, int nx, int nu, PackedModel&
 bool tc_mlp_wanted(const tampc_mppi* h, const std::vector<HostLayer>& net, int nx, int nu, bool has_tuned_variant) {
   if (h->cfg.precision != TAMPC_PREC_TF32X3 || net.size() != 3) return false;
   const int h1 = net[0].out, h2 = net[1].out;
-  if (h1 % 16 || h2 % 16 || h1 < 16 || h2 < 16 || h1 > 256 || h2 > 256 || nx > 8 || nu > kMaxNu || !tc_mlp_launcher(nx, nu)) return false;
+  if (h1 > 256 || h2 > 256 || nx > 8 || nu > kMaxNu || !tc_mlp_launcher(nx, nu)) return false;  // (widths are padded to multiples of 16)
   const int env = env_int("TAMPC_TC", -1);
   if (env == 0) return false;
   if (env == 1 || !has_tuned_variant) return true;

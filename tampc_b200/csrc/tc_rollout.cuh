@@ -1,5 +1,5 @@
 // tc_rollout.cuh — the Blackwell-native contraction path: fused K x T rollout for plain-MLP dynamics
-// (nx+nu) -> H1 -> H2 -> nx of ANY hidden widths (multiples of 16 up to 256) on tcgen05 tensor cores.
+// (nx+nu) -> H1 -> H2 -> nx of ANY hidden widths up to 256 (the host pads them to multiples of 16 with zero units) on tcgen05 tensor cores.
 //
 // Replaces, like the other rollout kernels, ExperimentalMPPI._compute_total_cost_batch + _compute_rollout_costs
 // (tampc/controller/controller.py:340-402) with OnlineMPC._apply_dynamics (online_controller.py:60-79), the network

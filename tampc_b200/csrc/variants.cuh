@@ -90,7 +90,7 @@ const ModelVariant* variant_mlp_5_3_32(); // 8-32-32-5
 const ModelVariant* variant_mlp_5_3_64(); // 8-64-64-5
 const ModelVariant* variant_mlp_5_3_128(); // 8-128-128-5 (tensor-core kernels only)
 const ModelVariant* variant_pendulum();
-// plain MLP (nx+nu) -> H1 -> H2 -> nx of any widths (multiples of 16, <= 256), nx <= 8, nu <= 4: tcgen05 kernel (tc_rollout.cuh)
+// plain MLP (nx+nu) -> H1 -> H2 -> nx of any widths <= 256 (padded to multiples of 16), nx <= 8, nu <= 4: tcgen05 kernel (tc_rollout.cuh)
 rollout_launch_fn tc_mlp_launcher(int nx, int nu);
 
 }  // namespace tampc

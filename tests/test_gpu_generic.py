@@ -56,8 +56,8 @@ def test_mlp_of_any_depth_and_width(cuda_lib, hidden, precision, tol):
     spec, x0 = make_synthetic_spec(H=32, K=700, T=15, seed=len(hidden) + hidden[0])
     rng = np.random.RandomState(hidden[0])
     spec.dynamics.net = _mlp(rng, [8] + list(hidden) + [5])
-    if precision == 'tf32x3' and len(hidden) == 2 and all(h % 16 == 0 for h in hidden):
-        pytest.skip('two hidden layers of multiples of 16 run on the tcgen05 kernel in tf32x3 (tests/test_gpu_tc.py)')
+    if precision == 'tf32x3' and len(hidden) == 2:
+        pytest.skip('two hidden layers run on the tcgen05 kernel in tf32x3, padded to multiples of 16 (tests/test_gpu_tc.py)')
     _check(spec, x0, precision, tol)
 
 

@@ -202,7 +202,10 @@ def test_unsupported_shapes_and_bad_arguments_raise(cuda_lib):
     rng = np.random.RandomState(0)
     spec.dynamics.net = S.MLPSpec([rng.randn(24, 8), rng.randn(24, 24), rng.randn(5, 24)],
                                   [np.zeros(24), np.zeros(24), np.zeros(5)])
-    m = B200MPPI(spec, precision='tf32x3')  # widths without a compiled kernel: the run-time-shaped one (tests/test_gpu_generic.py)
+    m = B200MPPI(spec, precision='tf32x3')  # widths without a tuned kernel: tcgen05 (padded to 16) here, the run-time-shaped kernel
+    assert 'tcgen05' in m.kernel_name       # for other depths and precisions (tests/test_gpu_tc.py, tests/test_gpu_generic.py)
+    m.close()
+    m = B200MPPI(spec, precision='f64')
     assert 'generic' in m.kernel_name
     m.close()
     spec.dynamics.net = S.MLPSpec([rng.randn(300, 8), rng.randn(5, 300)], [np.zeros(300), np.zeros(5)])

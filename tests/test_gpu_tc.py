@@ -82,10 +82,10 @@ def test_default_choice_keeps_the_tuned_kernels_for_their_shapes(cuda_lib):
 
 def test_widths_outside_the_kernel_go_elsewhere_or_are_refused(cuda_lib):
     from tampc_b200.mppi import B200MPPI, TampcError
-    for H1, H2 in [(40, 32), (32, 8)]:   # not multiples of 16: the run-time-shaped FMA kernel (tests/test_gpu_generic.py)
-        spec, _ = make_synthetic_spec(H=H1, H2=H2, K=256, T=10)
-        m = B200MPPI(spec, precision='tf32x3')
-        assert 'generic' in m.kernel_name
+    for H1, H2 in [(40, 32), (32, 8), (24, 100)]:   # not multiples of 16: padded with zero units, same kernel, same gates
+        spec, x0 = make_synthetic_spec(H=H1, H2=H2, K=700, T=20, seed=H1 + H2)
+        m, _ = _check(spec, x0, 700, 20, 3)
+        assert 'tcgen05' in m.kernel_name
         m.close()
     spec, _ = make_synthetic_spec(H=272, H2=32, K=256, T=10)
     with pytest.raises(TampcError) as e:
