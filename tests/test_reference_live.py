@@ -295,3 +295,44 @@ def test_real_reference_controller_drives_the_drop_in_through_its_own_constructo
     assert fake.cost_desc.kind == S.COST_GOAL_TRAP
     with torch.no_grad():
         np.testing.assert_allclose(cb.get_rollouts(obs), cr.get_rollouts(obs), rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize('enc_h,dyn_h,dec_h', [((24, 40), (48, 24), (20, 36)), ((64,), (32, 32, 16), (16,))])
+def test_networks_of_other_shapes_extract_and_match_the_live_reference(enc_h, dyn_h, dec_h):
+    """The reference builds its networks from `encoder_opts` / `decoder_opts` / `dynamics_opts` h_units
+    (invariant.py:745-785, util.py:560): swap the live controller's three networks for ones of other widths and depths made
+    by the same `make_sequential_network`, and the extraction + oracle still reproduce the reference's own command.  (On the
+    device such shapes run on the run-time-shaped kernel, held to this oracle by tests/test_gpu_generic.py.)"""
+    ref = rh.load_reference()  # (puts the shim of the un-vendored arm_pytorch_utilities on the path)
+    import arm_pytorch_utilities.model.make as make
+    torch.manual_seed(1)
+    ctrl, ds, env = rh.build_task('push', num_samples=80, rollout_samples=2, horizon=10)
+    ctrl.set_goal(np.array([0.55, -0.65, 0., 0., 0.]))
+    nm = ctrl.dynamics.nominal_model
+    inv = nm.ds.preprocessor.tsf.transforms[1].tsf
+
+    def net(n_in, n_out, h_units, out_scale):
+        cfg = ref.load_data.DataConfig()
+        cfg.nx, cfg.ny = n_in, n_out
+        m = make.make_sequential_network(cfg, h_units=h_units).double()
+        with torch.no_grad():
+            list(m.modules())[-1].weight.mul_(out_scale)  # keep the untrained rollout bounded
+        return m
+
+    nz, nv, ne = 5, int(inv.nv), inv.x_extractor.out_features
+    inv.encoder.model = net(8, nz, enc_h, 1.0)
+    inv.extracted_linear_decoder.model = net(ne, 5 * nv, dec_h, 0.2)
+    nm.model = nm.user.model = net(nz, nv, dyn_h, 1.0)  # (NetworkModelWrapper keeps the network under both names, model.py:212-213)
+    spec = extract.spec_from_controller(ctrl)
+    d = spec.dynamics
+    assert d.encoder.dims == [8] + list(enc_h) + [nz] and d.net.dims == [nz] + list(dyn_h) + [nv]
+    assert d.decoder.dims == [ne] + list(dec_h) + [5 * nv]
+    g = torch.Generator().manual_seed(5)
+    state = torch.randn(5, dtype=torch.double, generator=g) * 0.4
+    U0 = torch.rand(spec.sampler.T, 3, dtype=torch.double, generator=g) * 0.5
+    noise = O.sample_noise(spec, 9)
+    a_ref = _run_ref(ctrl, spec, state, U0, noise)
+    out = O.command(spec, state, U0, noise)
+    rel = ((out['cost_total'] - ctrl.mpc.cost_total).abs() / ctrl.mpc.cost_total.abs()).max().item()
+    assert rel < 1e-12 and out['argmin'] == int(ctrl.mpc.cost_total.argmin())
+    assert (out['action'] - a_ref).abs().max().item() < 1e-12
