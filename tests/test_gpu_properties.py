@@ -275,8 +275,9 @@ def test_ragged_and_maximum_sizes(cuda_lib, precision, K, T, P):
     cost = m.cost_total
     assert cost.shape == (K,)
     rel = float(((cost - want['cost_total']).abs() / want['cost_total'].abs()).max())
-    # the 1e-5 gate is for the task horizons; 128 steps of float32 state drift further (f64 stays at 1e-9)
-    assert rel < (RTOL[precision] if T <= 40 or precision == 'f64' else 1e-4), rel
+    # the 1e-5 gate is for the task horizons; over 128 steps the float32-class modes drift further (measured on B200: tf32x3
+    # 2.8e-5, mixed 1.2e-5, f16x3 8.9e-6; f64 5e-14) — DESIGN.md §4 records it as a known limit
+    assert rel < (RTOL[precision] if T <= 40 or precision == 'f64' else 3e-5), rel
     s = torch.sort(want['cost_total']).values
     gap = 1.0 if K == 1 else float(s[1] - s[0]) / float(s[0].abs())
     print('K', K, 'T', T, 'P', P, precision, 'cost rel', rel, 'top-2 cost gap', gap)
